@@ -1,0 +1,210 @@
+"""TEST INFRASTRUCTURE ONLY — pins the oracle against the UNMODIFIED reference and writes tests/golden/*.npz.
+
+Run in the authoring container (needs /root/reference):   python -m oracle.make_golden
+For every case it (1) builds the seeded fixture, (2) constructs the reference's own
+TensorVMSplit with the same seed and checks the parameters are identical, (3) runs the
+reference's renderer and the oracle restatement on the same inputs and asserts they are
+BIT-IDENTICAL, (4) stores the *reference's* outputs as the golden vectors.
+"""
+import contextlib
+import io
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import fixtures as fx
+from . import tensorf_oracle as orc
+from .ref_import import import_reference
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def build_reference_model(R, fld, seed=fx.SEED):
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = R.TensorVMSplit(fld.aabb.clone(), list(fld.grid), "cpu", density_n_comp=[16] * 3,
+                            appearance_n_comp=[48] * 3, app_dim=27, near_far=list(fld.near_far),
+                            shadingMode="MLP_Fea", alphaMask_thres=1e-4, density_shift=fld.density_shift,
+                            distance_scale=25, pos_pe=6, view_pe=2, fea_pe=2, featureC=128, step_ratio=0.5,
+                            fea2denseAct="softplus")
+    sd = m.state_dict()
+    mine = {}
+    for k in range(3):
+        mine[f"density_plane.{k}"] = fld.density_plane[k]
+        mine[f"density_line.{k}"] = fld.density_line[k]
+        mine[f"app_plane.{k}"] = fld.app_plane[k]
+        mine[f"app_line.{k}"] = fld.app_line[k]
+    mine["basis_mat.weight"] = fld.basis
+    for i, li in enumerate((0, 2, 4)):
+        mine[f"renderModule.mlp.{li}.weight"] = fld.mlp_w[i]
+        mine[f"renderModule.mlp.{li}.bias"] = fld.mlp_b[i]
+    assert set(sd.keys()) == set(mine.keys()), (sd.keys(), mine.keys())
+    for k, v in sd.items():
+        assert torch.equal(v, mine[k]), f"param {k} differs between reference ctor and oracle.init_field"
+    if fld.occupancy is not None:
+        m.alphaMask = R.AlphaGridMask("cpu", fld.occupancy.aabb.clone(), fld.occupancy.volume.clone())
+    geo = orc.step_geometry(fld.aabb, fld.grid, fld.step_ratio)
+    assert geo["nSamples"] == m.nSamples and torch.equal(geo["stepSize"], m.stepSize)
+    return m
+
+
+def reference_valid_mask(m, rays, n_samples=-1):
+    """ray_valid exactly as the reference computes it (tensorBase.py:820-837), via its own methods."""
+    with torch.no_grad():
+        xyz, z, valid = m.sample_ray(rays[:, :3], rays[:, 3:6], None, is_train=False, N_samples=n_samples)
+        if m.alphaMask is not None:
+            keep = m.alphaMask.sample_alpha(xyz[valid]) > 0
+            bad = ~valid
+            bad[valid] |= ~keep
+            valid = ~bad
+    return valid
+
+
+def eval_case(R, name, fld, rays, white_bg=True, bg_color=None, extra=None):
+    t = time.time()
+    m = build_reference_model(R, fld)
+    with torch.no_grad():
+        rgb, _, depth, _, _ = R.OctreeRender_trilinear_fast(rays, m, chunk=4096, N_samples=-1, white_bg=white_bg,
+                                                          bg_color=bg_color, ndc_ray=False, device="cpu")
+        full = m(rays[:4096], white_bg=white_bg, bg_color=bg_color, is_train=False, N_samples=-1)
+        o = orc.render_rays(fld, rays, chunk=4096, white_bg=white_bg, bg_color=bg_color,
+                            keys=("rgb_map", "depth_map", "acc_map", "ray_valid", "app_mask"))
+    assert torch.equal(rgb, o["rgb_map"]) and torch.equal(depth, o["depth_map"]), f"{name}: oracle != reference"
+    assert torch.equal(full[2], o["acc_map"][:4096])
+    valid = reference_valid_mask(m, rays)
+    assert torch.equal(valid, o["ray_valid"]), f"{name}: oracle mask != reference mask"
+    bits = orc.pack_valid_bits(valid)
+    rec = dict(rgb_map=rgb.numpy(), depth_map=depth.numpy(), acc_map=o["acc_map"].numpy(),
+               valid_bits=bits.numpy().astype(np.uint32), valid_count=valid.sum(-1).numpy().astype(np.int32),
+               app_count=o["app_mask"].sum(-1).numpy().astype(np.int32),
+               n_samples=np.int32(m.nSamples), step_size=np.float32(m.stepSize.item()),
+               param_checksum=fx.param_checksum(fld))
+    if extra:
+        rec.update(extra)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(f"[golden] {name}: rays={rays.shape[0]} S={m.nSamples} valid={valid.float().mean():.3f} "
+          f"app/ray={o['app_mask'].sum(-1).float().mean():.1f} rgb_mean={rgb.mean():.4f}  ({time.time()-t:.1f}s) "
+          f"oracle==reference bit-exact")
+
+
+def sampled_entries(t, n=256, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, t.numel(), (n,), generator=g)
+    return idx.numpy(), t.reshape(-1)[idx].numpy()
+
+
+def train_case(R, name, fld, rays, n_samples):
+    """Config 3: train.py:285-339 step — forward(is_train=True) + loss + backward; grads of every parameter."""
+    t = time.time()
+    m = build_reference_model(R, fld)
+    N = rays.shape[0]
+    torch.manual_seed(1234)
+    jitter = torch.rand(N, 1)
+    target = torch.rand(N, 3)
+    torch.manual_seed(1234)                       # the reference draws rand_like([N,1]) first thing in sample_ray
+    rgb, depth, acc, alpha, z, dists = m(rays, bg_color=torch.ones(3), is_train=True, N_samples=n_samples)
+    loss = torch.mean((rgb - target) ** 2) + 0.1 * torch.mean(torch.exp(torch.abs(alpha)))
+    m.zero_grad()
+    loss.backward()
+    # oracle on the same jitter
+    for p in fld.params():
+        p.requires_grad_(True)
+    o = orc.render_chunk(fld, rays, bg_color=torch.ones(3), n_samples=n_samples, jitter=jitter)
+    assert torch.equal(o["rgb_map"], rgb) and torch.equal(o["alpha"], alpha) and torch.equal(o["z_vals"], z), \
+        f"{name}: oracle fwd != reference (jitter draw mismatch?)"
+    lo = orc.train_loss(o, target)
+    assert torch.equal(lo, loss)
+    grads = torch.autograd.grad(lo, fld.params())
+    ref_grads = [p.grad for p in ([*m.density_plane, *m.density_line, *m.app_plane, *m.app_line, m.basis_mat.weight]
+                                  + [m.renderModule.mlp[i].weight for i in (0, 2, 4)]
+                                  + [m.renderModule.mlp[i].bias for i in (0, 2, 4)])]
+    for a, b in zip(grads, ref_grads):
+        assert torch.allclose(a, b, rtol=0, atol=0) or torch.equal(a, b), f"{name}: oracle grads != reference"
+    for p in fld.params():
+        p.requires_grad_(False)
+    rec = dict(jitter=jitter.numpy(), target=target.numpy(), rgb_map=rgb.detach().numpy(),
+               acc_map=acc.detach().numpy(), depth_map=depth.numpy(), loss=np.float64(loss.item()),
+               alpha_rows=alpha[:32].detach().numpy(), alpha_sum=alpha.detach().double().sum(-1).numpy(),
+               n_samples=np.int32(n_samples), param_checksum=fx.param_checksum(fld))
+    names = ([f"density_plane.{k}" for k in range(3)] + [f"density_line.{k}" for k in range(3)]
+             + [f"app_plane.{k}" for k in range(3)] + [f"app_line.{k}" for k in range(3)] + ["basis"]
+             + [f"mlp_w{i}" for i in range(3)] + [f"mlp_b{i}" for i in range(3)])
+    for nme, g in zip(names, ref_grads):
+        idx, val = sampled_entries(g)
+        # always include the largest-magnitude entries so the comparison is not all zeros
+        top = torch.topk(g.abs().reshape(-1), min(256, g.numel())).indices
+        rec[f"g_idx/{nme}"] = np.concatenate([idx, top.numpy()])
+        rec[f"g_val/{nme}"] = np.concatenate([val, g.reshape(-1)[top].numpy()])
+        rec[f"g_sum/{nme}"] = np.float64(g.double().sum().item())
+        rec[f"g_l2/{nme}"] = np.float64(g.double().norm().item())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(f"[golden] {name}: rays={N} S={n_samples} loss={loss.item():.6f} ({time.time()-t:.1f}s) "
+          f"oracle==reference bit-exact fwd+bwd")
+
+
+def pose_case(R, name, fld, rays):
+    """Config 5: frozen factors, gradients w.r.t. the rays (inerf/estimate_pose_inerf.py:164-178)."""
+    t = time.time()
+    m = build_reference_model(R, fld)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    torch.manual_seed(4321)
+    bg = torch.rand(3)
+    target = torch.rand(rays.shape[0], 3)
+    r = rays.clone().requires_grad_(True)
+    rgb, _, acc, _, _, _ = m(r, bg_color=bg, is_train=False)
+    loss = torch.mean((rgb - target) ** 2)
+    loss.backward()
+    r2 = rays.clone().requires_grad_(True)
+    o = orc.render_chunk(fld, r2, bg_color=bg)
+    lo = torch.mean((o["rgb_map"] - target) ** 2)
+    lo.backward()
+    assert torch.equal(o["rgb_map"], rgb) and torch.equal(r.grad, r2.grad), f"{name}: oracle != reference"
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), bg=bg.numpy(), target=target.numpy(),
+                        rgb_map=rgb.detach().numpy(), acc_map=acc.detach().numpy(), d_rays=r.grad.numpy(),
+                        loss=np.float64(loss.item()), param_checksum=fx.param_checksum(fld))
+    print(f"[golden] {name}: rays={rays.shape[0]} |d_rays|max={r.grad.abs().max():.3e} ({time.time()-t:.1f}s) "
+          f"oracle==reference bit-exact")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    R = import_reference()
+    torch.set_num_threads(os.cpu_count())
+    only = set(sys.argv[1:])
+
+    def want(n):
+        return not only or n in only
+
+    if want("c1_dense_mask"):
+        fld, rays = fx.config1(density_shift=0.0, occupancy="sphere", cols=6)
+        eval_case(R, "c1_dense_mask", fld, rays)
+    if want("c1_refdefault_nomask"):
+        fld, rays = fx.config1(density_shift=-10.0, occupancy=None, cols=6)
+        eval_case(R, "c1_refdefault_nomask", fld, rays)
+    if want("c1_dense_7col_blackbg"):
+        fld, rays = fx.config1(density_shift=0.0, occupancy="sphere", cols=7)
+        rays, idx = fx.subsample(rays, 2048, seed=3)
+        eval_case(R, "c1_dense_7col_blackbg", fld, rays, white_bg=None, extra=dict(ray_index=idx.numpy()))
+    if any(want(n) for n in ("c2_sub", "c3_train", "c5_pose")):
+        fld, rays = fx.config2()
+        if want("c2_sub"):
+            sub, idx = fx.subsample(rays, 2048, seed=0)
+            eval_case(R, "c2_sub", fld, sub, extra=dict(ray_index=idx.numpy()))
+        if want("c3_train"):
+            sub, idx = fx.subsample(rays, 1024, seed=1)
+            train_case(R, "c3_train", fld, sub, n_samples=1039)
+        if want("c5_pose"):
+            sub, idx = fx.subsample(rays, 512, seed=2)
+            pose_case(R, "c5_pose", fld, sub)
+    if want("c4_sub"):
+        fld, rays = fx.config4()
+        sub, idx = fx.subsample(rays, 2048, seed=0)
+        eval_case(R, "c4_sub", fld, sub, extra=dict(ray_index=idx.numpy(), grid=np.array(fld.grid)))
+
+
+if __name__ == "__main__":
+    main()
