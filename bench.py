@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — TensoRF-VM render throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one full-image render (800x800 = 640 000 rays, lego-shaped 300^3 VM field, 16x3/48x3 components,
+S=1036 samples/ray, synthetic sphere occupancy) — BASELINE.json configs[1].
+  value       rays/s with the rays already resident in HBM (march + shade kernels, device-timed, L2 flushed
+              between steps)
+  e2e         the same through OctreeRender_trilinear_fast with HOST (pinned) rays: H2D of the rays and D2H of
+              rgb+depth inside the timed region
+  roofline    march kernel alone: algorithmic gather bytes / its device time, vs measured HBM peak
+  cpu_baseline  the CPU oracle (port of the reference renderer) on a bounded ray sample, host cores
+N>1 (torchrun): every rank renders its own full view (weak scaling, no data-path collective); value = all
+rays / max-over-ranks time.
+--impl reference: times the oracle port of the reference's CPU renderer on the host cores (rank 0 only).
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "TensoRF VM render rays/s"
+UNIT = "rays/s"
+H = W = 800
+GRID = [300, 300, 300]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-rays", type=int, default=16384, help="rays in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(extra=None):
+    cfg = {"workload": "lego-shaped TensoRF VM 300^3 (density 16x3, app 48x3, app_dim 27, MLP_Fea 150-128-128-3), "
+                       "800x800 full-image render, S=1036, forward only",
+           "rays_per_step": H * W, "n_samples": 1036, "grid": GRID, "density_shift": 0.0,
+           "occupancy": "sphere r=1.0 on 200^3", "white_bg": True, "cache": "L2 flushed between timed steps"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.idx = gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if sm:
+            self.result = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                           "samples": len(sm)}
+
+
+def cpu_oracle_rate(n_rays, threads=None):
+    """Times the oracle port of the reference CPU renderer (OctreeRender_trilinear_fast, chunk 4096) on a strided
+    sample of the SAME 800x800 ray set; returns (rays/s, threads, description)."""
+    import torch
+    from oracle import fixtures as fx, tensorf_oracle as orc
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    fld = fx.make_field(GRID, density_shift=0.0)
+    rays = fx.config2_rays(H, W)
+    stride = max(1, rays.shape[0] // n_rays)
+    sample = rays[::stride][:n_rays].contiguous()
+    with torch.no_grad():
+        orc.render_rays(fld, sample[:4096], chunk=4096, white_bg=True)          # warm-up
+        t0 = time.perf_counter()
+        orc.render_rays(fld, sample, chunk=4096, white_bg=True)
+        dt = time.perf_counter() - t0
+    return sample.shape[0] / dt, torch.get_num_threads(), \
+        f"{sample.shape[0]} rays (every {stride}th ray of the 800x800 image), chunk 4096, 1 warm-up + 1 timed pass"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU renderer (oracle port; the reference is pure Python/torch and cannot
+    travel to the GPU box), all host threads, each step a bounded sample of the workload."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import fixtures as fx, tensorf_oracle as orc
+    torch.set_num_threads(os.cpu_count())
+    fld = fx.make_field(GRID, density_shift=0.0)
+    rays = fx.config2_rays(H, W)
+    n = 8192
+    stride = rays.shape[0] // n
+    times = []
+    with torch.no_grad():
+        for s in range(args.warmup + args.steps):
+            sample = rays[(s % stride)::stride][:n].contiguous()
+            t0 = time.perf_counter()
+            orc.render_rays(fld, sample, chunk=4096, white_bg=True)
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = n * len(times) / total
+    sample_desc = f"{n} rays per step (strided sample of the 800x800 image), chunk 4096"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config({"rays_per_step": n, "note": "CPU oracle port of the reference renderer"}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample_desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import iffnerf_b200 as I
+    from iffnerf_b200 import _lib, build
+    from oracle import fixtures as fx          # fixtures only (seeded synthetic inputs); the oracle is not on this path
+    from tests import helpers as Hh
+
+    build.build()
+    _lib.load()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    fld = fx.make_field(GRID, density_shift=0.0)
+    model = Hh.module_from_field(fld, dev)
+    model.eval()
+    # weak scaling: rank r renders its own full view of the orbit
+    rays_host = fx.config2_rays(H, W, theta_deg=35.0 + 45.0 * rank).pin_memory()
+    rays_dev = rays_host.to(dev)
+    n = rays_dev.shape[0]
+    S = model.nSamples
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
+    out_host = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in evs)                        # ms, device time of the steps only
+
+    def step_device():
+        return model.render_eval(rays_dev, white_bg=True)
+
+    def step_march_only():
+        d, keep = model.field_desc()
+        import ctypes as C
+        need = C.c_size_t(0)
+        lib = _lib.load()
+        lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need))
+        ws = torch.empty((need.value,), dtype=torch.uint8, device=dev)
+        bg = model._bg(None, True, dev)
+        _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays_dev), n, rays_dev.shape[1], S, None, _lib.ptr(bg),
+                                      _lib.F_EARLY_TERM | _lib.F_NO_SHADE, None, None, None, None, None, None,
+                                      None, None, None, _lib.ptr(ws), ws.numel(),
+                                      C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "march")
+
+    def step_e2e():
+        rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(rays_host, model, chunk=4096, N_samples=-1, white_bg=True,
+                                                          ndc_ray=False, device=dev)
+        out_host[:, :3].copy_(rgb, non_blocking=True)
+        out_host[:, 3].copy_(depth, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    with ClockSampler(local_rank) as clk:
+        ms_dev = timed(step_device, args.steps, args.warmup)
+    ms_march = timed(step_march_only, args.steps, 1)
+    ms_e2e = timed(step_e2e, args.steps, 1)
+
+    # work counters of one step (from the march workspace) for the algorithmic-bytes roofline
+    o = model.render_eval(rays_dev, white_bg=True, keep_workspace=True)
+    wsv = o["workspace"]
+    v0 = int(wsv["occ_count"].sum().item())
+    v = int(wsv["sigma_count"].sum().item())
+    a = int(wsv["app_count"].sum().item())
+    has_occ = model.alphaMask is not None
+    alg_bytes = 44 * n + (32 * v0 if has_occ else 0) + 1152 * v + 3456 * a
+
+    t = torch.tensor([ms_dev, ms_march, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_march, ms_e2e = t.tolist()
+    if rank == 0:
+        K = args.steps
+        peak, peak_src = peaks()
+        march_s = ms_march / K / 1e3
+        achieved = alg_bytes / march_s / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("march_fwd_dram_bytes_per_launch")
+        line = {"metric": METRIC, "value": world * n * K / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world,
+                "steps": K, "warmup": args.warmup, "ms_per_step": ms_dev / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config({"parallelism": f"ray-sharded views x{world}", "early_term_eps":
+                                           model.early_term_eps}),
+                "samples_per_s_nominal": world * n * S * K / (ms_dev / 1e3),
+                "sigma_samples_per_s": world * v * K / (ms_dev / 1e3),
+                "app_samples_per_s": world * a * K / (ms_dev / 1e3),
+                "e2e": {"value": world * n * K / (ms_e2e / 1e3), "unit": UNIT,
+                        "h2d_bytes_per_step": int(rays_host.numel() * 4), "d2h_bytes_per_step": int(n * 16),
+                        "ms_per_step": ms_e2e / K},
+                "gpu_launches": 2 * K,
+                "roofline": {"bound": "hbm", "kernel": "march_fwd_kernel", "achieved": achieved, "peak": peak,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                             "ms_per_launch": ms_march / K,
+                             "units_per_launch": {"rays": n, "occupancy_tests": v0, "sigma_samples": v,
+                                                  "app_samples": a}},
+                "clocks": clk.result}
+        if not args.no_cpu_baseline and world == 1:
+            rate, cores, desc = cpu_oracle_rate(args.cpu_rays)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: relaunch under torchrun when called plainly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,293 @@
+// march.cu — the fused per-ray march kernel of the TensoRF-VM renderer (forward).
+//
+// Replaces, in ONE launch over all rays of a batch, the reference's per-chunk op sequence
+//   sample_ray (models/tensorBase.py:494-536) -> AlphaGridMask.sample_alpha (:66-72, :832-837)
+//   -> normalize_coord (:397) -> compute_densityfeature (models/tensoRF.py:216-235)
+//   -> feature2density (:750-754) -> raw2alpha (:23-35) -> app_mask (:851)
+//   -> compute_appfeature (tensoRF.py:237-256, basis_mat hoisted past the weighted sum)
+//   -> weighted accumulation (:886-888) and the depth partial (:906-907).
+//
+// Mapping (B200, sm_100a): one warp marches one ray.  Each iteration covers 32 consecutive samples,
+// lane == sample: positions, aabb test and occupancy test use the reference's exact fp32 op order
+// (bit-exact ray_valid).  Valid samples are compacted through shared memory and evaluated by QUADS:
+// 4 lanes share a sample, each lane owning one float4 channel slice, so a texel (64 B density /
+// 192 B appearance, channel-last) is fetched with fully used 16-B vector loads from L1/L2 and the
+// plane x line product is reduced with two xor-shuffles.  Transmittance is a warp product-scan.
+// The per-ray appearance accumulator (sum_w plane*line, 3 x n_app floats) lives in registers,
+// distributed over the quad lanes, so the reference's [N,S,27] temporary never exists.
+#include "tvm_common.cuh"
+#include "tvm_gather.cuh"
+
+namespace {
+
+constexpr int MARCH_WARPS = 4;
+constexpr int MARCH_RAYS_PER_CTA = 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct MarchArgs {
+    tvm_field_desc f;
+    const float* rays;
+    long long n_rays;
+    int ray_stride;
+    int S;
+    const float* jitter;
+    unsigned flags;
+    // optional per-sample outputs [n][S]
+    float* alpha;
+    float* z_vals;
+    float* dists;
+    unsigned* valid_bits;
+    int* valid_count;
+    int* app_count_out;
+    // workspace (per ray)
+    float* ray_feat;
+    float* acc;
+    float* depth;
+    int* sigma_count;
+    int* app_count;
+    int* occ_count;
+    int ta;
+    int app_off[3];
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+template <int G, bool MASK_ONLY>
+__global__ void __launch_bounds__(MARCH_WARPS * 32) march_fwd_kernel(const __grid_constant__ MarchArgs a) {
+    __shared__ int s_next;
+    __shared__ float4 s_slot[MARCH_WARPS][32];
+    __shared__ float s_ret[MARCH_WARPS][32];
+    const tvm_field_desc& f = a.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 3, quad = lane >> 2;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    if (threadIdx.x == 0) s_next = MARCH_WARPS;
+    __syncthreads();
+
+    const long long base = (long long)blockIdx.x * MARCH_RAYS_PER_CTA;
+    const bool sample_out = a.alpha || a.z_vals || a.dists;
+    const bool visit_all = sample_out || a.valid_bits;          // every sample index must be written
+    const bool early = (a.flags & TVM_F_EARLY_TERM) && !sample_out;
+    const int S = a.S, words = (S + 31) >> 5;
+    int local = warp;
+
+    while (local < MARCH_RAYS_PER_CTA) {
+        const long long r = base + local;
+        if (r >= a.n_rays) break;
+        TvmRay ray;
+        {
+            const float* rp = a.rays + r * a.ray_stride;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { ray.o[c] = __ldg(rp + c); ray.d[c] = __ldg(rp + 3 + c); }
+        }
+        ray.t0 = tvm_ray_entry(f, ray.o, ray.d);
+        ray.jit = a.jitter ? __ldg(a.jitter + r) : 0.f;
+
+        float T = 1.f, acc = 0.f, dep = 0.f;
+        int n_valid = 0, n_sigma = 0, n_app = 0, n_occ = 0;
+        bool dead = false, seen_inside = false;
+        float4 A[3][G];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int g = 0; g < G; ++g) A[k][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        for (int i0 = 0; i0 < S; i0 += 32) {
+            const int i = i0 + lane;
+            const bool in_range = i < S;
+            const float z = tvm_sample_z(f, ray, i);
+            float p[3];
+            const bool inside = tvm_sample_point(f, ray, z, p) && in_range;
+            bool keep = inside;
+            if (f.occ_cells != nullptr && inside) keep = tvm_occupancy_keep(f, p);
+            const unsigned imask = __ballot_sync(FULL, inside);
+            const unsigned vmask = __ballot_sync(FULL, keep);
+            n_valid += __popc(vmask);
+            n_occ += __popc(imask);
+            if (a.valid_bits && lane == 0) a.valid_bits[r * words + (i0 >> 5)] = vmask;
+
+            float alpha = 0.f, dist = 0.f;
+            if (!MASK_ONLY) {
+                if (sample_out || (!dead && vmask)) {
+                    const float zn = tvm_sample_z(f, ray, i + 1);
+                    dist = (i < S - 1) ? rn_sub(zn, z) : 0.f;           // tensorBase.py:827-830
+                }
+                if (!dead && vmask) {
+                    float n[3];
+                    tvm_normalize(f, p, n);
+                    // ---- density: compact valid samples, 8 per pass, one quad per sample
+                    const int nv = __popc(vmask), rank = __popc(vmask & lt_mask);
+                    if (keep) s_slot[warp][rank] = make_float4(n[0], n[1], n[2], 0.f);
+                    __syncwarp();
+                    for (int g = 0; g * 8 < nv; ++g) {
+                        const int ci = g * 8 + quad;
+                        float part = 0.f;
+                        if (ci < nv) {
+                            const float4 s = s_slot[warp][ci];
+                            const float q[3] = {s.x, s.y, s.z};
+                            part = density_partial(f, q, sub);
+                        }
+                        part += __shfl_xor_sync(FULL, part, 1);
+                        part += __shfl_xor_sync(FULL, part, 2);
+                        if (sub == 0 && ci < nv) s_ret[warp][ci] = part;
+                    }
+                    __syncwarp();
+                    float sigma = 0.f;
+                    if (keep) sigma = tvm_density(f, s_ret[warp][rank]);
+                    n_sigma += nv;
+                    // ---- raw2alpha (tensorBase.py:23-35): alpha, T (exclusive cumprod), weight
+                    alpha = 1.f - expf(-sigma * rn_mul(dist, f.distance_scale));
+                    float incl = 1.f - alpha + 1e-10f;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const float v = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl *= v;
+                    }
+                    float excl = __shfl_up_sync(FULL, incl, 1);
+                    if (lane == 0) excl = 1.f;
+                    const float w = alpha * (T * excl);
+                    T *= __shfl_sync(FULL, incl, 31);
+                    acc += w;
+                    dep = fmaf(w, z, dep);
+                    // ---- appearance for samples with weight > rayMarch_weight_thres (:851)
+                    const bool app = keep && (w > f.weight_thres);
+                    const unsigned amask = __ballot_sync(FULL, app);
+                    if (amask) {
+                        const int na = __popc(amask), ranka = __popc(amask & lt_mask);
+                        if (app) s_slot[warp][ranka] = make_float4(n[0], n[1], n[2], w);
+                        __syncwarp();
+                        for (int g = 0; g * 8 < na; ++g) {
+                            const int ci = g * 8 + quad;
+                            if (ci < na) {
+                                const float4 s = s_slot[warp][ci];
+                                const float q[3] = {s.x, s.y, s.z};
+                                app_accumulate<G>(f, q, s.w, sub, A);
+                            }
+                        }
+                        __syncwarp();
+                        n_app += na;
+                    }
+                    if (early && T < f.early_term_eps) dead = true;
+                }
+                if (sample_out && in_range) {
+                    const long long o = r * S + i;
+                    if (a.alpha) a.alpha[o] = alpha;
+                    if (a.z_vals) a.z_vals[o] = z;
+                    if (a.dists) a.dists[o] = dist;
+                }
+            }
+            // the in-aabb samples of a ray form ONE interval (o + d*z is monotone in z in fp32 too),
+            // so once it has been left nothing further can be valid
+            if (imask) seen_inside = true;
+            else if (seen_inside && !visit_all) break;
+            if (dead && !visit_all && !a.valid_count) break;
+        }
+
+        if (visit_all && a.valid_bits) {
+            // (nothing to do: every word was written in the loop)
+        }
+        if (lane == 0) {
+            if (a.valid_count) a.valid_count[r] = n_valid;
+            if (a.occ_count) a.occ_count[r] = n_occ;
+        }
+        if (!MASK_ONLY) {
+            acc = warp_sum(acc);
+            dep = warp_sum(dep);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    float4 v = A[k][g];
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        v.x += __shfl_xor_sync(FULL, v.x, o); v.y += __shfl_xor_sync(FULL, v.y, o);
+                        v.z += __shfl_xor_sync(FULL, v.z, o); v.w += __shfl_xor_sync(FULL, v.w, o);
+                    }
+                    const int j = sub + 4 * g;
+                    if (quad == 0 && j < (f.n_app[k] >> 2))
+                        reinterpret_cast<float4*>(a.ray_feat + r * a.ta + a.app_off[k])[j] = v;
+                }
+            if (lane == 0) {
+                a.acc[r] = acc;
+                a.depth[r] = dep;
+                a.sigma_count[r] = n_sigma;
+                a.app_count[r] = n_app;
+                if (a.app_count_out) a.app_count_out[r] = n_app;
+            }
+        }
+        int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(&s_next, 1);
+        local = __shfl_sync(FULL, nxt, 0);
+    }
+}
+
+int fill_args(MarchArgs& a, const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
+              int n_samples, const float* jitter) {
+    int rc = tvm_check_desc(desc);
+    if (rc) return rc;
+    if (!rays) return TVM_E_NULL;
+    if (ray_stride < 6 || n_samples <= 0 || n_rays < 0) return TVM_E_SHAPE;
+    a = MarchArgs{};
+    a.f = *desc;
+    a.rays = rays; a.n_rays = n_rays; a.ray_stride = ray_stride; a.S = n_samples; a.jitter = jitter;
+    a.ta = tvm_total_app(desc);
+    a.app_off[0] = 0; a.app_off[1] = desc->n_app[0]; a.app_off[2] = desc->n_app[0] + desc->n_app[1];
+    return 0;
+}
+
+template <typename K>
+int launch(K kernel, const MarchArgs& a, cudaStream_t st) {
+    if (a.n_rays == 0) return 0;
+    static bool configured = false;   // idempotent attribute; benign if raced
+    (void)configured;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    const long long ctas = (a.n_rays + MARCH_RAYS_PER_CTA - 1) / MARCH_RAYS_PER_CTA;
+    kernel<<<(unsigned)ctas, MARCH_WARPS * 32, 0, st>>>(a);
+    TVM_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int tvm_sample_mask(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
+                               int n_samples, const float* jitter, uint32_t* valid_bits, int32_t* counts,
+                               void* stream) {
+    MarchArgs a;
+    int rc = fill_args(a, desc, rays, n_rays, ray_stride, n_samples, jitter);
+    if (rc) return rc;
+    a.valid_bits = valid_bits;
+    a.valid_count = counts;
+    return launch(march_fwd_kernel<1, true>, a, (cudaStream_t)stream);
+}
+
+// march stage of tvm_render_fwd (shade.cu finishes the job)
+int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,
+                         const float* jitter, uint32_t flags, float* alpha, float* z_vals, float* dists,
+                         uint32_t* valid_bits, int32_t* valid_count, int32_t* app_count, void* ws, size_t ws_bytes,
+                         cudaStream_t st) {
+    MarchArgs a;
+    int rc = fill_args(a, desc, rays, n_rays, ray_stride, n_samples, jitter);
+    if (rc) return rc;
+    if (!desc->factors) return TVM_E_NULL;
+    if (!ws) return TVM_E_NULL;
+    const TvmWorkspace w = tvm_ws_layout(desc, n_rays);
+    if (ws_bytes < w.total) return TVM_E_WORKSPACE;
+    char* base = (char*)ws;
+    a.flags = flags;
+    a.alpha = alpha; a.z_vals = z_vals; a.dists = dists;
+    a.valid_bits = valid_bits; a.valid_count = valid_count; a.app_count_out = app_count;
+    a.ray_feat = (float*)(base + w.ray_feat);
+    a.acc = (float*)(base + w.acc);
+    a.depth = (float*)(base + w.depth);
+    a.sigma_count = (int*)(base + w.sigma_count);
+    a.app_count = (int*)(base + w.app_count);
+    a.occ_count = (int*)(base + w.occ_count);
+    int gmax = 0;
+    for (int k = 0; k < 3; ++k) gmax = max(gmax, (desc->n_app[k] + 15) / 16);
+    if (gmax <= 1) return launch(march_fwd_kernel<1, false>, a, st);
+    if (gmax == 2) return launch(march_fwd_kernel<2, false>, a, st);
+    return launch(march_fwd_kernel<3, false>, a, st);
+}

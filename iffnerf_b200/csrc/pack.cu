@@ -1,0 +1,210 @@
+// pack.cu — layout conversion between the reference's parameter layout and the kernel layout,
+// plus the small ABI utilities (version, error strings, workspace sizes).
+//
+//   * factors: reference stores planes as [1,C,H,W] and lines as [1,C,L,1] (models/tensoRF.py:160-170),
+//     i.e. each (texel, channel) in its own 32-B sector.  The kernels want channel-last [H*W][C] so a
+//     texel is one contiguous 64-B / 192-B run.  Both directions are a tiled [C][P] <-> [P][C] transpose
+//     through shared memory (coalesced on both sides, HBM-bound: 2 x 69 MB at 300^3).
+//   * occupancy: AlphaGridMask's {0,1} fp32 volume (models/tensorBase.py:50-64) -> one byte per cell
+//     holding the occupancy of its 8 corners (see tvm_occupancy_keep in tvm_math.cuh).
+//   * MLP: torch Linear weights [out][in] -> transposed [in][out] rows for the shade kernels.
+#include "tvm_common.cuh"
+
+namespace {
+
+constexpr int TP = 32;   // pixels per tile
+
+// src [C][P] -> dst [P][C]
+__global__ void __launch_bounds__(256) cp_to_pc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C,
+                                                       long long P) {
+    __shared__ float tile[TVM_MAX_APP_C][TP + 1];
+    const long long p0 = (long long)blockIdx.x * TP;
+    const int px = threadIdx.x & 31, cy = threadIdx.x >> 5;
+    for (int c = cy; c < C; c += 8) {
+        const long long p = p0 + px;
+        tile[c][px] = (p < P) ? __ldg(src + (long long)c * P + p) : 0.f;
+    }
+    __syncthreads();
+    const long long lim = min((long long)TP, P - p0) * C;
+    for (int i = threadIdx.x; i < lim; i += 256) {
+        const int p = i / C, c = i - p * C;
+        dst[p0 * C + i] = tile[c][p];
+    }
+}
+
+// src [P][C] -> dst [C][P]  (dst = src^T, or dst += src^T)
+__global__ void __launch_bounds__(256) pc_to_cp_kernel(const float* __restrict__ src, float* __restrict__ dst, int C,
+                                                       long long P, int accumulate) {
+    __shared__ float tile[TVM_MAX_APP_C][TP + 1];
+    const long long p0 = (long long)blockIdx.x * TP;
+    const long long lim = min((long long)TP, P - p0) * C;
+    for (int i = threadIdx.x; i < lim; i += 256) {
+        const int p = i / C, c = i - p * C;
+        tile[c][p] = __ldg(src + p0 * C + i);
+    }
+    __syncthreads();
+    const int px = threadIdx.x & 31, cy = threadIdx.x >> 5;
+    const long long p = p0 + px;
+    if (p < P)
+        for (int c = cy; c < C; c += 8) {
+            float* d = dst + (long long)c * P + p;
+            *d = accumulate ? (*d + tile[c][px]) : tile[c][px];
+        }
+}
+
+__global__ void occupancy_cells_kernel(const float* __restrict__ vol, int dx, int dy, int dz,
+                                       uint8_t* __restrict__ cells) {
+    const long long n = (long long)dx * dy * dz;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = (int)(i % dx), y = (int)((i / dx) % dy), z = (int)(i / ((long long)dx * dy));
+    unsigned code = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const int xx = x + (b & 1), yy = y + ((b >> 1) & 1), zz = z + (b >> 2);
+        if (xx < dx && yy < dy && zz < dz && __ldg(vol + ((long long)zz * dy + yy) * dx + xx) > 0.f) code |= 1u << b;
+    }
+    cells[i] = (uint8_t)code;
+}
+
+// dst [cols][rows_padded...]: generic small transpose  src [R][Cc] -> dst [Cc (padded to kpad)][R]
+__global__ void transpose_small_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int Cc, int kpad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kpad * R) return;
+    const int k = i / R, r = i - k * R;
+    dst[i] = (k < Cc) ? __ldg(src + r * Cc + k) : 0.f;
+}
+// inverse: packed [kpad][R] -> torch [R][Cc], optional accumulate
+__global__ void untranspose_small_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int Cc,
+                                         int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * Cc) return;
+    const int r = i / Cc, k = i - r * Cc;
+    const float v = __ldg(src + k * R + r);
+    dst[i] = accumulate ? dst[i] + v : v;
+}
+__global__ void copy_small_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int npad,
+                                  int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    if (i < n) dst[i] = accumulate ? dst[i] + __ldg(src + i) : __ldg(src + i);
+    else if (!accumulate) dst[i] = 0.f;
+}
+
+struct FactorView { long long off; int C; long long P; };
+
+void factor_views(const tvm_field_desc* d, FactorView planes[6], FactorView lines[6]) {
+    for (int k = 0; k < 3; ++k) {
+        const long long hw = (long long)d->grid[TVM_M0(k)] * d->grid[TVM_M1(k)];
+        const long long l = d->grid[TVM_V(k)];
+        planes[k] = {d->dplane_off[k], d->n_sigma[k], hw};
+        planes[3 + k] = {d->aplane_off[k], d->n_app[k], hw};
+        lines[k] = {d->dline_off[k], d->n_sigma[k], l};
+        lines[3 + k] = {d->aline_off[k], d->n_app[k], l};
+    }
+}
+
+}  // namespace
+
+extern "C" int tvm_abi_version(void) { return TVM_ABI_VERSION; }
+
+extern "C" const char* tvm_error_string(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case TVM_E_NULL: return "tvm: required pointer is NULL";
+        case TVM_E_SHAPE: return "tvm: unsupported shape (channels must be multiples of 4, sigma<=16, app<=48, featureC==128)";
+        case TVM_E_WORKSPACE: return "tvm: workspace too small";
+        case TVM_E_MODE: return "tvm: unsupported mode";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "tvm: unknown error";
+    }
+}
+
+extern "C" int tvm_pack_factors(const tvm_field_desc* desc, const float* const planes[6], const float* const lines[6],
+                                float* packed, void* stream) {
+    int rc = tvm_check_desc(desc);
+    if (rc) return rc;
+    if (!planes || !lines || !packed) return TVM_E_NULL;
+    FactorView pv[6], lv[6];
+    factor_views(desc, pv, lv);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < 6; ++i) {
+        if (!planes[i] || !lines[i]) return TVM_E_NULL;
+        cp_to_pc_kernel<<<(unsigned)((pv[i].P + TP - 1) / TP), 256, 0, st>>>(planes[i], packed + pv[i].off, pv[i].C, pv[i].P);
+        cp_to_pc_kernel<<<(unsigned)((lv[i].P + TP - 1) / TP), 256, 0, st>>>(lines[i], packed + lv[i].off, lv[i].C, lv[i].P);
+    }
+    TVM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int tvm_unpack_factor_grads(const tvm_field_desc* desc, const float* packed_grad, float* const planes[6],
+                                       float* const lines[6], int accumulate, void* stream) {
+    int rc = tvm_check_desc(desc);
+    if (rc) return rc;
+    if (!planes || !lines || !packed_grad) return TVM_E_NULL;
+    FactorView pv[6], lv[6];
+    factor_views(desc, pv, lv);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < 6; ++i) {
+        if (planes[i])
+            pc_to_cp_kernel<<<(unsigned)((pv[i].P + TP - 1) / TP), 256, 0, st>>>(packed_grad + pv[i].off, planes[i], pv[i].C, pv[i].P, accumulate);
+        if (lines[i])
+            pc_to_cp_kernel<<<(unsigned)((lv[i].P + TP - 1) / TP), 256, 0, st>>>(packed_grad + lv[i].off, lines[i], lv[i].C, lv[i].P, accumulate);
+    }
+    TVM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int tvm_pack_occupancy(const float* volume, int dx, int dy, int dz, uint8_t* cells, void* stream) {
+    if (!volume || !cells) return TVM_E_NULL;
+    if (dx < 1 || dy < 1 || dz < 1) return TVM_E_SHAPE;
+    const long long n = (long long)dx * dy * dz;
+    occupancy_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(volume, dx, dy, dz, cells);
+    TVM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t tvm_mlp_pack_floats(const tvm_field_desc* desc) {
+    if (!desc) return 0;
+    return tvm_mlp_layout(desc).total;
+}
+
+extern "C" int tvm_pack_mlp(const tvm_field_desc* desc, const float* w1, const float* b1, const float* w2,
+                            const float* b2, const float* w3, const float* b3, float* packed, void* stream) {
+    if (!desc || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !packed) return TVM_E_NULL;
+    if (desc->feature_c != TVM_FEATURE_C) return TVM_E_SHAPE;
+    const TvmMlpLayout m = tvm_mlp_layout(desc);
+    const int FC = TVM_FEATURE_C;
+    cudaStream_t st = (cudaStream_t)stream;
+    transpose_small_kernel<<<(m.k1 * FC + 255) / 256, 256, 0, st>>>(w1, packed + m.w1t, FC, m.in_c, m.k1);
+    copy_small_kernel<<<1, 256, 0, st>>>(b1, packed + m.b1, FC, FC, 0);
+    transpose_small_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(w2, packed + m.w2t, FC, FC, FC);
+    copy_small_kernel<<<1, 256, 0, st>>>(b2, packed + m.b2, FC, FC, 0);
+    copy_small_kernel<<<2, 256, 0, st>>>(w3, packed + m.w3, 3 * FC, 3 * FC, 0);
+    copy_small_kernel<<<1, 32, 0, st>>>(b3, packed + m.b3, 3, 4, 0);
+    TVM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int tvm_workspace_bytes(const tvm_field_desc* desc, int64_t n_rays, uint32_t flags, size_t* out) {
+    (void)flags;
+    int rc = tvm_check_desc(desc);
+    if (rc) return rc;
+    if (!out) return TVM_E_NULL;
+    *out = tvm_ws_layout(desc, n_rays).total;
+    return 0;
+}
+
+extern "C" int tvm_workspace_layout(const tvm_field_desc* desc, int64_t n_rays, size_t* ray_feat_off, size_t* acc_off,
+                                    size_t* depth_off, size_t* sigma_count_off, size_t* app_count_off,
+                                    size_t* occ_count_off) {
+    int rc = tvm_check_desc(desc);
+    if (rc) return rc;
+    const TvmWorkspace w = tvm_ws_layout(desc, n_rays);
+    if (ray_feat_off) *ray_feat_off = w.ray_feat;
+    if (acc_off) *acc_off = w.acc;
+    if (depth_off) *depth_off = w.depth;
+    if (sigma_count_off) *sigma_count_off = w.sigma_count;
+    if (app_count_off) *app_count_off = w.app_count;
+    if (occ_count_off) *occ_count_off = w.occ_count;
+    return 0;
+}

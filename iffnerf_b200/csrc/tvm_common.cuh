@@ -1,0 +1,81 @@
+// tvm_common.cuh — host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "tvm_math.cuh"
+
+#define TVM_CUDA_OK(expr)                         \
+    do {                                          \
+        cudaError_t e__ = (expr);                 \
+        if (e__ != cudaSuccess) return (int)e__;  \
+    } while (0)
+
+#define TVM_LAUNCH_CHECK()                        \
+    do {                                          \
+        cudaError_t e__ = cudaGetLastError();     \
+        if (e__ != cudaSuccess) return (int)e__;  \
+    } while (0)
+
+constexpr int TVM_SM_COUNT = 148;        // B200: 2 dies x 74 SMs
+constexpr int TVM_MAX_SIGMA_C = 16;
+constexpr int TVM_MAX_APP_C = 48;
+constexpr int TVM_FEATURE_C = 128;       // hidden width the shade kernels are specialised for
+
+static inline int tvm_total_app(const tvm_field_desc* d) { return d->n_app[0] + d->n_app[1] + d->n_app[2]; }
+static inline int tvm_mlp_in(const tvm_field_desc* d) {
+    // MLPRender_Fea.in_mlpC (models/tensorBase.py:169)
+    return 2 * d->view_pe * 3 + 2 * d->fea_pe * d->app_dim + 3 + d->app_dim;
+}
+static inline int tvm_round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline size_t tvm_align(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// Workspace layout for n rays (all sections 256-B aligned):
+//   ray_feat [n][TA] f32 | acc [n] f32 | depth [n] f32 | sigma_count [n] i32 (density samples evaluated)
+//   | app_count [n] i32 (appearance samples evaluated) | occ_count [n] i32 (occupancy tests = in-aabb samples visited)
+struct TvmWorkspace {
+    size_t ray_feat, acc, depth, sigma_count, app_count, occ_count, total;
+};
+static inline TvmWorkspace tvm_ws_layout(const tvm_field_desc* d, int64_t n) {
+    TvmWorkspace w;
+    size_t off = 0;
+    w.ray_feat = off;    off = tvm_align(off + (size_t)n * tvm_total_app(d) * sizeof(float));
+    w.acc = off;         off = tvm_align(off + (size_t)n * sizeof(float));
+    w.depth = off;       off = tvm_align(off + (size_t)n * sizeof(float));
+    w.sigma_count = off; off = tvm_align(off + (size_t)n * sizeof(int32_t));
+    w.app_count = off;   off = tvm_align(off + (size_t)n * sizeof(int32_t));
+    w.occ_count = off;   off = tvm_align(off + (size_t)n * sizeof(int32_t));
+    w.total = off;
+    return w;
+}
+
+// Packed MLP layout (floats): W1^T [k1][FC] (rows >= in_c are zero) | b1 [FC] | W2^T [FC][FC] | b2 [FC] | W3 [3][FC] | b3 [4]
+struct TvmMlpLayout {
+    int in_c, k1;
+    size_t w1t, b1, w2t, b2, w3, b3, total;
+};
+static inline TvmMlpLayout tvm_mlp_layout(const tvm_field_desc* d) {
+    TvmMlpLayout m;
+    m.in_c = tvm_mlp_in(d);
+    m.k1 = tvm_round_up(m.in_c, 4);
+    const size_t FC = TVM_FEATURE_C;
+    size_t off = 0;
+    m.w1t = off; off += (size_t)m.k1 * FC;
+    m.b1 = off;  off += FC;
+    m.w2t = off; off += FC * FC;
+    m.b2 = off;  off += FC;
+    m.w3 = off;  off += 3 * FC;
+    m.b3 = off;  off += 4;
+    m.total = off;
+    return m;
+}
+
+static inline int tvm_check_desc(const tvm_field_desc* d) {
+    if (!d) return TVM_E_NULL;
+    for (int k = 0; k < 3; ++k) {
+        if (d->n_sigma[k] <= 0 || d->n_sigma[k] % 4 || d->n_sigma[k] > TVM_MAX_SIGMA_C) return TVM_E_SHAPE;
+        if (d->n_app[k] <= 0 || d->n_app[k] % 4 || d->n_app[k] > TVM_MAX_APP_C) return TVM_E_SHAPE;
+        if (d->grid[k] < 2) return TVM_E_SHAPE;
+        if ((d->dplane_off[k] | d->dline_off[k] | d->aplane_off[k] | d->aline_off[k]) & 3) return TVM_E_SHAPE;
+    }
+    if (d->act != 0 && d->act != 1) return TVM_E_MODE;
+    return 0;
+}

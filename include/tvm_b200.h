@@ -1,0 +1,144 @@
+/*
+ * tvm_b200.h — C ABI of the B200-native TensoRF-VM ray renderer (libtvm_b200.so).
+ *
+ * The reference (mbortolon97/IFFNeRF) has no FFI layer: its boundary for this path is
+ * two Python callables, TensorBase.forward (models/tensorBase.py:775-917) and
+ * OctreeRender_trilinear_fast (renderer.py:12-25).  This header is the boundary a
+ * native replacement exposes *underneath* those callables; the Python host in
+ * iffnerf_b200/ binds it with ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - every entry point returns int: 0 = ok, >0 = cudaError_t, <0 = TVM_E_* argument error
+ *   - never allocates, never synchronises the device, never throws; the caller owns all
+ *     buffers (device pointers unless stated) and passes an explicit cudaStream_t (as void*)
+ *   - no global mutable state: re-entrant per stream, one process per GPU
+ *   - all floating point is IEEE fp32; `valid_bits` / counts are bit-exact w.r.t. the
+ *     reference (sample positions are computed with the reference's un-fused op order)
+ */
+#ifndef TVM_B200_H
+#define TVM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVM_ABI_VERSION 3
+
+/* argument errors (negative so they cannot collide with cudaError_t) */
+#define TVM_E_NULL        (-1)   /* required pointer is NULL                      */
+#define TVM_E_SHAPE       (-2)   /* unsupported channel count / grid / stride     */
+#define TVM_E_WORKSPACE   (-3)   /* workspace too small                           */
+#define TVM_E_MODE        (-4)   /* unsupported activation / shading mode         */
+
+/* flags for tvm_render_fwd / tvm_render_bwd */
+#define TVM_F_EARLY_TERM   (1u << 0)  /* eval only: stop a ray once T < early_term_eps                      */
+#define TVM_F_MLP_BF16     (1u << 1)  /* shade with the bf16 tensor-core MLP (tolerance 1e-2) instead of fp32 */
+#define TVM_F_NO_SHADE     (1u << 2)  /* stop after the march stage: workspace holds ray_feat/acc/depth      */
+
+/*
+ * Field descriptor (POD, passed by pointer from the host; copied into kernel params).
+ * Mirrors the scalars TensorBase.__init__/update_stepSize derive
+ * (models/tensorBase.py:262-326, :354-375) and the factor shapes of
+ * TensorVMSplit.init_one_svd (models/tensoRF.py:160-170).
+ *
+ * Packed factor buffer (`factors`, fp32, channel-last so one texel is one contiguous
+ * run of C floats): for k in 0..2
+ *     density plane k : [G[m1]][G[m0]][n_sigma[k]]   at float offset dplane_off[k]
+ *     density line  k : [G[v]][n_sigma[k]]           at dline_off[k]
+ *     app plane k     : [G[m1]][G[m0]][n_app[k]]     at aplane_off[k]
+ *     app line  k     : [G[v]][n_app[k]]             at aline_off[k]
+ * with matMode (m0,m1) = (0,1),(0,2),(1,2) and vecMode v = 2,1,0 (tensorBase.py:311-312).
+ * Channel counts must be multiples of 4, n_sigma[k] <= 16, n_app[k] <= 48.
+ */
+typedef struct tvm_field_desc {
+    float    aabb[6];            /* lo.xyz, hi.xyz                      (self.aabb)                        */
+    float    inv_aabb[3];        /* 2 / aabbSize                        (self.invaabbSize, :358)           */
+    int32_t  grid[3];            /* gridSize x,y,z                      (self.gridSize)                    */
+    float    step_size;          /* self.stepSize.item()                (:366)                             */
+    float    near_t, far_t;      /* (float)near_far[0], [1]             (:498, clamp :502)                 */
+    float    density_shift;      /* (:752)                                                                 */
+    float    distance_scale;     /* (:849)                                                                 */
+    float    weight_thres;       /* rayMarch_weight_thres               (:851)                             */
+    float    early_term_eps;     /* T threshold for TVM_F_EARLY_TERM (0 disables)                          */
+    int32_t  act;                /* 0 = softplus(beta 1, threshold 20), 1 = relu   (:750-754)              */
+    int32_t  n_sigma[3];         /* density components per plane                                           */
+    int32_t  n_app[3];           /* appearance components per plane                                        */
+    int32_t  app_dim;            /* basis_mat rows (27)                                                    */
+    int32_t  fea_pe, view_pe;    /* MLPRender_Fea frequencies (:165-183)                                   */
+    int32_t  feature_c;          /* hidden width (128)                                                     */
+    int64_t  dplane_off[3], dline_off[3], aplane_off[3], aline_off[3];   /* float offsets into `factors`   */
+    int64_t  n_factor_floats;    /* total floats in `factors`                                              */
+    /* occupancy (AlphaGridMask, tensorBase.py:50-83); occ_cells == NULL -> no mask                        */
+    const uint8_t* occ_cells;    /* [Dz][Dy][Dx] corner codes from tvm_pack_occupancy                      */
+    int32_t  occ_dims[3];        /* Dx, Dy, Dz                                                             */
+    float    occ_lo[3];          /* alphaMask.aabb[0]                                                      */
+    float    occ_inv[3];         /* alphaMask.invgridSize = 1/aabbSize*2 (:59)                             */
+    /* device pointers to parameters                                                                       */
+    const float* factors;        /* packed factors (layout above)                                          */
+    const float* basis;          /* basis_mat.weight [app_dim][sum(n_app)] row-major (torch layout)        */
+    const float* mlp;            /* packed MLP from tvm_pack_mlp                                           */
+} tvm_field_desc;
+
+int  tvm_abi_version(void);
+/* last error string for a returned code (static storage) */
+const char* tvm_error_string(int code);
+
+/* ---- layout conversion (reference layout <-> kernel layout) -------------------------------------- */
+
+/* Reference NCHW parameters -> packed channel-last buffer.  planes/lines: 6 device pointers each,
+ * order density[0..2], app[0..2]; shapes [1,C,G[m1],G[m0]] and [1,C,G[v],1] (tensoRF.py:165-168). */
+int tvm_pack_factors(const tvm_field_desc* desc, const float* const planes[6], const float* const lines[6],
+                     float* packed, void* stream);
+/* Inverse, for gradients: packed grad buffer -> 12 NCHW tensors; accumulate != 0 adds into them
+ * (so torch-side regularisers, train.py:299-325, keep adding into the same .grad). */
+int tvm_unpack_factor_grads(const tvm_field_desc* desc, const float* packed_grad, float* const planes[6],
+                            float* const lines[6], int accumulate, void* stream);
+/* alphaMask volume [Dz][Dy][Dx] fp32 (>0 = occupied) -> per-cell 8-corner codes, same dims (bytes). */
+int tvm_pack_occupancy(const float* volume, int dx, int dy, int dz, uint8_t* cells, void* stream);
+/* MLPRender_Fea weights (torch layout: w1 [C,in], w2 [C,C], w3 [3,C]) -> kernel layout. */
+size_t tvm_mlp_pack_floats(const tvm_field_desc* desc);
+int tvm_pack_mlp(const tvm_field_desc* desc, const float* w1, const float* b1, const float* w2, const float* b2,
+                 const float* w3, const float* b3, float* packed, void* stream);
+
+/* ---- the hot path ---------------------------------------------------------------------------------- */
+
+/* sample_ray + aabb clip + alphaMask test (tensorBase.py:494-536, :832-837), no factor access.
+ * rays: [n_rays][ray_stride] fp32 (cols 0-2 origin, 3-5 direction); jitter: NULL (eval) or [n_rays]
+ * (train, one U[0,1) per ray, :507-509).  valid_bits: [n_rays][ceil(n_samples/32)] little-endian bit i%32
+ * of word i/32 = ray_valid[i] (nullable); counts: [n_rays] = popcount (nullable). */
+int tvm_sample_mask(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,
+                    const float* jitter, uint32_t* valid_bits, int32_t* counts, void* stream);
+
+/* bytes of scratch tvm_render_fwd needs for n_rays (ray_feat [n][sum(n_app)], acc, depth, counters). */
+int tvm_workspace_bytes(const tvm_field_desc* desc, int64_t n_rays, uint32_t flags, size_t* out);
+
+/* TensorBase.forward (tensorBase.py:775-917) for one batch of rays, sample_ray branch.
+ * bg: DEVICE pointer to the 3 background floats (train.py:267-271 draws it on the device).
+ * Outputs (device, caller-allocated): rgb [n][3], depth [n], acc [n]; optional alpha/z_vals/dists
+ * [n][n_samples] (train outputs; any may be NULL), optional valid_bits/valid_count/app_count as above.
+ * `ws` keeps the per-ray accumulations tvm_render_bwd needs. */
+int tvm_render_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,
+                   const float* jitter, const float* bg /* device [3] */, uint32_t flags,
+                   float* rgb, float* depth, float* acc,
+                   float* alpha, float* z_vals, float* dists,
+                   uint32_t* valid_bits, int32_t* valid_count, int32_t* app_count,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* Shade stage alone (basis_mat + MLPRender_Fea + background blend + depth tail, tensorBase.py:886-908),
+ * reading ray_feat/acc/depth partials from ws. */
+int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
+                  const float* bg /* device [3] */,
+                  uint32_t flags, float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes,
+                  void* stream);
+
+/* workspace layout helpers (byte offsets inside ws for n_rays) so the host can view the march outputs */
+int tvm_workspace_layout(const tvm_field_desc* desc, int64_t n_rays, size_t* ray_feat_off, size_t* acc_off,
+                         size_t* depth_off, size_t* sigma_count_off, size_t* app_count_off, size_t* occ_count_off);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVM_B200_H */

@@ -1,0 +1,179 @@
+"""Parity of the CUDA path (through the C ABI) against the reference-generated goldens and the oracle.
+
+Tolerances (BASELINE.json north_star): valid-sample mask and counts BIT-EXACT; rgb_map / depth_map within
+1e-4 max-abs in fp32.  Every test here needs a B200 (`-m gpu`)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures as fx
+from oracle import tensorf_oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+EVAL_CASES = {
+    "c1_dense_mask": (lambda: fx.config1(0.0, "sphere", 6), None, True),
+    "c1_refdefault_nomask": (lambda: fx.config1(-10.0, None, 6), None, True),
+    "c1_dense_7col_blackbg": (lambda: fx.config1(0.0, "sphere", 7), "ray_index", None),
+    "c2_sub": (lambda: fx.config2(), "ray_index", True),
+    "c4_sub": (lambda: fx.config4(), "ray_index", True),
+}
+
+
+@pytest.fixture(scope="module")
+def dev(built_lib):
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+_cache = {}
+
+
+def _case(name, dev):
+    if name not in _cache:
+        _cache.clear()                       # one 300^3 model at a time is plenty
+        build, idx_key, white = EVAL_CASES[name]
+        fld, rays = build()
+        g = H.golden(name)
+        H.check_params(fld, g)
+        if idx_key:
+            rays = rays[torch.from_numpy(g[idx_key])].contiguous()
+        _cache[name] = (fld, rays, g, white, H.module_from_field(fld, dev))
+    return _cache[name]
+
+
+@pytest.mark.parametrize("name", sorted(EVAL_CASES))
+def test_valid_mask_and_counts_bit_exact(name, dev):
+    fld, rays, g, white, m = _case(name, dev)
+    bits, counts = m.sample_mask(rays.to(dev))
+    assert m.nSamples == int(g["n_samples"])
+    assert np.array_equal(bits.cpu().numpy().view(np.uint32), g["valid_bits"])
+    assert np.array_equal(counts.cpu().numpy(), g["valid_count"])
+
+
+@pytest.mark.parametrize("early_term", [False, True])
+@pytest.mark.parametrize("name", sorted(EVAL_CASES))
+def test_render_matches_reference_golden(name, early_term, dev):
+    fld, rays, g, white, m = _case(name, dev)
+    o = m.render_eval(rays.to(dev), white_bg=bool(white), early_term=early_term, want_counts=True)
+    torch.cuda.synchronize()
+    assert np.abs(o["rgb_map"].cpu().numpy() - g["rgb_map"]).max() <= TOL
+    assert np.abs(o["depth_map"].cpu().numpy() - g["depth_map"]).max() <= TOL
+    assert np.abs(o["acc_map"].cpu().numpy() - g["acc_map"]).max() <= TOL
+    # the full valid count is bit-exact even when rays terminate early
+    assert np.array_equal(o["valid_count"].cpu().numpy(), g["valid_count"])
+    # app_mask depends on fp32 reduction order: borderline samples only
+    assert np.abs(o["app_count"].cpu().numpy() - g["app_count"]).max() <= 2
+
+
+def test_forward_six_tuple_matches_oracle(dev):
+    fld, rays, g, white, m = _case("c1_dense_mask", dev)
+    sub = rays[3000:3700].contiguous()
+    with torch.no_grad():
+        rgb, depth, acc, alpha, z, dists = m(sub.to(dev), white_bg=True, is_train=False)
+        o = orc.render_chunk(fld, sub, white_bg=True)
+    assert alpha.shape == (700, m.nSamples) and z.shape == alpha.shape and dists.shape == alpha.shape
+    assert torch.equal(z.cpu(), o["z_vals"])                     # same fp32 op order -> identical
+    assert torch.equal(dists.cpu(), o["dists"])
+    assert (alpha.cpu() - o["alpha"]).abs().max() <= 1e-5
+    assert torch.equal(alpha.cpu() > 0, o["ray_valid"])          # sigma>0 exactly on the valid samples
+    assert (rgb.cpu() - o["rgb_map"]).abs().max() <= TOL
+    assert (depth.cpu() - o["depth_map"]).abs().max() <= TOL
+    assert (acc.cpu() - o["acc_map"]).abs().max() <= TOL
+
+
+def test_train_mode_jitter_matches_oracle(dev):
+    fld, rays, g, white, m = _case("c1_dense_mask", dev)
+    sub = rays[4000:4300].contiguous()
+    torch.manual_seed(11)
+    jit = torch.rand(300, 1)
+    with torch.no_grad():
+        rgb, depth, acc, alpha, z, dists = m(sub.to(dev), bg_color=torch.ones(3, device=dev), is_train=True,
+                                             N_samples=443, jitter=jit.to(dev))
+        o = orc.render_chunk(fld, sub, bg_color=torch.ones(3), n_samples=443, jitter=jit)
+    assert torch.equal(z.cpu(), o["z_vals"])
+    assert torch.equal(alpha.cpu() > 0, o["ray_valid"])
+    assert (alpha.cpu() - o["alpha"]).abs().max() <= 1e-5
+    assert (rgb.cpu() - o["rgb_map"]).abs().max() <= TOL
+
+
+def test_octree_render_cpu_rays_and_chunking(dev):
+    import iffnerf_b200 as I
+    fld, rays, g, white, m = _case("c1_dense_mask", dev)
+    m.max_launch_rays = 3000                                   # force several launches + the copy stream
+    try:
+        rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(rays, m, chunk=4096, N_samples=-1, white_bg=True,
+                                                          ndc_ray=False, device=dev)
+    finally:
+        m.max_launch_rays = type(m).max_launch_rays
+    assert rgb.is_cuda and rgb.shape == (10000, 3) and depth.shape == (10000,)
+    assert np.abs(rgb.cpu().numpy() - g["rgb_map"]).max() <= TOL
+    assert np.abs(depth.cpu().numpy() - g["depth_map"]).max() <= TOL
+
+
+def test_edge_cases(dev):
+    fld, rays, g, white, m = _case("c1_dense_mask", dev)
+    # empty batch
+    o = m.render_eval(rays[:0].to(dev), white_bg=True)
+    assert o["rgb_map"].shape == (0, 3)
+    # ragged batch sizes (not multiples of the 32-ray CTA tile / 64-ray shade tile)
+    for n in (1, 31, 33, 65, 127):
+        o = m.render_eval(rays[5000:5000 + n].to(dev), white_bg=True)
+        assert np.abs(o["rgb_map"].cpu().numpy() - g["rgb_map"][5000:5000 + n]).max() <= TOL
+    # rays that miss the box, axis-parallel rays (zero direction components), origin inside the box
+    special = torch.tensor([[0.0, 0.0, 4.0, 0.0, 1.0, 0.0],      # parallel to a face, misses
+                            [0.0, 0.0, 4.0, 0.0, 0.0, -1.0],     # straight down the z axis
+                            [0.2, -0.1, 0.3, 0.6, 0.0, -0.8],    # starts inside
+                            [9.0, 9.0, 9.0, 1.0, 0.0, 0.0]])     # far away, pointing off
+    fld2 = fx.make_field([128] * 3, density_shift=0.0, near_far=(0.05, 6.0), holes_seed=1)
+    m2 = H.module_from_field(fld2, dev)
+    o = m2.render_eval(special.to(dev), white_bg=True, early_term=False)
+    ref = orc.render_chunk(fld2, special, white_bg=True)
+    bits, counts = m2.sample_mask(special.to(dev))
+    assert np.array_equal(H.unpack_bits(bits.cpu().numpy(), m2.nSamples), ref["ray_valid"].numpy())
+    assert (o["rgb_map"].cpu() - ref["rgb_map"]).abs().max() <= TOL
+    assert (o["depth_map"].cpu() - ref["depth_map"]).abs().max() <= TOL
+    # N_samples override
+    o = m.render_eval(rays[5000:5100].to(dev), white_bg=True, N_samples=200)
+    ref = orc.render_chunk(fld, rays[5000:5100], white_bg=True, n_samples=200)
+    assert (o["rgb_map"].cpu() - ref["rgb_map"]).abs().max() <= TOL
+
+
+def test_pack_roundtrip_and_layout(dev, built_lib):
+    """tvm_pack_factors writes the documented channel-last layout; tvm_unpack_factor_grads inverts it."""
+    import ctypes as C
+    from iffnerf_b200 import _lib
+    fld = fx.make_field([37, 41, 29], occupancy=None)
+    m = H.module_from_field(fld, dev)
+    packed = m.packed_factors()
+    d, host = H.host_pack_factors(m)
+    assert np.array_equal(packed.cpu().numpy(), host)
+    planes, lines = m._factor_params()
+    outs_p = [torch.zeros_like(p) for p in planes]
+    outs_l = [torch.zeros_like(p) for p in lines]
+    for acc_flag, scale in ((0, 1.0), (1, 2.0)):
+        _lib.check(built_lib.tvm_unpack_factor_grads(C.byref(d), _lib.ptr(packed), _lib.ptr_array(outs_p),
+                                                     _lib.ptr_array(outs_l), acc_flag, None), "unpack")
+        torch.cuda.synchronize()
+        for a, b in zip(outs_p + outs_l, planes + lines):
+            assert torch.equal(a, scale * b.detach())
+
+
+def test_full_size_properties(dev):
+    """BASELINE config 2 at full size (800x800, 300^3): size-independent properties.
+    (a) the ray-subset golden rows are reproduced inside the full render, (b) rendering is permutation-
+    equivariant (rays are independent units), (c) outputs are finite and in range, (d) acc in [0,1]."""
+    fld, rays, g, white, m = _case("c2_sub", dev)
+    full = fx.config2_rays()
+    o = m.render_eval(full.to(dev), white_bg=True)
+    rgb = o["rgb_map"]
+    assert torch.isfinite(rgb).all() and rgb.min() >= 0 and rgb.max() <= 1
+    assert o["acc_map"].min() >= 0 and o["acc_map"].max() <= 1 + 1e-5
+    idx = torch.from_numpy(g["ray_index"])
+    assert np.abs(rgb[idx.to(dev)].cpu().numpy() - g["rgb_map"]).max() <= TOL
+    perm = torch.randperm(full.shape[0], generator=torch.Generator().manual_seed(0))
+    o2 = m.render_eval(full[perm].to(dev), white_bg=True)
+    assert torch.equal(o2["rgb_map"], rgb[perm.to(dev)])
+    assert torch.equal(o2["depth_map"], o["depth_map"][perm.to(dev)])

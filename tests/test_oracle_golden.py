@@ -1,0 +1,47 @@
+"""The oracle restatement against the committed reference-generated goldens (CPU, small cases)."""
+import numpy as np
+import torch
+
+from oracle import fixtures as fx
+from oracle import tensorf_oracle as orc
+from tests import helpers as H
+
+
+def test_oracle_reproduces_reference_golden_config1():
+    fld, rays = fx.config1(0.0, "sphere", 6)
+    g = H.golden("c1_dense_mask")
+    H.check_params(fld, g)
+    sel = slice(2000, 6096)
+    with torch.no_grad():
+        o = orc.render_chunk(fld, rays[sel], white_bg=True)
+    assert np.array_equal(o["rgb_map"].numpy(), g["rgb_map"][sel])          # bit-identical
+    assert np.array_equal(o["depth_map"].numpy(), g["depth_map"][sel])
+    assert np.array_equal(orc.pack_valid_bits(o["ray_valid"]).numpy().astype(np.uint32), g["valid_bits"][sel])
+    assert np.array_equal(o["ray_valid"].sum(-1).numpy(), g["valid_count"][sel])
+
+
+def test_oracle_refdefault_density_is_background():
+    """density_shift=-10 (the reference default) leaves the appearance path dead: rgb == white."""
+    fld, rays = fx.config1(-10.0, None, 6)
+    g = H.golden("c1_refdefault_nomask")
+    with torch.no_grad():
+        o = orc.render_chunk(fld, rays[:1024], white_bg=True)
+    assert np.array_equal(o["rgb_map"].numpy(), g["rgb_map"][:1024])
+    assert int(o["app_mask"].sum()) == 0
+
+
+def test_oracle_7col_depth_tail_uses_last_column():
+    """depth += (1-acc)*rays[:, -1]: radii for 7-col rays (tensorBase.py:908)."""
+    fld, rays = fx.config1(0.0, "sphere", 7)
+    g = H.golden("c1_dense_7col_blackbg")
+    sub = rays[torch.from_numpy(g["ray_index"])][:512]
+    with torch.no_grad():
+        o = orc.render_chunk(fld, sub, white_bg=None)
+    assert np.array_equal(o["rgb_map"].numpy(), g["rgb_map"][:512])
+    assert np.array_equal(o["depth_map"].numpy(), g["depth_map"][:512])
+
+
+def test_bit_packing_roundtrip():
+    v = torch.rand(5, 70) > 0.5
+    w = orc.pack_valid_bits(v).numpy().astype(np.uint32)
+    assert np.array_equal(H.unpack_bits(w, 70), v.numpy())
