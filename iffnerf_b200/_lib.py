@@ -58,6 +58,8 @@ _SIGNATURES = {
     "tvm_workspace_bytes": (C.c_int, [C.POINTER(FieldDesc), C.c_int64, C.c_uint32, C.POINTER(C.c_size_t)]),
     "tvm_render_fwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_uint32,
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "tvm_march_bwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P,
+                                C.c_size_t, _P]),
     "tvm_shade_fwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, _P, C.c_uint32, _P, _P, _P, _P,
                                 C.c_size_t, _P]),
     "tvm_workspace_layout": (C.c_int, [C.POINTER(FieldDesc), C.c_int64] + [C.POINTER(C.c_size_t)] * 6),

@@ -241,9 +241,9 @@ int fill_args(MarchArgs& a, const tvm_field_desc* desc, const float* rays, int64
 template <typename K>
 int launch(K kernel, const MarchArgs& a, cudaStream_t st) {
     if (a.n_rays == 0) return 0;
-    static bool configured = false;   // idempotent attribute; benign if raced
-    (void)configured;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    // small static smem per CTA: ask for a 32 KB carve-out (enough for every resident CTA) and leave the rest
+    // of the 228 KB to L1, which is what serves the texel gathers
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 14);
     const long long ctas = (a.n_rays + MARCH_RAYS_PER_CTA - 1) / MARCH_RAYS_PER_CTA;
     kernel<<<(unsigned)ctas, MARCH_WARPS * 32, 0, st>>>(a);
     TVM_LAUNCH_CHECK();

@@ -123,10 +123,13 @@ TVM_HD void tvm_normalize(const tvm_field_desc& f, const float p[3], float n[3])
 }
 
 // One axis of an align_corners=True, zero-padded (bi)linear tap: index pair + weights.
-// Out-of-range taps get weight 0 and a clamped (safe) index.  `dscale` = d(idx)/d(coord) = (size-1)/2.
+// Out-of-range taps get weight 0 and a clamped (safe) index.  m0/m1 are the in-bounds masks and
+// `scale` = d(idx)/d(coord) = (size-1)/2, both only used by the backward (coordinate gradients).
 struct TvmTap {
     int i0, i1;
     float w0, w1;
+    float m0, m1;
+    float scale;
 };
 TVM_HD TvmTap tvm_axis_tap(float coord, int size) {
     float idx = ((coord + 1.0f) * 0.5f) * (float)(size - 1);
@@ -135,10 +138,13 @@ TVM_HD TvmTap tvm_axis_tap(float coord, int size) {
     fl = fminf(fmaxf(fl, -2.0f), (float)size + 1.0f);
     int a = (int)fl, b = a + 1;
     TvmTap t;
-    t.w0 = (a >= 0 && a < size) ? 1.0f - fr : 0.0f;
-    t.w1 = (b >= 0 && b < size) ? fr : 0.0f;
+    t.m0 = (a >= 0 && a < size) ? 1.0f : 0.0f;
+    t.m1 = (b >= 0 && b < size) ? 1.0f : 0.0f;
+    t.w0 = t.m0 * (1.0f - fr);
+    t.w1 = t.m1 * fr;
     t.i0 = min(max(a, 0), size - 1);
     t.i1 = min(max(b, 0), size - 1);
+    t.scale = 0.5f * (float)(size - 1);
     return t;
 }
 

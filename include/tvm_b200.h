@@ -127,6 +127,15 @@ int tvm_render_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays
                    uint32_t* valid_bits, int32_t* valid_count, int32_t* app_count,
                    void* ws, size_t ws_bytes, void* stream);
 
+/* Backward of the march stage: given d(ray_feat) [n][sum(n_app)], d(acc) [n] and d(alpha) [n][n_samples]
+ * (any NULL = zero) it re-marches the rays and scatters into g_factors (packed layout, pre-zeroed or
+ * accumulating) and, when g_rays != NULL, writes d(rays) [n][6] (pose mode). ws is the forward workspace
+ * (tvm_render_fwd with the same rays / n_samples / jitter; replaces autograd through grid_sampler_2d_backward,
+ * cumprod, softplus ... driven by train.py:338 and inerf/estimate_pose_inerf.py:178). */
+int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,
+                  const float* jitter, const float* d_ray_feat, const float* d_acc, const float* d_alpha,
+                  float* g_factors, float* g_rays, const void* ws, size_t ws_bytes, void* stream);
+
 /* Shade stage alone (basis_mat + MLPRender_Fea + background blend + depth tail, tensorBase.py:886-908),
  * reading ray_feat/acc/depth partials from ws. */
 int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,

@@ -45,7 +45,7 @@ def module_from_field(fld, device):
 
 def check_params(fld, g):
     """RNG-drift guard: the regenerated fixture must have the parameters the goldens were made with."""
-    np.testing.assert_allclose(fx.param_checksum(fld), g["param_checksum"], rtol=0, atol=0)
+    np.testing.assert_allclose(fx.param_checksum(fld), g["param_checksum"], rtol=1e-10, atol=1e-10)  # double sums: thread-count dependent order
 
 
 def host_pack_factors(m):

@@ -92,3 +92,93 @@ extern "C" void hc_march(const tvm_field_desc* f, const float* rays, long long n
         if (app_count) app_count[r] = napp;
     }
 }
+
+// sequential restatement of march_bwd_kernel: gradients of (ray_feat, acc, alpha) -> packed factor grads, d(rays)
+extern "C" void hc_march_bwd(const tvm_field_desc* f, const float* rays, long long n, int stride, int S,
+                             const float* jitter, const float* ray_feat, const float* acc_fwd,
+                             const float* d_ray_feat, const float* d_acc, const float* d_alpha, float* g_factors,
+                             float* g_rays) {
+    const int ta = f->n_app[0] + f->n_app[1] + f->n_app[2];
+    const int off[3] = {0, f->n_app[0], f->n_app[0] + f->n_app[1]};
+    for (long long r = 0; r < n; ++r) {
+        TvmRay ray;
+        for (int c = 0; c < 3; ++c) { ray.o[c] = rays[r * stride + c]; ray.d[c] = rays[r * stride + 3 + c]; }
+        ray.t0 = tvm_ray_entry(*f, ray.o, ray.d);
+        ray.jit = jitter ? jitter[r] : 0.f;
+        float4 gF[4][3][3];
+        memset(gF, 0, sizeof(gF));
+        float total = 0.f;
+        for (int k = 0; k < 3; ++k)
+            for (int sub = 0; sub < 4; ++sub)
+                for (int g = 0; g < 3; ++g) {
+                    const int j = sub + 4 * g;
+                    if (d_ray_feat && j < (f->n_app[k] >> 2)) {
+                        memcpy(&gF[sub][k][g], d_ray_feat + r * ta + off[k] + 4 * j, 16);
+                        float4 Fv;
+                        memcpy(&Fv, ray_feat + r * ta + off[k] + 4 * j, 16);
+                        total += f4_dot(gF[sub][k][g], Fv);
+                    }
+                }
+        const float g_acc = d_acc ? d_acc[r] : 0.f;
+        total += g_acc * acc_fwd[r];
+        float T = 1.f, run = 0.f;
+        float go[3] = {0, 0, 0}, gd[3] = {0, 0, 0};
+        for (int i = 0; i < S; ++i) {
+            float p[3], nrm[3];
+            const float z = tvm_sample_z(*f, ray, i);
+            bool keep = tvm_sample_point(*f, ray, z, p);
+            if (keep && f->occ_cells) keep = tvm_occupancy_keep(*f, p);
+            if (!keep) continue;
+            tvm_normalize(*f, p, nrm);
+            float part[4];
+            for (int sub = 0; sub < 4; ++sub) part[sub] = density_partial(*f, nrm, sub);
+            const float feat = (part[0] + part[1]) + (part[2] + part[3]);
+            const float sigma = tvm_density(*f, feat);
+            const float dist = (i < S - 1) ? rn_sub(tvm_sample_z(*f, ray, i + 1), z) : 0.f;
+            const float delta = rn_mul(dist, f->distance_scale);
+            const float alpha = 1.f - expf(-sigma * delta);
+            const float one_m = 1.f - alpha + 1e-10f;
+            const float w = alpha * T;
+            float c = g_acc;
+            if (w > f->weight_thres && d_ray_feat) {
+                float dn[3] = {0, 0, 0};
+                for (int sub = 0; sub < 4; ++sub) {
+                    if (g_factors && g_rays) c += app_bwd<3, true, true>(*f, nrm, w, sub, gF[sub], g_factors, dn);
+                    else if (g_factors) c += app_bwd<3, true, false>(*f, nrm, w, sub, gF[sub], g_factors, dn);
+                    else c += app_bwd<3, false, true>(*f, nrm, w, sub, gF[sub], g_factors, dn);
+                }
+                for (int cc = 0; cc < 3; ++cc) { const float dp = dn[cc] * f->inv_aabb[cc]; go[cc] += dp; gd[cc] += dp * z; }
+            }
+            run += w * c;
+            const float suffix = total - run;
+            float dalpha = T * c - suffix / one_m;
+            if (d_alpha) dalpha += d_alpha[r * S + i];
+            const float dfeat = dalpha * delta * (1.f - alpha) * tvm_density_grad(*f, feat);
+            T *= one_m;
+            if (dfeat != 0.f) {
+                float dn[3] = {0, 0, 0};
+                for (int sub = 0; sub < 4; ++sub) {
+                    if (g_factors && g_rays) density_bwd<true, true>(*f, nrm, dfeat, sub, g_factors, dn);
+                    else if (g_factors) density_bwd<true, false>(*f, nrm, dfeat, sub, g_factors, dn);
+                    else density_bwd<false, true>(*f, nrm, dfeat, sub, g_factors, dn);
+                }
+                for (int cc = 0; cc < 3; ++cc) { const float dp = dn[cc] * f->inv_aabb[cc]; go[cc] += dp; gd[cc] += dp * z; }
+            }
+        }
+        if (g_rays) {
+            const float gt0 = go[0] * ray.d[0] + go[1] * ray.d[1] + go[2] * ray.d[2];
+            float best = -INFINITY, bv = 1.f; int bc = 0; bool bzero = false;
+            for (int cc = 0; cc < 3; ++cc) {
+                const bool zero = ray.d[cc] == 0.0f;
+                const float v = zero ? 1e-6f : ray.d[cc];
+                const float m = fminf(rn_div(rn_sub(f->aabb[3 + cc], ray.o[cc]), v), rn_div(rn_sub(f->aabb[cc], ray.o[cc]), v));
+                if (m > best) { best = m; bc = cc; bv = v; bzero = zero; }
+            }
+            if (best >= f->near_t && best <= f->far_t) {
+                go[bc] -= gt0 / bv;
+                if (!bzero) gd[bc] -= gt0 * best / bv;
+            }
+            for (int cc = 0; cc < 3; ++cc) { g_rays[r * 6 + cc] = go[cc]; g_rays[r * 6 + 3 + cc] = gd[cc]; }
+        }
+    }
+}

@@ -1,0 +1,138 @@
+"""Backward parity on the GPU: the training step (BASELINE config 3) and pose gradients (config 5) against the
+reference-generated goldens / the oracle's autograd."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures as fx
+from oracle import tensorf_oracle as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+GRAD_NAMES = ([f"density_plane.{k}" for k in range(3)] + [f"density_line.{k}" for k in range(3)]
+              + [f"app_plane.{k}" for k in range(3)] + [f"app_line.{k}" for k in range(3)] + ["basis"]
+              + [f"mlp_w{i}" for i in range(3)] + [f"mlp_b{i}" for i in range(3)])
+
+
+@pytest.fixture(scope="module")
+def dev(built_lib):
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def lego(dev):
+    fld, rays = fx.config2()
+    return fld, rays, H.module_from_field(fld, dev)
+
+
+def _module_params(m):
+    return ([*m.density_plane, *m.density_line, *m.app_plane, *m.app_line, m.basis_mat.weight]
+            + [m.renderModule.mlp[i].weight for i in (0, 2, 4)] + [m.renderModule.mlp[i].bias for i in (0, 2, 4)])
+
+
+def test_train_step_matches_reference_golden(lego, dev):
+    """train.py:285-339: forward(is_train=True, N_samples=1039) + MSE + 0.1*mean(exp|alpha|) + backward."""
+    fld, rays, m = lego
+    g = H.golden("c3_train")
+    H.check_params(fld, g)
+    sub, _ = fx.subsample(rays, 1024, seed=1)
+    jit = torch.from_numpy(g["jitter"]).to(dev)
+    target = torch.from_numpy(g["target"]).to(dev)
+    m.train()
+    m.zero_grad()
+    rgb, depth, acc, alpha, z, dists = m(sub.to(dev), bg_color=torch.ones(3, device=dev), is_train=True,
+                                         N_samples=int(g["n_samples"]), jitter=jit)
+    assert rgb.requires_grad and acc.requires_grad and alpha.requires_grad and not depth.requires_grad
+    loss = torch.mean((rgb - target) ** 2) + 0.1 * torch.mean(torch.exp(torch.abs(alpha)))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert np.abs(rgb.detach().cpu().numpy() - g["rgb_map"]).max() <= 1e-4
+    assert np.abs(acc.detach().cpu().numpy() - g["acc_map"]).max() <= 1e-4
+    assert np.abs(depth.cpu().numpy() - g["depth_map"]).max() <= 1e-4
+    assert np.abs(alpha[:32].detach().cpu().numpy() - g["alpha_rows"]).max() <= 1e-5
+    assert np.abs(alpha.detach().double().sum(-1).cpu().numpy() - g["alpha_sum"]).max() <= 1e-3
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5
+    for name, p in zip(GRAD_NAMES, _module_params(m)):
+        assert p.grad is not None, name
+        gr = p.grad.detach().cpu().reshape(-1).numpy()
+        idx, val = g[f"g_idx/{name}"], g[f"g_val/{name}"]
+        scale = np.abs(val).max()
+        assert scale > 0, name
+        assert np.abs(gr[idx] - val).max() <= 3e-3 * scale, (name, np.abs(gr[idx] - val).max(), scale)
+        l2 = float(np.linalg.norm(gr.astype(np.float64)))
+        assert abs(l2 - float(g[f"g_l2/{name}"])) <= 2e-3 * float(g[f"g_l2/{name}"]), name
+    m.zero_grad()
+
+
+def test_pose_gradients_match_reference_golden(lego, dev):
+    """inerf/estimate_pose_inerf.py:164-178: frozen factors, random background, MSE, gradient w.r.t. the rays."""
+    fld, rays, m = lego
+    g = H.golden("c5_pose")
+    sub, _ = fx.subsample(rays, 512, seed=2)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    try:
+        r = sub.to(dev).requires_grad_(True)
+        rgb, _, acc, _, _, _ = m(r, bg_color=torch.from_numpy(g["bg"]).to(dev), is_train=False)
+        loss = torch.mean((rgb - torch.from_numpy(g["target"]).to(dev)) ** 2)
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        for p in m.parameters():
+            p.requires_grad_(True)
+    assert np.abs(rgb.detach().cpu().numpy() - g["rgb_map"]).max() <= 1e-4
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6
+    ref = g["d_rays"]
+    scale = np.abs(ref).max()
+    got = r.grad.cpu().numpy()
+    assert got.shape == ref.shape and scale > 0
+    assert np.abs(got - ref).max() <= 5e-3 * scale, (np.abs(got - ref).max(), scale)
+
+
+def _pose_rays(base_c2w, w, t, dirs, radii):
+    """Minimal SE(3) perturbation (stand-in for inerf.CameraTransfer): c2w = [exp(skew(w)) R | p + t]."""
+    zero = torch.zeros((), dtype=w.dtype, device=w.device)
+    K = torch.stack([torch.stack([zero, -w[2], w[1]]), torch.stack([w[2], zero, -w[0]]),
+                     torch.stack([-w[1], w[0], zero])])
+    R = torch.linalg.matrix_exp(K) @ base_c2w[:3, :3]
+    d = dirs @ R.T
+    d = d / d.norm(dim=-1, keepdim=True)
+    o = (base_c2w[:3, 3] + t).expand_as(d)
+    return torch.cat([o, d, radii], -1)
+
+
+def test_batched_candidate_poses_chain_to_pose_parameters(dev):
+    """BASELINE config 5 shape (scaled down): several candidate poses rendered in ONE call; d(loss)/d(pose
+    parameters) through torch autograd + the renderer's d(rays) equals the oracle's autograd."""
+    fld = fx.make_field([128] * 3, density_shift=0.0, holes_seed=1)
+    m = H.module_from_field(fld, dev)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    n_pose, n_pix = 6, 48
+    gen = torch.Generator().manual_seed(55176280)
+    dirs = torch.cat([0.25 * (torch.rand(n_pix, 2, generator=gen) - 0.5), torch.ones(n_pix, 1)], -1)
+    radii = torch.full((n_pix, 1), 1e-3)
+    bases = [fx.orbit_pose(20.0 + 50.0 * i, 25.0, 4.0) for i in range(n_pose)]
+    w0 = 0.02 * torch.randn(n_pose, 3, generator=gen)
+    t0 = 0.02 * torch.randn(n_pose, 3, generator=gen)
+    target = torch.rand(n_pose * n_pix, 3, generator=gen)
+    bg = torch.tensor([0.3, 0.6, 0.1])
+
+    def run(device, render):
+        w = w0.clone().to(device).requires_grad_(True)
+        t = t0.clone().to(device).requires_grad_(True)
+        rays = torch.cat([_pose_rays(bases[i].to(device), w[i], t[i], dirs.to(device), radii.to(device))
+                          for i in range(n_pose)])
+        rgb = render(rays)
+        loss = torch.mean((rgb - target.to(device)) ** 2)
+        loss.backward()
+        return loss.item(), w.grad.cpu(), t.grad.cpu()
+
+    l_ref, gw_ref, gt_ref = run("cpu", lambda r: orc.render_chunk(fld, r, bg_color=bg)["rgb_map"])
+    l_gpu, gw, gt = run(dev, lambda r: m(r, bg_color=bg.to(dev), is_train=False)[0])
+    assert abs(l_ref - l_gpu) <= 1e-6
+    for a, b in ((gw, gw_ref), (gt, gt_ref)):
+        scale = b.abs().max().item()
+        assert scale > 0 and (a - b).abs().max().item() <= 1e-2 * scale, ((a - b).abs().max().item(), scale)
