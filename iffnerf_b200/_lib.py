@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtvm_b200.so")
+# TVM_B200_LIB lets the tuning scripts load a differently-compiled build of the SAME sources
+LIB_PATH = os.environ.get("TVM_B200_LIB") or os.path.join(_HERE, "libtvm_b200.so")
 
 ABI_VERSION = 3
 

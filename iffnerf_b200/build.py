@@ -37,17 +37,21 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(verbose=False, force=False):
-    if not force and not is_stale():
+def build(verbose=False, force=False, defines=(), out=None):
+    """defines/out: build a tuning variant (e.g. defines=["TVM_MARCH_MIN_BLOCKS=6"]) next to the default library."""
+    if out is None and os.environ.get("TVM_B200_LIB"):
+        return os.environ["TVM_B200_LIB"]
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    out = out or LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + \
+        ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libtvm_b200.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -20,8 +20,17 @@
 
 namespace {
 
-constexpr int MARCH_WARPS = 4;
-constexpr int MARCH_RAYS_PER_CTA = 32;
+#ifndef TVM_MARCH_WARPS
+#define TVM_MARCH_WARPS 4
+#endif
+#ifndef TVM_MARCH_RAYS_PER_CTA
+#define TVM_MARCH_RAYS_PER_CTA 32
+#endif
+#ifndef TVM_MARCH_MIN_BLOCKS
+#define TVM_MARCH_MIN_BLOCKS 4
+#endif
+constexpr int MARCH_WARPS = TVM_MARCH_WARPS;
+constexpr int MARCH_RAYS_PER_CTA = TVM_MARCH_RAYS_PER_CTA;
 constexpr unsigned FULL = 0xffffffffu;
 
 struct MarchArgs {
@@ -57,7 +66,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 template <int G, bool MASK_ONLY>
-__global__ void __launch_bounds__(MARCH_WARPS * 32) march_fwd_kernel(const __grid_constant__ MarchArgs a) {
+__global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_fwd_kernel(const __grid_constant__ MarchArgs a) {
     __shared__ int s_next;
     __shared__ float4 s_slot[MARCH_WARPS][32];
     __shared__ float s_ret[MARCH_WARPS][32];
@@ -228,8 +237,8 @@ int fill_args(MarchArgs& a, const tvm_field_desc* desc, const float* rays, int64
               int n_samples, const float* jitter) {
     int rc = tvm_check_desc(desc);
     if (rc) return rc;
-    if (!rays) return TVM_E_NULL;
     if (ray_stride < 6 || n_samples <= 0 || n_rays < 0) return TVM_E_SHAPE;
+    if (!rays && n_rays > 0) return TVM_E_NULL;
     a = MarchArgs{};
     a.f = *desc;
     a.rays = rays; a.n_rays = n_rays; a.ray_stride = ray_stride; a.S = n_samples; a.jitter = jitter;
@@ -271,6 +280,7 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
     MarchArgs a;
     int rc = fill_args(a, desc, rays, n_rays, ray_stride, n_samples, jitter);
     if (rc) return rc;
+    if (n_rays == 0) return 0;
     if (!desc->factors) return TVM_E_NULL;
     if (!ws) return TVM_E_NULL;
     const TvmWorkspace w = tvm_ws_layout(desc, n_rays);

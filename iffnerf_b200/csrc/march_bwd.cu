@@ -289,9 +289,9 @@ extern "C" int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int6
                              void* stream) {
     int rc = tvm_check_desc(desc);
     if (rc) return rc;
-    if (!rays || !ws || !desc->factors) return TVM_E_NULL;
     if (ray_stride < 6 || n_samples <= 0 || n_rays < 0) return TVM_E_SHAPE;
     if (n_rays == 0 || (!g_factors && !g_rays)) return 0;
+    if (!rays || !ws || !desc->factors) return TVM_E_NULL;
     const TvmWorkspace w = tvm_ws_layout(desc, n_rays);
     if (ws_bytes < w.total) return TVM_E_WORKSPACE;
     BwdArgs a{};

@@ -209,11 +209,11 @@ extern "C" int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int6
                              size_t ws_bytes, void* stream) {
     int rc = tvm_check_desc(desc);
     if (rc) return rc;
+    if (n_rays == 0) return 0;
     if (!rays || !rgb || !ws || !desc->basis || !desc->mlp || !bg) return TVM_E_NULL;
     if (desc->feature_c != FC) return TVM_E_SHAPE;
     if (desc->app_dim > 32 || desc->app_dim <= 0) return TVM_E_SHAPE;
     if (flags & TVM_F_MLP_BF16) return TVM_E_MODE;   // tensor-core variant not built into this library yet
-    if (n_rays == 0) return 0;
     const TvmWorkspace w = tvm_ws_layout(desc, n_rays);
     if (ws_bytes < w.total) return TVM_E_WORKSPACE;
     const TvmMlpLayout m = tvm_mlp_layout(desc);

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Quick device-side timing of the march / shade kernels on the bench workload (tuning aid, not the official bench).
+    TVM_B200_LIB=path/to/variant.so python scripts/bench_march.py [--steps K] [--no-early]"""
+import argparse, ctypes as C, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from iffnerf_b200 import _lib
+from oracle import fixtures as fx
+from tests import helpers as H
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--no-early", action="store_true")
+ap.add_argument("--tag", default=os.environ.get("TVM_B200_LIB", "default"))
+a = ap.parse_args()
+dev = torch.device("cuda:0")
+fld = fx.make_field([300] * 3, density_shift=0.0)
+m = H.module_from_field(fld, dev)
+rays = fx.config2_rays().to(dev)
+n, S = rays.shape[0], m.nSamples
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+lib = _lib.load()
+d, keep = m.field_desc()
+need = C.c_size_t(0)
+lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need))
+ws = torch.empty((need.value,), dtype=torch.uint8, device=dev)
+bg = m._bg(None, True, dev)
+rgb = torch.empty((n, 3), device=dev); depth = torch.empty(n, device=dev); acc = torch.empty(n, device=dev)
+st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+fl = 0 if a.no_early else _lib.F_EARLY_TERM
+
+def march():
+    _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, None, _lib.ptr(bg), fl | _lib.F_NO_SHADE,
+                                  None, None, None, None, None, None, None, None, None, _lib.ptr(ws), ws.numel(), st), "march")
+def shade():
+    _lib.check(lib.tvm_shade_fwd(C.byref(d), _lib.ptr(rays), n, rays.shape[1], _lib.ptr(bg), 0, _lib.ptr(rgb), _lib.ptr(depth),
+                                 _lib.ptr(acc), _lib.ptr(ws), ws.numel(), st), "shade")
+def timeit(fn):
+    fn(); fn(); torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(a.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / a.steps
+print(json.dumps({"tag": a.tag, "march_ms": round(timeit(march), 4), "shade_ms": round(timeit(shade), 4), "early": not a.no_early}))
