@@ -69,6 +69,10 @@ class _March(torch.autograd.Function):
                    "tvm_march_bwd")
         grads = [None] * 12
         if want_factors:
+            sync = getattr(model, "grad_sync", None)
+            if sync is not None:
+                # data parallel: ONE all-reduce of the flat packed buffer, on this stream, before unpacking
+                sync.reduce_packed_factor_grads(g_packed)
             planes, lines = model._factor_params()
             gp = [torch.empty_like(p) for p in planes]
             gl = [torch.empty_like(p) for p in lines]

@@ -1,0 +1,121 @@
+"""Ray-sharded data parallelism across the GPUs of one box (one process per GPU, torch.distributed).
+
+The reference is single-GPU; this is the B200-native addition of SURVEY.md 8e:
+  * factors + MLP are replicated (69.5 MB at 300^3), rays are the sharded unit;
+  * forward/eval needs NO data-path collective — each rank renders its tiles and the results are
+    written back at their original offsets (optionally all-gathered, 16 B/ray);
+  * tiles are dealt round-robin (cyclic) because contiguous image rows are badly load-imbalanced
+    (background rays leave the field at the occupancy test, object rays march hundreds of samples);
+  * training all-reduces ONE flat fp32 bucket — the packed factor-gradient buffer the backward kernel
+    scatters into — over NCCL/NVLink, on the stream the kernel ran on, before it is unpacked into the
+    reference-layout .grad tensors; basis/MLP gradients (90 KB) go in a second small bucket.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+DEFAULT_TILE = 4096
+
+
+def shard_tiles(n_rays: int, world: int, rank: int, tile: int = DEFAULT_TILE) -> List[Tuple[int, int]]:
+    """[start, stop) ray ranges owned by `rank`: tile t belongs to rank t % world."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    n_tiles = (n_rays + tile - 1) // tile
+    return [(t * tile, min((t + 1) * tile, n_rays)) for t in range(rank, n_tiles, world)]
+
+
+def shard_index(n_rays: int, world: int, rank: int, tile: int = DEFAULT_TILE, device=None) -> torch.Tensor:
+    """Flat ray indices owned by `rank` (concatenation of its tiles, ascending)."""
+    parts = [torch.arange(a, b, device=device) for a, b in shard_tiles(n_rays, world, rank, tile)]
+    return torch.cat(parts) if parts else torch.empty(0, dtype=torch.long, device=device)
+
+
+def local_rays(rays: torch.Tensor, world: int, rank: int, tile: int = DEFAULT_TILE) -> Tuple[torch.Tensor, torch.Tensor]:
+    idx = shard_index(rays.shape[0], world, rank, tile, device=rays.device)
+    return rays.index_select(0, idx), idx
+
+
+def render_sharded(rays, tensorf, renderer, group=None, tile: int = DEFAULT_TILE, gather: bool = True,
+                   device=None, **render_kw):
+    """Renders this rank's cyclic tiles of `rays` with `renderer` (OctreeRender_trilinear_fast signature) and
+    returns (rgb [N,3], depth [N]) for ALL rays when `gather` (every rank gets the full image), else the local
+    slice plus its ray indices.  No collective touches the render itself."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = rays.shape[0]
+    mine, idx = local_rays(rays, world, rank, tile)
+    kw = dict(render_kw)
+    if device is not None:
+        kw["device"] = device
+    rgb, _, depth, _, _ = renderer(mine, tensorf, **kw)
+    if not gather or world == 1:
+        if world == 1:
+            return rgb, depth
+        return rgb, depth, idx
+    # equal-sized payloads for all_gather_into_tensor: pad every shard to the largest one
+    per = max(len(shard_index(n, world, r, tile)) for r in range(world))
+    payload = torch.zeros((per, 4), dtype=rgb.dtype, device=rgb.device)
+    payload[: rgb.shape[0], :3] = rgb
+    payload[: rgb.shape[0], 3] = depth
+    full = torch.empty((world * per, 4), dtype=rgb.dtype, device=rgb.device)
+    dist.all_gather_into_tensor(full, payload, group=group)
+    out = torch.empty((n, 4), dtype=rgb.dtype, device=rgb.device)
+    for r in range(world):
+        ridx = shard_index(n, world, r, tile, device=rgb.device)
+        out[ridx] = full[r * per: r * per + ridx.numel()]
+    return out[:, :3].contiguous(), out[:, 3].contiguous()
+
+
+class GradSync:
+    """All-reduce (SUM or MEAN) of the gradient buckets of a replicated TensorVMSplit.
+
+    Attach with `GradSync(model, group).install()`: the packed factor-gradient buffer is reduced inside the
+    autograd backward (before it is unpacked), and `finish()` — called after loss.backward() — reduces the
+    small basis/MLP bucket.  With losses normalised by the LOCAL ray count use average=True (global mean)."""
+
+    def __init__(self, model, group=None, average: bool = True):
+        self.model, self.group, self.average = model, group, average
+        self.calls = 0
+        self.bytes = 0
+
+    def install(self):
+        self.model.grad_sync = self
+        return self
+
+    def remove(self):
+        self.model.grad_sync = None
+
+    def _reduce(self, flat: torch.Tensor):
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return flat
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        if self.average:
+            flat.div_(dist.get_world_size(self.group))
+        self.calls += 1
+        self.bytes += flat.numel() * flat.element_size()
+        return flat
+
+    def reduce_packed_factor_grads(self, g_packed: torch.Tensor):
+        """Called by the backward with the flat packed factor-gradient buffer (in place)."""
+        return self._reduce(g_packed)
+
+    def small_params(self):
+        m = self.model
+        return [m.basis_mat.weight] + list(m.renderModule.parameters())
+
+    def finish(self):
+        """Reduce basis_mat + MLP gradients as one flat bucket (call once per step, after backward)."""
+        ps = [p for p in self.small_params() if p.grad is not None]
+        if not ps:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        self._reduce(flat)
+        off = 0
+        for p in ps:
+            k = p.grad.numel()
+            p.grad.copy_(flat[off:off + k].view_as(p.grad))
+            off += k

@@ -161,7 +161,7 @@ class TensorVMSplit(torch.nn.Module):
         self._mlp_packed = None
         self._mlp_key = None
         self._bg_cache = {}
-        self.last_stats = None
+        self.grad_sync = None      # sharding.GradSync when training data-parallel
 
     # ------------------------------------------------------------------ geometry
     def update_stepSize(self, gridSize):
