@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_B200_LIB lets the tuning scripts load a differently-compiled build of the SAME sources
 LIB_PATH = os.environ.get("TVM_B200_LIB") or os.path.join(_HERE, "libtvm_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 F_EARLY_TERM = 1 << 0
 F_MLP_BF16 = 1 << 1
@@ -36,6 +36,7 @@ class FieldDesc(C.Structure):
         ("dplane_off", _l3), ("dline_off", _l3), ("aplane_off", _l3), ("aline_off", _l3),
         ("n_factor_floats", C.c_int64),
         ("occ_cells", C.c_void_p), ("occ_dims", _i3), ("occ_lo", _f3), ("occ_inv", _f3),
+        ("occ_coarse", C.c_void_p), ("occ_cdims", _i3),
         ("factors", C.c_void_p), ("basis", C.c_void_p), ("mlp", C.c_void_p),
     ]
 
@@ -52,6 +53,8 @@ _SIGNATURES = {
     "tvm_error_string": (C.c_char_p, [C.c_int]),
     "tvm_pack_factors": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(_P), C.POINTER(_P), _P, _P]),
     "tvm_unpack_factor_grads": (C.c_int, [C.POINTER(FieldDesc), _P, C.POINTER(_P), C.POINTER(_P), C.c_int, _P]),
+    "tvm_occupancy_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "tvm_occupancy_coarse_offset": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "tvm_pack_occupancy": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "tvm_mlp_pack_floats": (C.c_size_t, [C.POINTER(FieldDesc)]),
     "tvm_pack_mlp": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtvm_b200.so")
 SOURCES = ["pack.cu", "march.cu", "march_bwd.cu", "shade.cu"]
-HEADERS = ["tvm_math.cuh", "tvm_common.cuh", "tvm_gather.cuh", os.path.join("..", "..", "include", "tvm_b200.h")]
+HEADERS = ["tvm_math.cuh", "tvm_common.cuh", "tvm_gather.cuh", "tvm_warp.cuh", os.path.join("..", "..", "include", "tvm_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

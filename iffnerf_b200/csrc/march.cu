@@ -17,6 +17,7 @@
 // distributed over the quad lanes, so the reference's [N,S,27] temporary never exists.
 #include "tvm_common.cuh"
 #include "tvm_gather.cuh"
+#include "tvm_warp.cuh"
 
 namespace {
 
@@ -65,7 +66,7 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-template <int G, bool MASK_ONLY>
+template <int G, bool MASK_ONLY, int CS4, int CA4>
 __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_fwd_kernel(const __grid_constant__ MarchArgs a) {
     __shared__ int s_next;
     __shared__ float4 s_slot[MARCH_WARPS][32];
@@ -97,26 +98,34 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
 
         float T = 1.f, acc = 0.f, dep = 0.f;
         int n_valid = 0, n_sigma = 0, n_app = 0, n_occ = 0;
-        bool dead = false, seen_inside = false;
+        bool dead = false;
         float4 A[3][G];
 #pragma unroll
         for (int k = 0; k < 3; ++k)
 #pragma unroll
             for (int g = 0; g < G; ++g) A[k][g] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+        // empty-space skip mask (exact): blocks whose end-sample box misses the aabb / every occupied super-cell
+        const TvmBlockMask bm = tvm_block_prepass(f, ray, S, lane);
+        if (a.valid_bits)
+            for (int w = lane; w < words; w += 32)
+                if (!bm.test(w)) a.valid_bits[r * words + w] = 0u;
+
         for (int i0 = 0; i0 < S; i0 += 32) {
+            const bool flagged = bm.test(i0 >> 5);
+            if (!flagged && !sample_out) continue;
             const int i = i0 + lane;
             const bool in_range = i < S;
             const float z = tvm_sample_z(f, ray, i);
             float p[3];
-            const bool inside = tvm_sample_point(f, ray, z, p) && in_range;
+            const bool inside = flagged && tvm_sample_point(f, ray, z, p) && in_range;
             bool keep = inside;
             if (f.occ_cells != nullptr && inside) keep = tvm_occupancy_keep(f, p);
             const unsigned imask = __ballot_sync(FULL, inside);
             const unsigned vmask = __ballot_sync(FULL, keep);
             n_valid += __popc(vmask);
             n_occ += __popc(imask);
-            if (a.valid_bits && lane == 0) a.valid_bits[r * words + (i0 >> 5)] = vmask;
+            if (a.valid_bits && flagged && lane == 0) a.valid_bits[r * words + (i0 >> 5)] = vmask;
 
             float alpha = 0.f, dist = 0.f;
             if (!MASK_ONLY) {
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                         if (ci < nv) {
                             const float4 s = s_slot[warp][ci];
                             const float q[3] = {s.x, s.y, s.z};
-                            part = density_partial(f, q, sub);
+                            part = density_partial<CS4>(f, q, sub);
                         }
                         part += __shfl_xor_sync(FULL, part, 1);
                         part += __shfl_xor_sync(FULL, part, 2);
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                             if (ci < na) {
                                 const float4 s = s_slot[warp][ci];
                                 const float q[3] = {s.x, s.y, s.z};
-                                app_accumulate<G>(f, q, s.w, sub, A);
+                                app_accumulate<G, CA4>(f, q, s.w, sub, A);
                             }
                         }
                         __syncwarp();
@@ -188,16 +197,9 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                     if (a.dists) a.dists[o] = dist;
                 }
             }
-            // the in-aabb samples of a ray form ONE interval (o + d*z is monotone in z in fp32 too),
-            // so once it has been left nothing further can be valid
-            if (imask) seen_inside = true;
-            else if (seen_inside && !visit_all) break;
             if (dead && !visit_all && !a.valid_count) break;
         }
 
-        if (visit_all && a.valid_bits) {
-            // (nothing to do: every word was written in the loop)
-        }
         if (lane == 0) {
             if (a.valid_count) a.valid_count[r] = n_valid;
             if (a.occ_count) a.occ_count[r] = n_occ;
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                         v.z += __shfl_xor_sync(FULL, v.z, o); v.w += __shfl_xor_sync(FULL, v.w, o);
                     }
                     const int j = sub + 4 * g;
-                    if (quad == 0 && j < (f.n_app[k] >> 2))
+                    if (quad == 0 && j < (CA4 > 0 ? CA4 : (f.n_app[k] >> 2)))
                         reinterpret_cast<float4*>(a.ray_feat + r * a.ta + a.app_off[k])[j] = v;
                 }
             if (lane == 0) {
@@ -237,7 +239,7 @@ int fill_args(MarchArgs& a, const tvm_field_desc* desc, const float* rays, int64
               int n_samples, const float* jitter) {
     int rc = tvm_check_desc(desc);
     if (rc) return rc;
-    if (ray_stride < 6 || n_samples <= 0 || n_rays < 0) return TVM_E_SHAPE;
+    if (ray_stride < 6 || n_samples <= 0 || n_samples > 32 * TVM_MAX_BLOCKS || n_rays < 0) return TVM_E_SHAPE;
     if (!rays && n_rays > 0) return TVM_E_NULL;
     a = MarchArgs{};
     a.f = *desc;
@@ -269,7 +271,7 @@ extern "C" int tvm_sample_mask(const tvm_field_desc* desc, const float* rays, in
     if (rc) return rc;
     a.valid_bits = valid_bits;
     a.valid_count = counts;
-    return launch(march_fwd_kernel<1, true>, a, (cudaStream_t)stream);
+    return launch(march_fwd_kernel<1, true, 0, 0>, a, (cudaStream_t)stream);
 }
 
 // march stage of tvm_render_fwd (shade.cu finishes the job)
@@ -297,7 +299,10 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
     a.occ_count = (int*)(base + w.occ_count);
     int gmax = 0;
     for (int k = 0; k < 3; ++k) gmax = max(gmax, (desc->n_app[k] + 15) / 16);
-    if (gmax <= 1) return launch(march_fwd_kernel<1, false>, a, st);
-    if (gmax == 2) return launch(march_fwd_kernel<2, false>, a, st);
-    return launch(march_fwd_kernel<3, false>, a, st);
+    bool lego = true;     // the reference configs: 16 density / 48 appearance components on every plane
+    for (int k = 0; k < 3; ++k) lego = lego && desc->n_sigma[k] == 16 && desc->n_app[k] == 48;
+    if (lego) return launch(march_fwd_kernel<3, false, 4, 12>, a, st);
+    if (gmax <= 1) return launch(march_fwd_kernel<1, false, 0, 0>, a, st);
+    if (gmax == 2) return launch(march_fwd_kernel<2, false, 0, 0>, a, st);
+    return launch(march_fwd_kernel<3, false, 0, 0>, a, st);
 }

@@ -14,6 +14,7 @@
 // reductions (red.global.add.v4.f32), one per (corner, float4 channel slice).
 #include "tvm_common.cuh"
 #include "tvm_gather.cuh"
+#include "tvm_warp.cuh"
 
 namespace {
 
@@ -50,7 +51,7 @@ __device__ __forceinline__ float quad_sum(float v) {
     return v;
 }
 
-template <int G, bool SCATTER, bool POSE>
+template <int G, bool SCATTER, bool POSE, int CS4, int CA4>
 __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_constant__ BwdArgs a) {
     __shared__ int s_next;
     __shared__ float4 s_slot[BWD_WARPS][32];
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
             for (int g = 0; g < G; ++g) {
                 const int j = sub + 4 * g;
                 gF[k][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (a.d_ray_feat && j < (f.n_app[k] >> 2)) {
+                if (a.d_ray_feat && j < (CA4 > 0 ? CA4 : (f.n_app[k] >> 2))) {
                     gF[k][g] = __ldg(reinterpret_cast<const float4*>(a.d_ray_feat + r * a.ta + a.app_off[k]) + j);
                     const float4 Fv = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * a.ta + a.app_off[k]) + j);
                     total += f4_dot(gF[k][g], Fv);
@@ -98,9 +99,10 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
 
         float T = 1.f, run = 0.f;
         float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};   // sum dL/dp and sum z*dL/dp (sub==0 lanes)
-        bool seen_inside = false;
+        const TvmBlockMask bm = tvm_block_prepass(f, ray, S, lane);
 
         for (int i0 = 0; i0 < S; i0 += 32) {
+            if (!bm.test(i0 >> 5)) continue;
             const int i = i0 + lane;
             const bool in_range = i < S;
             const float z = tvm_sample_z(f, ray, i);
@@ -108,7 +110,6 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
             const bool inside = tvm_sample_point(f, ray, z, p) && in_range;
             bool keep = inside;
             if (f.occ_cells != nullptr && inside) keep = tvm_occupancy_keep(f, p);
-            const unsigned imask = __ballot_sync(FULL, inside);
             const unsigned vmask = __ballot_sync(FULL, keep);
             if (vmask) {
                 float n[3];
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
                     if (ci < nv) {
                         const float4 s = s_slot[warp][ci];
                         const float q[3] = {s.x, s.y, s.z};
-                        part = density_partial(f, q, sub);
+                        part = density_partial<CS4>(f, q, sub);
                     }
                     part = quad_sum(part);
                     if (sub == 0 && ci < nv) s_ret[warp][ci] = part;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
                         if (ci < na) {
                             const float4 s = s_slot[warp][ci];
                             const float q[3] = {s.x, s.y, s.z};
-                            dot = app_bwd<G, SCATTER, POSE>(f, q, s.w, sub, gF, a.g_factors, dn);
+                            dot = app_bwd<G, SCATTER, POSE, CA4>(f, q, s.w, sub, gF, a.g_factors, dn);
                         }
                         dot = quad_sum(dot);
                         if (POSE) {
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
                         if (ci < nd) {
                             const float4 s = s_slot[warp][ci];
                             const float q[3] = {s.x, s.y, s.z};
-                            density_bwd<SCATTER, POSE>(f, q, s.w, sub, a.g_factors, dn);
+                            density_bwd<SCATTER, POSE, CS4>(f, q, s.w, sub, a.g_factors, dn);
                         }
                         if (POSE) {
 #pragma unroll
@@ -231,8 +232,6 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
                     __syncwarp();
                 }
             }
-            if (imask) seen_inside = true;
-            else if (seen_inside) break;
         }
 
         if (POSE && a.g_rays) {
@@ -270,13 +269,13 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
     }
 }
 
-template <int G>
+template <int G, int CS4, int CA4>
 int dispatch(const BwdArgs& a, cudaStream_t st) {
     const long long ctas = (a.n_rays + BWD_RAYS_PER_CTA - 1) / BWD_RAYS_PER_CTA;
     const bool scatter = a.g_factors != nullptr, pose = a.g_rays != nullptr;
-    if (scatter && pose) march_bwd_kernel<G, true, true><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a);
-    else if (scatter) march_bwd_kernel<G, true, false><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a);
-    else if (pose) march_bwd_kernel<G, false, true><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a);
+    if (scatter && pose) march_bwd_kernel<G, true, true, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a);
+    else if (scatter) march_bwd_kernel<G, true, false, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a);
+    else if (pose) march_bwd_kernel<G, false, true, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a);
     TVM_LAUNCH_CHECK();
     return 0;
 }
@@ -289,7 +288,7 @@ extern "C" int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int6
                              void* stream) {
     int rc = tvm_check_desc(desc);
     if (rc) return rc;
-    if (ray_stride < 6 || n_samples <= 0 || n_rays < 0) return TVM_E_SHAPE;
+    if (ray_stride < 6 || n_samples <= 0 || n_samples > 32 * TVM_MAX_BLOCKS || n_rays < 0) return TVM_E_SHAPE;
     if (n_rays == 0 || (!g_factors && !g_rays)) return 0;
     if (!rays || !ws || !desc->factors) return TVM_E_NULL;
     const TvmWorkspace w = tvm_ws_layout(desc, n_rays);
@@ -306,7 +305,10 @@ extern "C" int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int6
     int gmax = 0;
     for (int k = 0; k < 3; ++k) gmax = max(gmax, (desc->n_app[k] + 15) / 16);
     cudaStream_t st = (cudaStream_t)stream;
-    if (gmax <= 1) return dispatch<1>(a, st);
-    if (gmax == 2) return dispatch<2>(a, st);
-    return dispatch<3>(a, st);
+    bool lego = true;
+    for (int k = 0; k < 3; ++k) lego = lego && desc->n_sigma[k] == 16 && desc->n_app[k] == 48;
+    if (lego) return dispatch<3, 4, 12>(a, st);
+    if (gmax <= 1) return dispatch<1, 0, 0>(a, st);
+    if (gmax == 2) return dispatch<2, 0, 0>(a, st);
+    return dispatch<3, 0, 0>(a, st);
 }

@@ -67,6 +67,21 @@ __global__ void occupancy_cells_kernel(const float* __restrict__ vol, int dx, in
     cells[i] = (uint8_t)code;
 }
 
+// one warp per 16^3 super-cell: 1 if any cell code inside is non-zero
+__global__ void occupancy_coarse_kernel(const uint8_t* __restrict__ cells, int dx, int dy, int dz, int cx, int cy,
+                                        int cz, uint8_t* __restrict__ coarse) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= cx * cy * cz) return;
+    const int X = warp % cx, Y = (warp / cx) % cy, Z = warp / (cx * cy);
+    bool any = false;
+    for (int i = lane; i < 4096; i += 32) {
+        const int x = X * 16 + (i & 15), y = Y * 16 + ((i >> 4) & 15), z = Z * 16 + (i >> 8);
+        if (x < dx && y < dy && z < dz && cells[((size_t)z * dy + y) * dx + x]) any = true;
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) coarse[warp] = any ? 1 : 0;
+}
+
 // dst [cols][rows_padded...]: generic small transpose  src [R][Cc] -> dst [Cc (padded to kpad)][R]
 __global__ void transpose_small_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int Cc, int kpad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -154,11 +169,22 @@ extern "C" int tvm_unpack_factor_grads(const tvm_field_desc* desc, const float* 
     return 0;
 }
 
+extern "C" size_t tvm_occupancy_coarse_offset(int dx, int dy, int dz) {
+    return tvm_align((size_t)dx * dy * dz, 16);
+}
+extern "C" size_t tvm_occupancy_bytes(int dx, int dy, int dz) {
+    return tvm_occupancy_coarse_offset(dx, dy, dz) + (size_t)((dx + 15) / 16) * ((dy + 15) / 16) * ((dz + 15) / 16);
+}
+
 extern "C" int tvm_pack_occupancy(const float* volume, int dx, int dy, int dz, uint8_t* cells, void* stream) {
     if (!volume || !cells) return TVM_E_NULL;
     if (dx < 1 || dy < 1 || dz < 1) return TVM_E_SHAPE;
     const long long n = (long long)dx * dy * dz;
     occupancy_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(volume, dx, dy, dz, cells);
+    const int cx = (dx + 15) / 16, cy = (dy + 15) / 16, cz = (dz + 15) / 16;
+    const int warps = cx * cy * cz;
+    occupancy_coarse_kernel<<<(warps * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        cells, dx, dy, dz, cx, cy, cz, cells + tvm_occupancy_coarse_offset(dx, dy, dz));
     TVM_LAUNCH_CHECK();
     return 0;
 }

@@ -23,51 +23,88 @@ TVM_HD float4 f4_fma(float s, float4 a, float4 acc) {
     return acc;
 }
 TVM_HD float4 f4_scale(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
+TVM_HD float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+TVM_HD float f4_dot(float4 a, float4 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w); }
+TVM_HD float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
 
+// Axis tap for a coordinate that lies inside the field's box.  Every marched sample does (it passed the aabb
+// test, so n = (p-lo)*inv-1 is in [-1, 1+1ulp] and idx in [0, size-1(+eps)]); the base index is clamped to size-2
+// so both taps are always in range and no zero-padding masks are needed (at idx == size-1 this yields exactly
+// the zero-padded value; beyond it the difference is O(ulp)).  Same unnormalise formula as ATen
+// (GridSampler.h:31).  `scale` = d(idx)/d(coord).
+struct AxisTap {
+    int i0;
+    float w0, w1;
+};
+TVM_HD AxisTap tvm_axis_tap_inbox(float coord, int size) {
+    const float idx = ((coord + 1.0f) * 0.5f) * (float)(size - 1);
+    AxisTap t;
+    t.i0 = min(max((int)idx, 0), size - 2);
+    t.w1 = idx - (float)t.i0;
+    t.w0 = 1.0f - t.w1;
+    return t;
+}
+struct SampleTaps {
+    AxisTap a[3];        // x, y, z axis of the field grid
+};
+TVM_HD SampleTaps make_sample_taps(const tvm_field_desc& f, const float n[3]) {
+    SampleTaps s;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s.a[c] = tvm_axis_tap_inbox(n[c], f.grid[c]);
+    return s;
+}
+
+// texel offsets (in float4 units, before adding the channel slice j) and weights of plane/line pair k
 struct PlaneTaps {
-    int t00, t01, t10, t11;      // texel indices (row-major y*W+x)
+    int pbase, prow, lbase;      // plane: (y0*W+x0)*C4, W*C4 ; line: l0*C4
     float w00, w01, w10, w11;    // bilinear weights (ATen: nw, ne, sw, se)
-    int l0, l1;                  // line taps
     float lw0, lw1;
 };
-
-TVM_HD PlaneTaps make_taps(const tvm_field_desc& f, const float n[3], int k) {
-    const int W = f.grid[TVM_M0(k)], H = f.grid[TVM_M1(k)], L = f.grid[TVM_V(k)];
-    const TvmTap tx = tvm_axis_tap(n[TVM_M0(k)], W);
-    const TvmTap ty = tvm_axis_tap(n[TVM_M1(k)], H);
-    const TvmTap tl = tvm_axis_tap(n[TVM_V(k)], L);
+TVM_HD PlaneTaps make_taps(const tvm_field_desc& f, const SampleTaps& s, int k, int C4) {
+    const AxisTap& tx = s.a[TVM_M0(k)];
+    const AxisTap& ty = s.a[TVM_M1(k)];
+    const AxisTap& tl = s.a[TVM_V(k)];
+    const int W = f.grid[TVM_M0(k)];
     PlaneTaps p;
-    p.t00 = ty.i0 * W + tx.i0; p.t01 = ty.i0 * W + tx.i1;
-    p.t10 = ty.i1 * W + tx.i0; p.t11 = ty.i1 * W + tx.i1;
+    p.pbase = (ty.i0 * W + tx.i0) * C4;
+    p.prow = W * C4;
+    p.lbase = tl.i0 * C4;
     p.w00 = tx.w0 * ty.w0; p.w01 = tx.w1 * ty.w0; p.w10 = tx.w0 * ty.w1; p.w11 = tx.w1 * ty.w1;
-    p.l0 = tl.i0; p.l1 = tl.i1; p.lw0 = tl.w0; p.lw1 = tl.w1;
+    p.lw0 = tl.w0; p.lw1 = tl.w1;
     return p;
 }
 
 // (plane (x) line) for one float4 channel slice j of a texel with C4 float4s
-TVM_HD float4 vm_product(const float4* __restrict__ P, const float4* __restrict__ Ln,
-                                             const PlaneTaps& t, int C4, int j) {
-    const float4 a = TVM_LDG4(P + t.t00 * C4 + j);
-    const float4 b = TVM_LDG4(P + t.t01 * C4 + j);
-    const float4 c = TVM_LDG4(P + t.t10 * C4 + j);
-    const float4 d = TVM_LDG4(P + t.t11 * C4 + j);
-    const float4 l0 = TVM_LDG4(Ln + t.l0 * C4 + j);
-    const float4 l1 = TVM_LDG4(Ln + t.l1 * C4 + j);
+TVM_HD float4 vm_product(const float4* __restrict__ P, const float4* __restrict__ Ln, const PlaneTaps& t, int C4,
+                         int j) {
+    const float4* pb = P + t.pbase + j;
+    const float4* lb = Ln + t.lbase + j;
+    const float4 a = TVM_LDG4(pb);
+    const float4 b = TVM_LDG4(pb + C4);
+    const float4 c = TVM_LDG4(pb + t.prow);
+    const float4 d = TVM_LDG4(pb + t.prow + C4);
+    const float4 l0 = TVM_LDG4(lb);
+    const float4 l1 = TVM_LDG4(lb + C4);
     float4 pl = f4_scale(t.w00, a);
     pl = f4_fma(t.w01, b, pl); pl = f4_fma(t.w10, c, pl); pl = f4_fma(t.w11, d, pl);
     float4 ln = f4_scale(t.lw0, l0);
     ln = f4_fma(t.lw1, l1, ln);
-    return make_float4(pl.x * ln.x, pl.y * ln.y, pl.z * ln.z, pl.w * ln.w);
+    return f4_mul(pl, ln);
 }
 
 // this lane's share of sigma_feature = sum_k sum_c plane_k[c] * line_k[c]   (tensoRF.py:227-233)
+// CS4 / CA4 template arguments: float4s per texel when all three planes have the same channel count (the
+// lego/truck configs: 16 -> 4, 48 -> 12), which turns the corner / channel-slice offsets into immediates;
+// 0 = read the per-plane counts from the descriptor.
+template <int CS4 = 0>
 TVM_HD float density_partial(const tvm_field_desc& f, const float n[3], int sub) {
     float tot = 0.f;
+    const SampleTaps st = make_sample_taps(f, n);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const int C4 = f.n_sigma[k] >> 2;
+        const int C4 = CS4 > 0 ? CS4 : (f.n_sigma[k] >> 2);
         if (sub < C4) {
-            const PlaneTaps t = make_taps(f, n, k);
+            const PlaneTaps t = make_taps(f, st, k, C4);
             const float4 v = vm_product(reinterpret_cast<const float4*>(f.factors + f.dplane_off[k]),
                                         reinterpret_cast<const float4*>(f.factors + f.dline_off[k]), t, C4, sub);
             tot += (v.x + v.y) + (v.z + v.w);
@@ -77,13 +114,13 @@ TVM_HD float density_partial(const tvm_field_desc& f, const float n[3], int sub)
 }
 
 // A[k][g] += w * (app_plane_k (x) app_line_k)[channels of this lane]   (tensoRF.py:237-254, weighted by :888)
-template <int G>
-TVM_HD void app_accumulate(const tvm_field_desc& f, const float n[3], float w, int sub,
-                                               float4 (&A)[3][G]) {
+template <int G, int CA4 = 0>
+TVM_HD void app_accumulate(const tvm_field_desc& f, const float n[3], float w, int sub, float4 (&A)[3][G]) {
+    const SampleTaps st = make_sample_taps(f, n);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const int C4 = f.n_app[k] >> 2;
-        const PlaneTaps t = make_taps(f, n, k);
+        const int C4 = CA4 > 0 ? CA4 : (f.n_app[k] >> 2);
+        const PlaneTaps t = make_taps(f, st, k, C4);
         const float4* P = reinterpret_cast<const float4*>(f.factors + f.aplane_off[k]);
         const float4* Ln = reinterpret_cast<const float4*>(f.factors + f.aline_off[k]);
 #pragma unroll
@@ -93,7 +130,6 @@ TVM_HD void app_accumulate(const tvm_field_desc& f, const float n[3], float w, i
         }
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // backward: gradient scatter into the packed factor-gradient buffer (same layout as `factors`) and,
@@ -108,88 +144,66 @@ static inline void tvm_host_add4(float4* p, float4 v) { p->x += v.x; p->y += v.y
 #define TVM_RED4(p, v) tvm_host_add4((p), (v))
 #endif
 
-TVM_HD float f4_dot(float4 a, float4 b) { return (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w); }
-TVM_HD float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
-
-struct PlaneTapsG {
-    PlaneTaps t;
-    TvmTap tx, ty, tl;
-};
-TVM_HD PlaneTapsG make_taps_g(const tvm_field_desc& f, const float n[3], int k) {
-    const int W = f.grid[TVM_M0(k)], H = f.grid[TVM_M1(k)], L = f.grid[TVM_V(k)];
-    PlaneTapsG g;
-    g.tx = tvm_axis_tap(n[TVM_M0(k)], W);
-    g.ty = tvm_axis_tap(n[TVM_M1(k)], H);
-    g.tl = tvm_axis_tap(n[TVM_V(k)], L);
-    PlaneTaps& p = g.t;
-    p.t00 = g.ty.i0 * W + g.tx.i0; p.t01 = g.ty.i0 * W + g.tx.i1;
-    p.t10 = g.ty.i1 * W + g.tx.i0; p.t11 = g.ty.i1 * W + g.tx.i1;
-    p.w00 = g.tx.w0 * g.ty.w0; p.w01 = g.tx.w1 * g.ty.w0; p.w10 = g.tx.w0 * g.ty.w1; p.w11 = g.tx.w1 * g.ty.w1;
-    p.l0 = g.tl.i0; p.l1 = g.tl.i1; p.lw0 = g.tl.w0; p.lw1 = g.tl.w1;
-    return g;
-}
-
 // One float4 channel slice j of plane/line pair k: given the upstream gradient `up` on (plane (x) line)[channels],
 // scatter into gP/gL and accumulate d/dn.  Returns (plane (x) line) for this slice.
 template <bool SCATTER, bool POSE>
-TVM_HD float4 vm_slice_bwd(const float4* __restrict__ P, const float4* __restrict__ Ln, float4* __restrict__ gP,
-                           float4* __restrict__ gL, const PlaneTapsG& g, int C4, int j, float4 up, int k,
-                           float dn[3]) {
-    const PlaneTaps& t = g.t;
-    const float4 a = TVM_LDG4(P + t.t00 * C4 + j);
-    const float4 b = TVM_LDG4(P + t.t01 * C4 + j);
-    const float4 c = TVM_LDG4(P + t.t10 * C4 + j);
-    const float4 d = TVM_LDG4(P + t.t11 * C4 + j);
-    const float4 l0 = TVM_LDG4(Ln + t.l0 * C4 + j);
-    const float4 l1 = TVM_LDG4(Ln + t.l1 * C4 + j);
+TVM_HD float4 vm_slice_bwd(const tvm_field_desc& f, const float4* __restrict__ P, const float4* __restrict__ Ln,
+                           float4* __restrict__ gP, float4* __restrict__ gL, const SampleTaps& s, const PlaneTaps& t,
+                           int C4, int j, float4 up, int k, float dn[3]) {
+    const float4* pb = P + t.pbase + j;
+    const float4* lb = Ln + t.lbase + j;
+    const float4 a = TVM_LDG4(pb);
+    const float4 b = TVM_LDG4(pb + C4);
+    const float4 c = TVM_LDG4(pb + t.prow);
+    const float4 d = TVM_LDG4(pb + t.prow + C4);
+    const float4 l0 = TVM_LDG4(lb);
+    const float4 l1 = TVM_LDG4(lb + C4);
     float4 pl = f4_scale(t.w00, a);
     pl = f4_fma(t.w01, b, pl); pl = f4_fma(t.w10, c, pl); pl = f4_fma(t.w11, d, pl);
     float4 ln = f4_scale(t.lw0, l0);
     ln = f4_fma(t.lw1, l1, ln);
+    const float4 up_ln = f4_mul(up, ln);        // d/d(plane value)
+    const float4 up_pl = f4_mul(up, pl);        // d/d(line value)
     if (SCATTER) {
-        const float4 up_ln = f4_mul(up, ln);        // d/d(plane value)
-        const float4 up_pl = f4_mul(up, pl);        // d/d(line value)
-        if (t.w00 != 0.f) TVM_RED4(gP + t.t00 * C4 + j, f4_scale(t.w00, up_ln));
-        if (t.w01 != 0.f) TVM_RED4(gP + t.t01 * C4 + j, f4_scale(t.w01, up_ln));
-        if (t.w10 != 0.f) TVM_RED4(gP + t.t10 * C4 + j, f4_scale(t.w10, up_ln));
-        if (t.w11 != 0.f) TVM_RED4(gP + t.t11 * C4 + j, f4_scale(t.w11, up_ln));
-        if (t.lw0 != 0.f) TVM_RED4(gL + t.l0 * C4 + j, f4_scale(t.lw0, up_pl));
-        if (t.lw1 != 0.f) TVM_RED4(gL + t.l1 * C4 + j, f4_scale(t.lw1, up_pl));
+        float4* gpb = gP + t.pbase + j;
+        float4* glb = gL + t.lbase + j;
+        TVM_RED4(gpb, f4_scale(t.w00, up_ln));
+        TVM_RED4(gpb + C4, f4_scale(t.w01, up_ln));
+        TVM_RED4(gpb + t.prow, f4_scale(t.w10, up_ln));
+        TVM_RED4(gpb + t.prow + C4, f4_scale(t.w11, up_ln));
+        TVM_RED4(glb, f4_scale(t.lw0, up_pl));
+        TVM_RED4(glb + C4, f4_scale(t.lw1, up_pl));
     }
     if (POSE) {
-        // d plane / d ix = wy0*(m1x*b - m0x*a) + wy1*(m1x*d - m0x*c); zero-padded taps contribute 0
-        float4 dx = f4_scale(g.ty.w0, make_float4(g.tx.m1 * b.x - g.tx.m0 * a.x, g.tx.m1 * b.y - g.tx.m0 * a.y,
-                                                  g.tx.m1 * b.z - g.tx.m0 * a.z, g.tx.m1 * b.w - g.tx.m0 * a.w));
-        dx = f4_fma(g.ty.w1, make_float4(g.tx.m1 * d.x - g.tx.m0 * c.x, g.tx.m1 * d.y - g.tx.m0 * c.y,
-                                         g.tx.m1 * d.z - g.tx.m0 * c.z, g.tx.m1 * d.w - g.tx.m0 * c.w), dx);
-        float4 dy = f4_scale(g.tx.w0, make_float4(g.ty.m1 * c.x - g.ty.m0 * a.x, g.ty.m1 * c.y - g.ty.m0 * a.y,
-                                                  g.ty.m1 * c.z - g.ty.m0 * a.z, g.ty.m1 * c.w - g.ty.m0 * a.w));
-        dy = f4_fma(g.tx.w1, make_float4(g.ty.m1 * d.x - g.ty.m0 * b.x, g.ty.m1 * d.y - g.ty.m0 * b.y,
-                                         g.ty.m1 * d.z - g.ty.m0 * b.z, g.ty.m1 * d.w - g.ty.m0 * b.w), dy);
-        const float4 dl = make_float4(g.tl.m1 * l1.x - g.tl.m0 * l0.x, g.tl.m1 * l1.y - g.tl.m0 * l0.y,
-                                      g.tl.m1 * l1.z - g.tl.m0 * l0.z, g.tl.m1 * l1.w - g.tl.m0 * l0.w);
-        dn[TVM_M0(k)] += g.tx.scale * f4_dot(f4_mul(up, ln), dx);
-        dn[TVM_M1(k)] += g.ty.scale * f4_dot(f4_mul(up, ln), dy);
-        dn[TVM_V(k)] += g.tl.scale * f4_dot(f4_mul(up, pl), dl);
+        const AxisTap& tx = s.a[TVM_M0(k)];
+        const AxisTap& ty = s.a[TVM_M1(k)];
+        // d plane/d ix = wy0*(b-a) + wy1*(d-c);  d plane/d iy = wx0*(c-a) + wx1*(d-b);  d line/d il = l1-l0
+        const float4 dx = f4_fma(ty.w1, f4_sub(d, c), f4_scale(ty.w0, f4_sub(b, a)));
+        const float4 dy = f4_fma(tx.w1, f4_sub(d, b), f4_scale(tx.w0, f4_sub(c, a)));
+        const float4 dl = f4_sub(l1, l0);
+        dn[TVM_M0(k)] += 0.5f * (float)(f.grid[TVM_M0(k)] - 1) * f4_dot(up_ln, dx);
+        dn[TVM_M1(k)] += 0.5f * (float)(f.grid[TVM_M1(k)] - 1) * f4_dot(up_ln, dy);
+        dn[TVM_V(k)] += 0.5f * (float)(f.grid[TVM_V(k)] - 1) * f4_dot(up_pl, dl);
     }
     return f4_mul(pl, ln);
 }
 
 // density: upstream dfeat (scalar, same for every channel).  Returns this lane's share of sigma_feature.
-template <bool SCATTER, bool POSE>
+template <bool SCATTER, bool POSE, int CS4 = 0>
 TVM_HD float density_bwd(const tvm_field_desc& f, const float n[3], float dfeat, int sub, float* gbuf, float dn[3]) {
     float tot = 0.f;
     const float4 up = make_float4(dfeat, dfeat, dfeat, dfeat);
+    const SampleTaps st = make_sample_taps(f, n);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const int C4 = f.n_sigma[k] >> 2;
+        const int C4 = CS4 > 0 ? CS4 : (f.n_sigma[k] >> 2);
         if (sub < C4) {
-            const PlaneTapsG g = make_taps_g(f, n, k);
+            const PlaneTaps t = make_taps(f, st, k, C4);
             const float4 v = vm_slice_bwd<SCATTER, POSE>(
-                reinterpret_cast<const float4*>(f.factors + f.dplane_off[k]),
+                f, reinterpret_cast<const float4*>(f.factors + f.dplane_off[k]),
                 reinterpret_cast<const float4*>(f.factors + f.dline_off[k]),
                 SCATTER ? reinterpret_cast<float4*>(gbuf + f.dplane_off[k]) : nullptr,
-                SCATTER ? reinterpret_cast<float4*>(gbuf + f.dline_off[k]) : nullptr, g, C4, sub, up, k, dn);
+                SCATTER ? reinterpret_cast<float4*>(gbuf + f.dline_off[k]) : nullptr, st, t, C4, sub, up, k, dn);
             tot += (v.x + v.y) + (v.z + v.w);
         }
     }
@@ -197,23 +211,24 @@ TVM_HD float density_bwd(const tvm_field_desc& f, const float n[3], float dfeat,
 }
 
 // appearance: upstream on (plane (x) line)[c] is w * gF[c].  Returns this lane's share of gF . phi.
-template <int G, bool SCATTER, bool POSE>
+template <int G, bool SCATTER, bool POSE, int CA4 = 0>
 TVM_HD float app_bwd(const tvm_field_desc& f, const float n[3], float w, int sub, const float4 (&gF)[3][G],
                      float* gbuf, float dn[3]) {
     float dot = 0.f;
+    const SampleTaps st = make_sample_taps(f, n);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const int C4 = f.n_app[k] >> 2;
-        const PlaneTapsG g = make_taps_g(f, n, k);
+        const int C4 = CA4 > 0 ? CA4 : (f.n_app[k] >> 2);
+        const PlaneTaps t = make_taps(f, st, k, C4);
 #pragma unroll
         for (int gi = 0; gi < G; ++gi) {
             const int j = sub + 4 * gi;
             if (j < C4) {
                 const float4 phi = vm_slice_bwd<SCATTER, POSE>(
-                    reinterpret_cast<const float4*>(f.factors + f.aplane_off[k]),
+                    f, reinterpret_cast<const float4*>(f.factors + f.aplane_off[k]),
                     reinterpret_cast<const float4*>(f.factors + f.aline_off[k]),
                     SCATTER ? reinterpret_cast<float4*>(gbuf + f.aplane_off[k]) : nullptr,
-                    SCATTER ? reinterpret_cast<float4*>(gbuf + f.aline_off[k]) : nullptr, g, C4, j,
+                    SCATTER ? reinterpret_cast<float4*>(gbuf + f.aline_off[k]) : nullptr, st, t, C4, j,
                     f4_scale(w, gF[k][gi]), k, dn);
                 dot += f4_dot(gF[k][gi], phi);
             }

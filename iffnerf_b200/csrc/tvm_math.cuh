@@ -116,6 +116,40 @@ TVM_HD bool tvm_occupancy_keep(const tvm_field_desc& f, const float p[3]) {
     return keep;
 }
 
+// Conservative block test used to skip empty space without touching bit-exactness: can ANY of the samples
+// i in [i_first, i_last] be valid?  z_i is monotone in i and every op of o + d*z and of the occupancy
+// unnormalise is monotone in its input, so per axis all sample coordinates / cell indices of the block lie
+// between those of its two end samples.  The block is discarded only if that box misses the aabb, or if every
+// 16^3 super-cell it touches has no occupied corner (occ_coarse, built by tvm_pack_occupancy).
+TVM_HD bool tvm_block_may_be_valid(const tvm_field_desc& f, const TvmRay& r, int i_first, int i_last) {
+    float pa[3], pb[3];
+    tvm_sample_point(f, r, tvm_sample_z(f, r, i_first), pa);
+    tvm_sample_point(f, r, tvm_sample_z(f, r, i_last), pb);
+    int c0[3], c1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float lo = fminf(pa[c], pb[c]), hi = fmaxf(pa[c], pb[c]);
+        if (hi < f.aabb[c] || lo > f.aabb[3 + c]) return false;            // whole block outside the box
+        if (f.occ_cells != nullptr) {
+            const float na = rn_sub(rn_mul(rn_sub(lo, f.occ_lo[c]), f.occ_inv[c]), 1.0f);
+            const float nb = rn_sub(rn_mul(rn_sub(hi, f.occ_lo[c]), f.occ_inv[c]), 1.0f);
+            const float ia = rn_mul(rn_mul(rn_add(na, 1.0f), 0.5f), (float)(f.occ_dims[c] - 1));
+            const float ib = rn_mul(rn_mul(rn_add(nb, 1.0f), 0.5f), (float)(f.occ_dims[c] - 1));
+            const float dmax = (float)(f.occ_dims[c] - 1);
+            // base cells outside [0, D-1] only ever look at the boundary cells (slow path of tvm_occupancy_keep)
+            c0[c] = (int)fminf(fmaxf(floorf(fminf(ia, ib)), 0.0f), dmax) >> 4;
+            c1[c] = (int)fminf(fmaxf(floorf(fmaxf(ia, ib)), 0.0f), dmax) >> 4;
+        }
+    }
+    if (f.occ_cells == nullptr || f.occ_coarse == nullptr) return true;
+    const int cx = f.occ_cdims[0], cy = f.occ_cdims[1];
+    for (int z = c0[2]; z <= c1[2]; ++z)
+        for (int y = c0[1]; y <= c1[1]; ++y)
+            for (int x = c0[0]; x <= c1[0]; ++x)
+                if (f.occ_coarse[((size_t)z * cy + y) * cx + x]) return true;
+    return false;
+}
+
 // normalize_coord (models/tensorBase.py:397): (xyz - aabb0) * invaabbSize - 1
 TVM_HD void tvm_normalize(const tvm_field_desc& f, const float p[3], float n[3]) {
 #pragma unroll

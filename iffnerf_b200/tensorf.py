@@ -72,11 +72,13 @@ class AlphaGridMask(torch.nn.Module):
                 raise _lib.TvmError("AlphaGridMask volume must live on a CUDA device for rendering")
             v = vol.detach().reshape(vol.shape[-3:]).contiguous().float()
             dz, dy, dx = v.shape
-            cells = torch.empty((dz, dy, dx), dtype=torch.uint8, device=v.device)
             lib = _lib.load()
+            cells = torch.empty((lib.tvm_occupancy_bytes(dx, dy, dz),), dtype=torch.uint8, device=v.device)
             _lib.check(lib.tvm_pack_occupancy(_lib.ptr(v), dx, dy, dz, _lib.ptr(cells), _stream(v.device)),
                        "tvm_pack_occupancy")
             self._cells, self._cells_key = cells, key
+            self._cells_dims = (dx, dy, dz)
+            self._coarse_off = int(lib.tvm_occupancy_coarse_offset(dx, dy, dz))
         return self._cells
 
 
@@ -358,8 +360,11 @@ class TensorVMSplit(torch.nn.Module):
             keep += [pf, pm, basis]
         if self.alphaMask is not None:
             cells = self.alphaMask.cells()
+            dx, dy, dz = self.alphaMask._cells_dims
             d.occ_cells = cells.data_ptr()
-            d.occ_dims[:] = [cells.shape[2], cells.shape[1], cells.shape[0]]
+            d.occ_dims[:] = [dx, dy, dz]
+            d.occ_coarse = cells.data_ptr() + self.alphaMask._coarse_off
+            d.occ_cdims[:] = [(dx + 15) // 16, (dy + 15) // 16, (dz + 15) // 16]
             d.occ_lo[:] = self.alphaMask._lo
             d.occ_inv[:] = self.alphaMask._inv
             keep.append(cells)

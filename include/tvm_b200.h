@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 3
+#define TVM_ABI_VERSION 4
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define TVM_E_NULL        (-1)   /* required pointer is NULL                      */
@@ -76,6 +76,8 @@ typedef struct tvm_field_desc {
     int32_t  occ_dims[3];        /* Dx, Dy, Dz                                                             */
     float    occ_lo[3];          /* alphaMask.aabb[0]                                                      */
     float    occ_inv[3];         /* alphaMask.invgridSize = 1/aabbSize*2 (:59)                             */
+    const uint8_t* occ_coarse;   /* [cz][cy][cx] 16^3 super-cells: any occupied corner inside (same buffer)  */
+    int32_t  occ_cdims[3];       /* cx, cy, cz = ceil(D/16)                                                */
     /* device pointers to parameters                                                                       */
     const float* factors;        /* packed factors (layout above)                                          */
     const float* basis;          /* basis_mat.weight [app_dim][sum(n_app)] row-major (torch layout)        */
@@ -96,7 +98,11 @@ int tvm_pack_factors(const tvm_field_desc* desc, const float* const planes[6], c
  * (so torch-side regularisers, train.py:299-325, keep adding into the same .grad). */
 int tvm_unpack_factor_grads(const tvm_field_desc* desc, const float* packed_grad, float* const planes[6],
                             float* const lines[6], int accumulate, void* stream);
-/* alphaMask volume [Dz][Dy][Dx] fp32 (>0 = occupied) -> per-cell 8-corner codes, same dims (bytes). */
+/* alphaMask volume [Dz][Dy][Dx] fp32 (>0 = occupied) -> `cells`: per-cell 8-corner codes [Dz][Dy][Dx] (bytes)
+ * followed, at byte offset tvm_occupancy_coarse_offset(), by the 16^3 super-cell summary [cz][cy][cx] used to
+ * skip empty space.  `cells` must hold tvm_occupancy_bytes() bytes. */
+size_t tvm_occupancy_bytes(int dx, int dy, int dz);
+size_t tvm_occupancy_coarse_offset(int dx, int dy, int dz);
 int tvm_pack_occupancy(const float* volume, int dx, int dy, int dz, uint8_t* cells, void* stream);
 /* MLPRender_Fea weights (torch layout: w1 [C,in], w2 [C,C], w3 [3,C]) -> kernel layout. */
 size_t tvm_mlp_pack_floats(const tvm_field_desc* desc);
@@ -106,7 +112,7 @@ int tvm_pack_mlp(const tvm_field_desc* desc, const float* w1, const float* b1, c
 /* ---- the hot path ---------------------------------------------------------------------------------- */
 
 /* sample_ray + aabb clip + alphaMask test (tensorBase.py:494-536, :832-837), no factor access.
- * rays: [n_rays][ray_stride] fp32 (cols 0-2 origin, 3-5 direction); jitter: NULL (eval) or [n_rays]
+ * n_samples <= 4096.  rays: [n_rays][ray_stride] fp32 (cols 0-2 origin, 3-5 direction); jitter: NULL (eval) or [n_rays]
  * (train, one U[0,1) per ray, :507-509).  valid_bits: [n_rays][ceil(n_samples/32)] little-endian bit i%32
  * of word i/32 = ray_valid[i] (nullable); counts: [n_rays] = popcount (nullable). */
 int tvm_sample_mask(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,

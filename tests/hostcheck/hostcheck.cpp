@@ -21,6 +21,30 @@ extern "C" void hc_pack_occupancy(const float* vol, int dx, int dy, int dz, uint
             }
 }
 
+// coarse[cz][cy][cx]: any non-zero cell code inside the 16^3 super-cell (mirror of occupancy_coarse_kernel)
+extern "C" void hc_pack_coarse(const uint8_t* cells, int dx, int dy, int dz, uint8_t* coarse) {
+    const int cx = (dx + 15) / 16, cy = (dy + 15) / 16, cz = (dz + 15) / 16;
+    memset(coarse, 0, (size_t)cx * cy * cz);
+    for (int z = 0; z < dz; ++z)
+        for (int y = 0; y < dy; ++y)
+            for (int x = 0; x < dx; ++x)
+                if (cells[((size_t)z * dy + y) * dx + x]) coarse[((size_t)(z >> 4) * cy + (y >> 4)) * cx + (x >> 4)] = 1;
+}
+
+// flags[r][b] = tvm_block_may_be_valid for 32-sample block b of ray r (the kernels' empty-space skip test)
+extern "C" void hc_block_flags(const tvm_field_desc* f, const float* rays, long long n, int stride, int S,
+                               const float* jitter, uint8_t* flags) {
+    const int nblk = (S + 31) / 32;
+    for (long long r = 0; r < n; ++r) {
+        TvmRay ray;
+        for (int c = 0; c < 3; ++c) { ray.o[c] = rays[r * stride + c]; ray.d[c] = rays[r * stride + 3 + c]; }
+        ray.t0 = tvm_ray_entry(*f, ray.o, ray.d);
+        ray.jit = jitter ? jitter[r] : 0.f;
+        for (int b = 0; b < nblk; ++b)
+            flags[r * nblk + b] = tvm_block_may_be_valid(*f, ray, b * 32, (b * 32 + 31 < S - 1) ? b * 32 + 31 : S - 1);
+    }
+}
+
 extern "C" void hc_sample_mask(const tvm_field_desc* f, const float* rays, long long n, int stride, int S,
                                const float* jitter, uint32_t* bits, int32_t* counts) {
     const int words = (S + 31) / 32;
@@ -48,6 +72,8 @@ extern "C" void hc_march(const tvm_field_desc* f, const float* rays, long long n
                          int32_t* app_count) {
     const int ta = f->n_app[0] + f->n_app[1] + f->n_app[2];
     const int off[3] = {0, f->n_app[0], f->n_app[0] + f->n_app[1]};
+    bool lego = true;      // exercise the same template specialisation the CUDA dispatch picks
+    for (int k = 0; k < 3; ++k) lego = lego && f->n_sigma[k] == 16 && f->n_app[k] == 48;
     for (long long r = 0; r < n; ++r) {
         TvmRay ray;
         for (int c = 0; c < 3; ++c) { ray.o[c] = rays[r * stride + c]; ray.d[c] = rays[r * stride + 3 + c]; }
@@ -66,7 +92,7 @@ extern "C" void hc_march(const tvm_field_desc* f, const float* rays, long long n
             if (keep) {
                 tvm_normalize(*f, p, nrm);
                 float part[4];
-                for (int sub = 0; sub < 4; ++sub) part[sub] = density_partial(*f, nrm, sub);
+                for (int sub = 0; sub < 4; ++sub) part[sub] = lego ? density_partial<4>(*f, nrm, sub) : density_partial<0>(*f, nrm, sub);
                 const float feat = (part[0] + part[1]) + (part[2] + part[3]);
                 const float sigma = tvm_density(*f, feat);
                 const float dist = (i < S - 1) ? rn_sub(tvm_sample_z(*f, ray, i + 1), z) : 0.f;
@@ -76,7 +102,7 @@ extern "C" void hc_march(const tvm_field_desc* f, const float* rays, long long n
                 dep += w * z;
                 if (w > f->weight_thres) {
                     ++napp;
-                    for (int sub = 0; sub < 4; ++sub) app_accumulate<3>(*f, nrm, w, sub, A[sub]);
+                    for (int sub = 0; sub < 4; ++sub) { if (lego) app_accumulate<3, 12>(*f, nrm, w, sub, A[sub]); else app_accumulate<3, 0>(*f, nrm, w, sub, A[sub]); }
                 }
                 T *= (1.f - alpha + 1e-10f);
             }

@@ -33,11 +33,16 @@ def _host_desc(hc, fld):
         dz, dy, dx = vol.shape
         cells = np.zeros(vol.shape, dtype=np.uint8)
         hc.hc_pack_occupancy(C.c_void_p(vol.ctypes.data), dx, dy, dz, C.c_void_p(cells.ctypes.data))
+        cdims = [(dx + 15) // 16, (dy + 15) // 16, (dz + 15) // 16]
+        coarse = np.zeros(cdims[::-1], dtype=np.uint8)
+        hc.hc_pack_coarse(C.c_void_p(cells.ctypes.data), dx, dy, dz, C.c_void_p(coarse.ctypes.data))
         d.occ_cells = cells.ctypes.data
         d.occ_dims[:] = [dx, dy, dz]
         d.occ_lo[:] = m.alphaMask._lo
         d.occ_inv[:] = m.alphaMask._inv
-        keep.append(cells)
+        d.occ_coarse = coarse.ctypes.data
+        d.occ_cdims[:] = cdims
+        keep += [cells, coarse]
     return m, d, keep
 
 
@@ -85,6 +90,36 @@ def test_sample_mask_bit_exact_noncubic_and_jitter(hc):
         bits, counts = _mask(hc, d, rays, m.nSamples, None if jitter is None else jitter.numpy().reshape(-1))
         assert np.array_equal(H.unpack_bits(bits, m.nSamples), keepm.numpy())
         assert counts.sum() > 0
+
+
+@pytest.mark.parametrize("case", ["c1_mask", "c1_nomask", "c4_jitter"])
+def test_block_skip_flags_are_conservative(hc, case):
+    """The empty-space skip test never discards a 32-sample block that holds a valid sample (so skipping cannot
+    change ray_valid), and it does discard most of the empty ones."""
+    if case == "c1_mask":
+        fld, rays = fx.config1(0.0, "sphere", 6)
+    elif case == "c1_nomask":
+        fld, rays = fx.config1(-10.0, None, 6)
+    else:
+        fld, rays = fx.config4(H=54, W=96)
+    rays = rays[::3].contiguous()
+    m, d, keep = _host_desc(hc, fld)
+    S = m.nSamples
+    jit = None
+    if case == "c4_jitter":
+        torch.manual_seed(9)
+        jit = np.ascontiguousarray(torch.rand(rays.shape[0]).numpy(), dtype=np.float32)
+    bits, counts = _mask(hc, d, rays, S, jit)
+    r = np.ascontiguousarray(rays.numpy(), dtype=np.float32)
+    nblk = (S + 31) // 32
+    flags = np.zeros((r.shape[0], nblk), dtype=np.uint8)
+    hc.hc_block_flags(C.byref(d), C.c_void_p(r.ctypes.data), C.c_longlong(r.shape[0]), r.shape[1], S,
+                      None if jit is None else C.c_void_p(jit.ctypes.data), C.c_void_p(flags.ctypes.data))
+    has_valid = bits != 0                                   # [n, nblk]: block holds at least one valid sample
+    assert not np.any(has_valid & (flags == 0))             # conservative: no valid block is ever skipped
+    assert has_valid.sum() > 0
+    if fld.occupancy is not None:
+        assert flags.sum() <= 3.0 * has_valid.sum() + 2 * r.shape[0]   # ...and the filter is reasonably tight
 
 
 def test_march_math_matches_reference_golden(hc):
