@@ -18,6 +18,9 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
                          uint32_t* valid_bits, int32_t* valid_count, int32_t* app_count, void* ws, size_t ws_bytes,
                          cudaStream_t st);
 
+int tvm_shade_tc_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, const float* bg,
+                        float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes, cudaStream_t st);
+
 namespace {
 
 constexpr int SH_RAYS = 64;
@@ -213,7 +216,9 @@ extern "C" int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int6
     if (!rays || !rgb || !ws || !desc->basis || !desc->mlp || !bg) return TVM_E_NULL;
     if (desc->feature_c != FC) return TVM_E_SHAPE;
     if (desc->app_dim > 32 || desc->app_dim <= 0) return TVM_E_SHAPE;
-    if (flags & TVM_F_MLP_BF16) return TVM_E_MODE;   // tensor-core variant not built into this library yet
+    if (flags & TVM_F_MLP_BF16)                       // tcgen05 bf16 variant (shade_tc.cu), tolerance 1e-2
+        return tvm_shade_tc_launch(desc, rays, n_rays, ray_stride, bg, rgb, depth, acc, ws, ws_bytes,
+                                   (cudaStream_t)stream);
     const TvmWorkspace w = tvm_ws_layout(desc, n_rays);
     if (ws_bytes < w.total) return TVM_E_WORKSPACE;
     const TvmMlpLayout m = tvm_mlp_layout(desc);

@@ -1,0 +1,381 @@
+// shade_tc.cu — tensor-core variant of the per-ray shading stage (flag TVM_F_MLP_BF16).
+//
+// Same math as shade.cu — basis_mat (models/tensoRF.py:158,256), MLPRender_Fea (models/tensorBase.py:165-195),
+// background blend and depth tail (:898-908) — but the four dense contractions
+//     feat = F[128x144] . B^T      h1 = relu(X[128x160] . W1^T + b1)
+//     h2   = relu(h1 . W2^T + b2)  rgb = sigmoid(h2 . W3^T + b3)
+// run on the 5th-gen tensor cores: bf16 operands in shared memory (K-major, no-swizzle canonical core-matrix
+// layout), fp32 accumulators in TMEM, `tcgen05.mma.cta_group::1.kind::f16` issued by one thread, completion
+// signalled through an mbarrier by `tcgen05.commit`, accumulators read back with `tcgen05.ld`.  One persistent
+// CTA per SM owns a 128-ray tile at a time (TMEM lane == ray), keeps all four weight images resident in shared
+// memory, and its 128 threads do the epilogues (positional encoding, bias, ReLU, bf16 repack) between MMAs.
+// bf16 operands bound the result to the 1e-2 tolerance of BASELINE.json's "bf16 MLP mode"; the fp32 SIMT
+// kernel in shade.cu stays the default (1e-4).
+#include <cuda_bf16.h>
+#include "tvm_common.cuh"
+
+namespace {
+
+constexpr int TC_RAYS = 128;
+constexpr int TC_THREADS = 128;
+constexpr int FC = TVM_FEATURE_C;
+constexpr int N0 = 32;                 // basis rows padded (app_dim <= 32)
+constexpr int N3 = 16;                 // rgb rows padded
+constexpr int COL0 = 0, COL1 = 32, COL2 = 160, COL3 = 288;   // TMEM column bases of the four accumulators
+constexpr int TMEM_COLS = 512;
+
+struct TcDims {
+    int ta, k0;        // sum(n_app), padded to 16
+    int in_c, k1;      // MLP input width, padded to 16
+    int app_dim, fea_pe, view_pe;
+    // byte offsets inside the weight image / shared memory
+    int img0, img1, img2, img3, img_bytes;
+};
+__host__ __device__ inline TcDims tc_dims(const tvm_field_desc* d) {
+    TcDims t;
+    t.ta = d->n_app[0] + d->n_app[1] + d->n_app[2];
+    t.k0 = (t.ta + 15) / 16 * 16;
+    t.in_c = 2 * d->view_pe * 3 + 2 * d->fea_pe * d->app_dim + 3 + d->app_dim;
+    t.k1 = (t.in_c + 15) / 16 * 16;
+    t.app_dim = d->app_dim; t.fea_pe = d->fea_pe; t.view_pe = d->view_pe;
+    t.img0 = 0;
+    t.img1 = t.img0 + N0 * t.k0 * 2;
+    t.img2 = t.img1 + FC * t.k1 * 2;
+    t.img3 = t.img2 + FC * FC * 2;
+    t.img_bytes = t.img3 + N3 * FC * 2;
+    return t;
+}
+
+// byte offset of element (row, k) of a K-major bf16 operand with K columns in the no-swizzle canonical layout:
+// 8x8 core matrices of 128 contiguous bytes (row stride 16 B); K-adjacent cores 128 B apart (LBO), 8-row groups
+// K*16 B apart (SBO).  (cute::UMMA canonical INTERLEAVE layout ((8,n),(8,2)):((8,SBO),(1,LBO)) in elements.)
+__host__ __device__ inline int canon_off(int row, int k, int K) {
+    return (row >> 3) * (K * 16) + (k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2;
+}
+
+// fp32 [R][Cc] (row-major, torch Linear weight) -> bf16 canonical image with R_pad rows and K_pad columns
+__global__ void pack_bf16_operand_kernel(const float* __restrict__ src, int R, int Cc, int R_pad, int K_pad,
+                                         unsigned char* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R_pad * K_pad) return;
+    const int r = i / K_pad, k = i - r * K_pad;
+    const float v = (r < R && k < Cc) ? __ldg(src + r * Cc + k) : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(dst + canon_off(r, k, K_pad)) = __float2bfloat16_rn(v);
+}
+
+// ---- raw PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int K) {
+    // start address [0,14) (>>4), LBO [16,30) = 128 B, SBO [32,46) = K*16 B, version [46,48) = 1, layout [61,64) = 0
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)((K * 16) >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    // c_format F32 [4,6)=1, a_format BF16 [7,10)=1, b_format BF16 [10,13)=1, K-major A/B, n_dim [17,23)=N>>3, m_dim [24,29)=M>>4
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 consecutive fp32 accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+        "%28,%29,%30,%31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+
+struct TcArgs {
+    const float* rays;
+    long long n_rays;
+    int ray_stride;
+    const float* bg;
+    float* rgb;
+    float* depth_out;
+    float* acc_out;
+    const float* ray_feat;
+    const float* acc;
+    const float* depth;
+    const int* app_count;
+    const unsigned char* wimg;     // bf16 weight images (tvm_pack_mlp_tc)
+    const float* b1; const float* b2; const float* b3;
+    TcDims d;
+};
+
+// one MMA chain: D[128 x N] (TMEM col base) = A[128 x K] . B[N x K]^T, issued by the calling thread
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, int K, int N,
+                                           uint32_t bar) {
+    const uint64_t da = make_desc(a_saddr, K), db = make_desc(b_saddr, K);
+    const uint32_t idesc = make_idesc(128, N);
+    for (int j = 0; j < K / 16; ++j)          // one UMMA_K = 16 step = 2 core matrices = 256 B (>>4 = 16) further along K
+        umma_bf16(tmem_d, da + (uint64_t)(j * 16), db + (uint64_t)(j * 16), idesc, j > 0 ? 1u : 0u);
+    umma_commit(bar);                          // implies tcgen05.fence::before_thread_sync
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_constant__ TcArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TcDims& d = a.d;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    // shared memory carve-up
+    unsigned char* s_img = smem;                                        // weight images
+    unsigned char* s_a = s_img + ((d.img_bytes + 127) & ~127);          // F tile (K0) / h1 (K=128)
+    const int a_bytes = TC_RAYS * (d.k0 > FC ? d.k0 : FC) * 2;
+    unsigned char* s_x = s_a + a_bytes;                                 // MLP input (K1) / h2 (K=128)
+    const int x_bytes = TC_RAYS * (d.k1 > FC ? d.k1 : FC) * 2;
+    float* s_row = reinterpret_cast<float*>(s_x + x_bytes);             // [128][33] fp32 scratch: feat | viewdir
+    float* s_bias = s_row + TC_RAYS * 33;                               // b1[128] b2[128] b3[4]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 2 * FC + 4);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(s_tmem)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(s_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid * 16; i < d.img_bytes; i += TC_THREADS * 16)
+        *reinterpret_cast<uint4*>(s_img + i) = __ldg(reinterpret_cast<const uint4*>(a.wimg + i));
+    for (int i = tid; i < 2 * FC + 4; i += TC_THREADS)
+        s_bias[i] = i < FC ? __ldg(a.b1 + i) : (i < 2 * FC ? __ldg(a.b2 + i - FC) : (i - 2 * FC < 3 ? __ldg(a.b3 + i - 2 * FC) : 0.f));
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's TMEM lane quarter
+    const uint32_t bar = smem_u32(s_bar);
+    const uint32_t sa = smem_u32(s_a), sx = smem_u32(s_x), simg = smem_u32(s_img);
+    uint32_t phase = 0;
+    const long long n_tiles = (a.n_rays + TC_RAYS - 1) / TC_RAYS;
+    const int nbase = d.app_dim + 3;
+    const int sin_f = nbase, cos_f = sin_f + d.app_dim * d.fea_pe;
+    const int sin_v = cos_f + d.app_dim * d.fea_pe, cos_v = sin_v + 3 * d.view_pe;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long r = tile * TC_RAYS + tid;          // this thread's ray == its TMEM lane
+        const bool live = r < a.n_rays;
+        // ---- stage 0: ray_feat row -> bf16 A operand (K0 columns)
+        for (int kc = 0; kc < d.k0 / 8; ++kc) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            if (live && kc * 8 < d.ta) {                   // ta is a multiple of 4
+                const float4 lo = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8));
+                v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+                if (kc * 8 + 4 < d.ta) {
+                    const float4 hi = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8 + 4));
+                    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+                }
+            }
+            *reinterpret_cast<uint4*>(s_a + canon_off(tid, kc * 8, d.k0)) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMA 1: feat = F . B^T
+        if (tid == 0) { tc_fence_after(); issue_gemm(tmem + COL0, sa, simg + d.img0, d.k0, N0, bar); }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        {
+            float v[32];
+            tmem_ld32(lane_base + COL0, v);
+            float* row = s_row + tid * 33;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) row[j] = v[j];
+            // viewdirs after the features
+            for (int c = 0; c < 3; ++c) row[d.app_dim + c] = live ? __ldg(a.rays + r * a.ray_stride + 3 + c) : 0.f;
+            // MLP input row (tensorBase.py:186-191): [feat | view | sin(feat 2^j) | cos | sin(view 2^j) | cos], zero pad
+            for (int ch = 0; ch < nbase; ++ch) {
+                const float x = row[ch];
+                *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(tid, ch, d.k1)) = __float2bfloat16_rn(x);
+                const bool is_feat = ch < d.app_dim;
+                const int nf = is_feat ? d.fea_pe : d.view_pe;
+                const int cc = is_feat ? ch : ch - d.app_dim;
+                const int sb = is_feat ? sin_f : sin_v, cb = is_feat ? cos_f : cos_v;
+                float scale = 1.f;
+                for (int j = 0; j < nf; ++j) {
+                    float s, c;
+                    sincosf(x * scale, &s, &c);
+                    *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(tid, sb + cc * nf + j, d.k1)) = __float2bfloat16_rn(s);
+                    *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(tid, cb + cc * nf + j, d.k1)) = __float2bfloat16_rn(c);
+                    scale *= 2.f;
+                }
+            }
+            for (int k = d.in_c; k < d.k1; ++k)
+                *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(tid, k, d.k1)) = __float2bfloat16_rn(0.f);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMA 2: h1 = X . W1^T
+        if (tid == 0) { tc_fence_after(); issue_gemm(tmem + COL1, sx, simg + d.img1, d.k1, FC, bar); }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int cb = 0; cb < FC; cb += 32) {              // bias + ReLU -> bf16 A operand (K = 128) in s_a
+            float v[32];
+            tmem_ld32(lane_base + COL1 + cb, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = q * 8 + e * 2;
+                    w[e] = pack_bf16x2(fmaxf(v[j] + s_bias[cb + j], 0.f), fmaxf(v[j + 1] + s_bias[cb + j + 1], 0.f));
+                }
+                *reinterpret_cast<uint4*>(s_a + canon_off(tid, cb + q * 8, FC)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMA 3: h2 = h1 . W2^T
+        if (tid == 0) { tc_fence_after(); issue_gemm(tmem + COL2, sa, simg + d.img2, FC, FC, bar); }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int cb = 0; cb < FC; cb += 32) {              // bias + ReLU -> bf16 A operand (K = 128) in s_x
+            float v[32];
+            tmem_ld32(lane_base + COL2 + cb, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = q * 8 + e * 2;
+                    w[e] = pack_bf16x2(fmaxf(v[j] + s_bias[FC + cb + j], 0.f), fmaxf(v[j + 1] + s_bias[FC + cb + j + 1], 0.f));
+                }
+                *reinterpret_cast<uint4*>(s_x + canon_off(tid, cb + q * 8, FC)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMA 4: rgb_raw = h2 . W3^T (N padded to 16)
+        if (tid == 0) { tc_fence_after(); issue_gemm(tmem + COL3, sx, simg + d.img3, FC, N3, bar); }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        {
+            float v[32];
+            tmem_ld32(lane_base + COL3, v);               // columns 3.. are padding / neighbouring accumulators
+            if (live) {
+                const bool lit = __ldg(a.app_count + r) > 0;          // rays_to_consider (tensorBase.py:886)
+                const float ac = __ldg(a.acc + r);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float col = lit ? 1.f / (1.f + expf(-(v[c] + s_bias[2 * FC + c]))) : 0.f;
+                    const float out = col * ac + __ldg(a.bg + c) * (1.f - ac);
+                    a.rgb[r * 3 + c] = fminf(fmaxf(out, 0.f), 1.f);
+                }
+                const float last = __ldg(a.rays + r * a.ray_stride + a.ray_stride - 1);
+                if (a.depth_out) a.depth_out[r] = __ldg(a.depth + r) + (1.f - ac) * last;
+                if (a.acc_out) a.acc_out[r] = ac;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                   // TMEM + smem operands free for the next tile
+        tc_fence_after();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+size_t tc_smem_bytes(const TcDims& d) {
+    const size_t a_bytes = (size_t)TC_RAYS * (d.k0 > FC ? d.k0 : FC) * 2;
+    const size_t x_bytes = (size_t)TC_RAYS * (d.k1 > FC ? d.k1 : FC) * 2;
+    return ((d.img_bytes + 127) & ~127) + a_bytes + x_bytes + (size_t)TC_RAYS * 33 * 4 + (2 * FC + 4) * 4 + 16;
+}
+
+}  // namespace
+
+extern "C" size_t tvm_mlp_tc_pack_bytes(const tvm_field_desc* desc) {
+    if (!desc) return 0;
+    return (size_t)tc_dims(desc).img_bytes;
+}
+
+extern "C" int tvm_pack_mlp_tc(const tvm_field_desc* desc, const float* basis, const float* w1, const float* w2,
+                               const float* w3, void* packed, void* stream) {
+    if (!desc || !basis || !w1 || !w2 || !w3 || !packed) return TVM_E_NULL;
+    if (desc->feature_c != FC || desc->app_dim > N0 || desc->app_dim <= 0) return TVM_E_SHAPE;
+    const TcDims d = tc_dims(desc);
+    if (tc_smem_bytes(d) > 227 * 1024) return TVM_E_SHAPE;
+    unsigned char* out = (unsigned char*)packed;
+    cudaStream_t st = (cudaStream_t)stream;
+    pack_bf16_operand_kernel<<<(N0 * d.k0 + 255) / 256, 256, 0, st>>>(basis, d.app_dim, d.ta, N0, d.k0, out + d.img0);
+    pack_bf16_operand_kernel<<<(FC * d.k1 + 255) / 256, 256, 0, st>>>(w1, FC, d.in_c, FC, d.k1, out + d.img1);
+    pack_bf16_operand_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(w2, FC, FC, FC, FC, out + d.img2);
+    pack_bf16_operand_kernel<<<(N3 * FC + 255) / 256, 256, 0, st>>>(w3, 3, FC, N3, FC, out + d.img3);
+    TVM_LAUNCH_CHECK();
+    return 0;
+}
+
+// called by tvm_shade_fwd when TVM_F_MLP_BF16 is set
+int tvm_shade_tc_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, const float* bg,
+                        float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (!desc->mlp_tc || !desc->mlp) return TVM_E_NULL;
+    if (desc->feature_c != FC || desc->app_dim > N0 || desc->app_dim <= 0) return TVM_E_SHAPE;
+    const TcDims d = tc_dims(desc);
+    const size_t smem = tc_smem_bytes(d);
+    if (smem > 227 * 1024) return TVM_E_SHAPE;
+    const TvmWorkspace w = tvm_ws_layout(desc, n_rays);
+    if (ws_bytes < w.total) return TVM_E_WORKSPACE;
+    const TvmMlpLayout m = tvm_mlp_layout(desc);
+    const char* base = (const char*)ws;
+    TcArgs a{};
+    a.rays = rays; a.n_rays = n_rays; a.ray_stride = ray_stride; a.bg = bg;
+    a.rgb = rgb; a.depth_out = depth; a.acc_out = acc;
+    a.ray_feat = (const float*)(base + w.ray_feat);
+    a.acc = (const float*)(base + w.acc);
+    a.depth = (const float*)(base + w.depth);
+    a.app_count = (const int*)(base + w.app_count);
+    a.wimg = (const unsigned char*)desc->mlp_tc;
+    a.b1 = desc->mlp + m.b1; a.b2 = desc->mlp + m.b2; a.b3 = desc->mlp + m.b3;
+    a.d = d;
+    TVM_CUDA_OK(cudaFuncSetAttribute(shade_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long tiles = (n_rays + TC_RAYS - 1) / TC_RAYS;
+    const unsigned grid = (unsigned)(tiles < TVM_SM_COUNT ? tiles : TVM_SM_COUNT);
+    shade_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+    TVM_LAUNCH_CHECK();
+    return 0;
+}

@@ -117,6 +117,9 @@ class TensorVMSplit(torch.nn.Module):
     max_launch_rays = 1 << 20
     # transmittance below which an eval ray stops marching (error on rgb/acc <= this value)
     early_term_eps = 1e-5
+    # shading-stage arithmetic on the no-grad path: "fp32" (SIMT FFMA kernel, rgb within 1e-4 of the reference) or
+    # "bf16" (tcgen05 tensor-core kernel, rgb within 1e-2 — BASELINE.json's "bf16 MLP mode")
+    mlp_precision = "fp32"
 
     def __init__(self, aabb, gridSize, device, density_n_comp=8, appearance_n_comp=24, app_dim=27,
                  shadingMode="MLP_PE", alphaMask=None, near_far=[2.0, 6.0], density_shift=-10,
@@ -162,6 +165,8 @@ class TensorVMSplit(torch.nn.Module):
         self._packed_key = None
         self._mlp_packed = None
         self._mlp_key = None
+        self._mlp_tc = None
+        self._mlp_tc_key = None
         self._bg_cache = {}
         self.grad_sync = None      # sharding.GradSync when training data-parallel
 
@@ -348,6 +353,24 @@ class TensorVMSplit(torch.nn.Module):
             self._mlp_key = key
         return self._mlp_packed
 
+    def packed_mlp_tc(self):
+        """bf16 operand images of basis_mat + MLP weights for the tcgen05 shade kernel."""
+        mods = [self.renderModule.mlp[i] for i in (0, 2, 4)]
+        ps = [self.basis_mat.weight] + [m.weight for m in mods]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._mlp_tc is None or self._mlp_tc_key != key:
+            dev = ps[0].device
+            d = self._base_desc()
+            lib = _lib.load()
+            n = lib.tvm_mlp_tc_pack_bytes(C.byref(d))
+            if self._mlp_tc is None or self._mlp_tc.numel() != n or self._mlp_tc.device != dev:
+                self._mlp_tc = torch.zeros(int(n), dtype=torch.uint8, device=dev)
+            b, w1, w2, w3 = [p.detach().contiguous() for p in ps]
+            _lib.check(lib.tvm_pack_mlp_tc(C.byref(d), _lib.ptr(b), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3),
+                                           _lib.ptr(self._mlp_tc), _stream(dev)), "tvm_pack_mlp_tc")
+            self._mlp_tc_key = key
+        return self._mlp_tc
+
     def field_desc(self, need_params=True):
         """Full descriptor with device pointers; keeps the referenced tensors alive via the returned tuple."""
         d = self._base_desc()
@@ -358,6 +381,12 @@ class TensorVMSplit(torch.nn.Module):
             basis = self.basis_mat.weight.detach().contiguous()
             d.factors, d.mlp, d.basis = pf.data_ptr(), pm.data_ptr(), basis.data_ptr()
             keep += [pf, pm, basis]
+            if self.mlp_precision == "bf16":
+                tc = self.packed_mlp_tc()
+                d.mlp_tc = tc.data_ptr()
+                keep.append(tc)
+            elif self.mlp_precision != "fp32":
+                raise ValueError(f"mlp_precision must be 'fp32' or 'bf16', got {self.mlp_precision!r}")
         if self.alphaMask is not None:
             cells = self.alphaMask.cells()
             dx, dy, dz = self.alphaMask._cells_dims
@@ -431,6 +460,8 @@ class TensorVMSplit(torch.nn.Module):
         _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need)), "tvm_workspace_bytes")
         ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
         flags = _lib.F_EARLY_TERM if (early_term and not sample_outputs) else 0
+        if self.mlp_precision == "bf16":
+            flags |= _lib.F_MLP_BF16
         jit = None if jitter is None else jitter.detach().to(dev).float().reshape(-1).contiguous()
         bg = self._bg(bg_color, white_bg, dev)
         _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, _lib.ptr(jit), _lib.ptr(bg),

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 4
+#define TVM_ABI_VERSION 5
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define TVM_E_NULL        (-1)   /* required pointer is NULL                      */
@@ -82,6 +82,8 @@ typedef struct tvm_field_desc {
     const float* factors;        /* packed factors (layout above)                                          */
     const float* basis;          /* basis_mat.weight [app_dim][sum(n_app)] row-major (torch layout)        */
     const float* mlp;            /* packed MLP from tvm_pack_mlp                                           */
+    const void*  mlp_tc;         /* bf16 tensor-core weight images from tvm_pack_mlp_tc (NULL unless
+                                    TVM_F_MLP_BF16 is used)                                                */
 } tvm_field_desc;
 
 int  tvm_abi_version(void);
@@ -108,6 +110,12 @@ int tvm_pack_occupancy(const float* volume, int dx, int dy, int dz, uint8_t* cel
 size_t tvm_mlp_pack_floats(const tvm_field_desc* desc);
 int tvm_pack_mlp(const tvm_field_desc* desc, const float* w1, const float* b1, const float* w2, const float* b2,
                  const float* w3, const float* b3, float* packed, void* stream);
+
+/* bf16 operand images (K-major canonical core-matrix layout) of basis_mat and the three MLP weights for the
+ * tcgen05 shade kernel selected by TVM_F_MLP_BF16; biases are read from the fp32 pack (desc->mlp). */
+size_t tvm_mlp_tc_pack_bytes(const tvm_field_desc* desc);
+int tvm_pack_mlp_tc(const tvm_field_desc* desc, const float* basis, const float* w1, const float* w2, const float* w3,
+                    void* packed, void* stream);
 
 /* ---- the hot path ---------------------------------------------------------------------------------- */
 

@@ -45,4 +45,13 @@ def timeit(fn):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         tot += e0.elapsed_time(e1)
     return tot / a.steps
-print(json.dumps({"tag": a.tag, "march_ms": round(timeit(march), 4), "shade_ms": round(timeit(shade), 4), "early": not a.no_early}))
+m.mlp_precision = "bf16"
+d2, keep2 = m.field_desc()
+def shade_tc():
+    _lib.check(lib.tvm_shade_fwd(C.byref(d2), _lib.ptr(rays), n, rays.shape[1], _lib.ptr(bg), _lib.F_MLP_BF16, _lib.ptr(rgb),
+                                 _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(ws), ws.numel(), st), "shade_tc")
+march()
+ref_rgb = torch.empty_like(rgb); shade(); ref_rgb.copy_(rgb)
+tc_ms = round(timeit(shade_tc), 4)
+tc_err = float((rgb - ref_rgb).abs().max())
+print(json.dumps({"tag": a.tag, "shade_tc_ms": tc_ms, "shade_tc_max_abs_vs_fp32": tc_err, "march_ms": round(timeit(march), 4), "shade_ms": round(timeit(shade), 4), "early": not a.no_early}))

@@ -68,6 +68,24 @@ def test_render_matches_reference_golden(name, early_term, dev):
     assert np.abs(o["app_count"].cpu().numpy() - g["app_count"]).max() <= 2
 
 
+@pytest.mark.parametrize("name", ["c1_dense_mask", "c2_sub", "c4_sub"])
+def test_bf16_tensor_core_mlp_mode(name, dev):
+    """TVM_F_MLP_BF16: the tcgen05 shade kernel — rgb within 1e-2 of the reference (north_star's bf16 MLP mode);
+    depth/acc do not go through the MLP and keep the fp32 bound."""
+    fld, rays, g, white, m = _case(name, dev)
+    m.mlp_precision = "bf16"
+    try:
+        o = m.render_eval(rays.to(dev), white_bg=bool(white))
+        torch.cuda.synchronize()
+    finally:
+        m.mlp_precision = "fp32"
+    err = np.abs(o["rgb_map"].cpu().numpy() - g["rgb_map"]).max()
+    assert err <= 1e-2, err
+    assert err > 0                                            # it really is the reduced-precision path
+    assert np.abs(o["depth_map"].cpu().numpy() - g["depth_map"]).max() <= TOL
+    assert np.abs(o["acc_map"].cpu().numpy() - g["acc_map"]).max() <= TOL
+
+
 def test_forward_six_tuple_matches_oracle(dev):
     fld, rays, g, white, m = _case("c1_dense_mask", dev)
     sub = rays[3000:3700].contiguous()
