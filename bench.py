@@ -242,6 +242,13 @@ def run_ours(args, rank, world, local_rank):
         ms_dev = timed(step_device, args.steps, args.warmup)
     ms_march = timed(step_march_only, args.steps, 1)
     ms_e2e = timed(step_e2e, args.steps, 1)
+    # the same step with the tcgen05 bf16 shading kernel (north_star's "bf16 MLP mode", rgb within 1e-2)
+    ref_rgb = step_device()["rgb_map"].clone()
+    model.mlp_precision = "bf16"
+    ms_dev_tc = timed(step_device, args.steps, 1)
+    ms_e2e_tc = timed(step_e2e, args.steps, 1)
+    tc_err = float((step_device()["rgb_map"] - ref_rgb).abs().max())
+    model.mlp_precision = "fp32"
 
     # work counters of one step (from the march workspace) for the algorithmic-bytes roofline
     o = model.render_eval(rays_dev, white_bg=True, keep_workspace=True)
@@ -252,10 +259,10 @@ def run_ours(args, rank, world, local_rank):
     has_occ = model.alphaMask is not None
     alg_bytes = 44 * n + (32 * v0 if has_occ else 0) + 1152 * v + 3456 * a
 
-    t = torch.tensor([ms_dev, ms_march, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_dev, ms_march, ms_e2e, ms_dev_tc, ms_e2e_tc], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_march, ms_e2e = t.tolist()
+    ms_dev, ms_march, ms_e2e, ms_dev_tc, ms_e2e_tc = t.tolist()
     if rank == 0:
         K = args.steps
         peak, peak_src = peaks()
@@ -283,6 +290,10 @@ def run_ours(args, rank, world, local_rank):
                              "ms_per_launch": ms_march / K,
                              "units_per_launch": {"rays": n, "occupancy_tests": v0, "sigma_samples": v,
                                                   "app_samples": a}},
+                "bf16_mlp_mode": {"value": world * n * K / (ms_dev_tc / 1e3), "e2e": world * n * K / (ms_e2e_tc / 1e3),
+                                  "unit": UNIT, "ms_per_step": ms_dev_tc / K, "max_abs_rgb_vs_fp32": tc_err,
+                                  "shade_tflops": 2 * 39856 * n * 1e-12 / max((ms_dev_tc - ms_march) / K / 1e3, 1e-9),
+                                  "note": "tcgen05 bf16 shade kernel; march stage unchanged"},
                 "clocks": clk.result}
         if not args.no_cpu_baseline and world == 1:
             rate, cores, desc = cpu_oracle_rate(args.cpu_rays)

@@ -43,7 +43,7 @@ struct ShadeArgs {
     const float* basis;      // [app_dim][ta]
     const float* w1t; const float* b1; const float* w2t; const float* b2; const float* w3; const float* b3;
     int ta, app_dim, fea_pe, view_pe, in_c, k1;
-    int sF_stride;           // ta + 1
+    int sF_stride;           // ta + 4
 };
 
 // acc[8][4] += X[8 rays][K] * Wt[K][4 cols]
@@ -71,39 +71,59 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const __grid_cons
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ta = a.ta, k1 = a.k1, fs = a.sF_stride;
-    float* sB = smem;                                            // [app_dim][ta]
-    float* sF = sB + ((a.app_dim * ta + 3) & ~3);                // [64][ta+1]; later aliased by sH [64][FC]
+    float* sB = smem;                                            // basis transposed + padded: [ta][32]
+    float* sF = sB + ta * 32;                                    // [64][ta+4]; later aliased by sH [64][FC]
     float* sX = sF + ((max(SH_RAYS * fs, SH_RAYS * FC) + 3) & ~3);   // [64][k1]
     float* sH = sF;
     const long long r0 = (long long)blockIdx.x * SH_RAYS;
 
-    for (int i = tid; i < a.app_dim * ta; i += SH_THREADS) sB[i] = __ldg(a.basis + i);
-    for (int i = tid; i < SH_RAYS * ta; i += SH_THREADS) {
-        const int ray = i / ta, c = i - ray * ta;
+    for (int i = tid; i < a.app_dim * ta; i += SH_THREADS) {
+        const int j = i / ta, c = i - j * ta;
+        sB[c * 32 + j] = __ldg(a.basis + i);
+    }
+    for (int i = tid; i < (32 - a.app_dim) * ta; i += SH_THREADS) {
+        const int c = i / (32 - a.app_dim), j = a.app_dim + i - c * (32 - a.app_dim);
+        sB[c * 32 + j] = 0.f;
+    }
+    for (int i = tid; i < SH_RAYS * (ta >> 2); i += SH_THREADS) {
+        const int ray = i / (ta >> 2), c4 = i - ray * (ta >> 2);
         const long long r = r0 + ray;
-        sF[ray * fs + c] = (r < a.n_rays) ? __ldg(a.ray_feat + r * ta + c) : 0.f;
+        const float4 v = (r < a.n_rays) ? __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * ta) + c4)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(sF + ray * fs + c4 * 4) = v;
     }
     __syncthreads();
 
     // ---- basis_mat: feat[j] = sum_c B[j][c] * F[c]  -> X[:, 0:app_dim]; viewdirs -> X[:, app_dim:app_dim+3]
     {
-        const int ray = tid & (SH_RAYS - 1), jg = tid >> 6;      // 4 groups of output rows
-        float o[8];
+        // register tile: 2 rays x 4 output columns per thread (tx = column group, ty = ray pair)
+        const int tx = tid & 7, ty = tid >> 3;
+        float o[2][4];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) o[m] = 0.f;
-        for (int c = 0; c < ta; ++c) {
-            const float fv = sF[ray * fs + c];
+        for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int j = jg + 4 * m;
-                if (j < a.app_dim) o[m] = fmaf(fv, sB[j * ta + c], o[m]);
+            for (int e = 0; e < 4; ++e) o[rr][e] = 0.f;
+        for (int c = 0; c < ta; c += 4) {
+            const float4 b0 = *reinterpret_cast<const float4*>(sB + (c + 0) * 32 + tx * 4);
+            const float4 b1 = *reinterpret_cast<const float4*>(sB + (c + 1) * 32 + tx * 4);
+            const float4 b2 = *reinterpret_cast<const float4*>(sB + (c + 2) * 32 + tx * 4);
+            const float4 b3 = *reinterpret_cast<const float4*>(sB + (c + 3) * 32 + tx * 4);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const float4 x = *reinterpret_cast<const float4*>(sF + (ty * 2 + rr) * fs + c);
+                o[rr][0] = fmaf(x.x, b0.x, fmaf(x.y, b1.x, fmaf(x.z, b2.x, fmaf(x.w, b3.x, o[rr][0]))));
+                o[rr][1] = fmaf(x.x, b0.y, fmaf(x.y, b1.y, fmaf(x.z, b2.y, fmaf(x.w, b3.y, o[rr][1]))));
+                o[rr][2] = fmaf(x.x, b0.z, fmaf(x.y, b1.z, fmaf(x.z, b2.z, fmaf(x.w, b3.z, o[rr][2]))));
+                o[rr][3] = fmaf(x.x, b0.w, fmaf(x.y, b1.w, fmaf(x.z, b2.w, fmaf(x.w, b3.w, o[rr][3]))));
             }
         }
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            const int j = jg + 4 * m;
-            if (j < a.app_dim) sX[ray * k1 + j] = o[m];
-        }
+        for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = tx * 4 + e;
+                if (j < a.app_dim) sX[(ty * 2 + rr) * k1 + j] = o[rr][e];
+            }
         if (tid < SH_RAYS * 3) {
             const int vr = tid / 3, c = tid - vr * 3;
             const long long r = r0 + vr;
@@ -235,8 +255,8 @@ extern "C" int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int6
     a.w1t = desc->mlp + m.w1t; a.b1 = desc->mlp + m.b1; a.w2t = desc->mlp + m.w2t; a.b2 = desc->mlp + m.b2;
     a.w3 = desc->mlp + m.w3; a.b3 = desc->mlp + m.b3;
     a.ta = tvm_total_app(desc); a.app_dim = desc->app_dim; a.fea_pe = desc->fea_pe; a.view_pe = desc->view_pe;
-    a.in_c = m.in_c; a.k1 = m.k1; a.sF_stride = a.ta + 1;
-    const size_t nB = (size_t)((a.app_dim * a.ta + 3) & ~3);
+    a.in_c = m.in_c; a.k1 = m.k1; a.sF_stride = a.ta + 4;     // +4: conflict-free float4 rows
+    const size_t nB = (size_t)a.ta * 32;
     const size_t nF = (size_t)((max(SH_RAYS * a.sF_stride, SH_RAYS * FC) + 3) & ~3);
     const size_t nX = (size_t)SH_RAYS * a.k1;
     const size_t smem = (nB + nF + nX) * sizeof(float);
