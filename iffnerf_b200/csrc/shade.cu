@@ -50,12 +50,17 @@ struct ShadeArgs {
 template <int XS_IS_FC>
 __device__ __forceinline__ void tile_gemm(float (&acc)[8][4], const float* __restrict__ sX, int x_stride, int K,
                                           const float* __restrict__ Wt, int tx, int ty) {
-    const float4* W4 = reinterpret_cast<const float4*>(Wt);
+    const float4* W4 = reinterpret_cast<const float4*>(Wt) + tx;
+    // register double-buffer of the weight rows: the loads for step k+4 are in flight while step k is computed
+    float4 n0 = __ldg(W4), n1 = __ldg(W4 + FC / 4), n2 = __ldg(W4 + 2 * (FC / 4)), n3 = __ldg(W4 + 3 * (FC / 4));
     for (int k = 0; k < K; k += 4) {
-        const float4 w0 = __ldg(W4 + (k + 0) * (FC / 4) + tx);
-        const float4 w1 = __ldg(W4 + (k + 1) * (FC / 4) + tx);
-        const float4 w2 = __ldg(W4 + (k + 2) * (FC / 4) + tx);
-        const float4 w3 = __ldg(W4 + (k + 3) * (FC / 4) + tx);
+        const float4 w0 = n0, w1 = n1, w2 = n2, w3 = n3;
+        if (k + 4 < K) {
+            n0 = __ldg(W4 + (k + 4) * (FC / 4));
+            n1 = __ldg(W4 + (k + 5) * (FC / 4));
+            n2 = __ldg(W4 + (k + 6) * (FC / 4));
+            n3 = __ldg(W4 + (k + 7) * (FC / 4));
+        }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const float4 x = *reinterpret_cast<const float4*>(sX + (ty * 8 + r) * x_stride + k);
