@@ -58,6 +58,7 @@ struct MarchArgs {
     int* occ_count;
     int ta;
     int app_off[3];
+    int rays_per_cta;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -77,14 +78,14 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
     if (threadIdx.x == 0) s_next = MARCH_WARPS;
     __syncthreads();
 
-    const long long base = (long long)blockIdx.x * MARCH_RAYS_PER_CTA;
+    const long long base = (long long)blockIdx.x * a.rays_per_cta;
     const bool sample_out = a.alpha || a.z_vals || a.dists;
     const bool visit_all = sample_out || a.valid_bits;          // every sample index must be written
     const bool early = (a.flags & TVM_F_EARLY_TERM) && !sample_out;
     const int S = a.S, words = (S + 31) >> 5;
     int local = warp;
 
-    while (local < MARCH_RAYS_PER_CTA) {
+    while (local < a.rays_per_cta) {
         const long long r = base + local;
         if (r >= a.n_rays) break;
         TvmRay ray;
@@ -249,13 +250,23 @@ int fill_args(MarchArgs& a, const tvm_field_desc* desc, const float* rays, int64
     return 0;
 }
 
+// rays per CTA: 32 consecutive rays share texels in L1 on big launches; small (training-sized) batches get fewer
+// rays per CTA so that every SM still holds several CTAs
+static int pick_rays_per_cta(long long n_rays, int warps, int max_rpc) {
+    long long rpc = n_rays / (TVM_SM_COUNT * 8);
+    if (rpc < warps) rpc = warps;
+    if (rpc > max_rpc) rpc = max_rpc;
+    return (int)rpc;
+}
+
 template <typename K>
-int launch(K kernel, const MarchArgs& a, cudaStream_t st) {
+int launch(K kernel, MarchArgs& a, cudaStream_t st) {
     if (a.n_rays == 0) return 0;
+    a.rays_per_cta = pick_rays_per_cta(a.n_rays, MARCH_WARPS, MARCH_RAYS_PER_CTA);
     // small static smem per CTA: ask for a 32 KB carve-out (enough for every resident CTA) and leave the rest
     // of the 228 KB to L1, which is what serves the texel gathers
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 14);
-    const long long ctas = (a.n_rays + MARCH_RAYS_PER_CTA - 1) / MARCH_RAYS_PER_CTA;
+    const long long ctas = (a.n_rays + a.rays_per_cta - 1) / a.rays_per_cta;
     kernel<<<(unsigned)ctas, MARCH_WARPS * 32, 0, st>>>(a);
     TVM_LAUNCH_CHECK();
     return 0;

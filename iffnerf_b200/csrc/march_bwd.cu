@@ -38,6 +38,7 @@ struct BwdArgs {
     const float* acc;
     int ta;
     int app_off[3];
+    int rays_per_cta;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -62,11 +63,11 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
     const unsigned lt_mask = (1u << lane) - 1u;
     if (threadIdx.x == 0) s_next = BWD_WARPS;
     __syncthreads();
-    const long long base = (long long)blockIdx.x * BWD_RAYS_PER_CTA;
+    const long long base = (long long)blockIdx.x * a.rays_per_cta;
     const int S = a.S;
     int local = warp;
 
-    while (local < BWD_RAYS_PER_CTA) {
+    while (local < a.rays_per_cta) {
         const long long r = base + local;
         if (r >= a.n_rays) break;
         TvmRay ray;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
 
 template <int G, int CS4, int CA4>
 int dispatch(const BwdArgs& a, cudaStream_t st) {
-    const long long ctas = (a.n_rays + BWD_RAYS_PER_CTA - 1) / BWD_RAYS_PER_CTA;
+    const long long ctas = (a.n_rays + a.rays_per_cta - 1) / a.rays_per_cta;
     const bool scatter = a.g_factors != nullptr, pose = a.g_rays != nullptr;
     if (scatter && pose) march_bwd_kernel<G, true, true, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a);
     else if (scatter) march_bwd_kernel<G, true, false, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a);
@@ -302,6 +303,10 @@ extern "C" int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int6
     a.acc = (const float*)((const char*)ws + w.acc);
     a.ta = tvm_total_app(desc);
     a.app_off[0] = 0; a.app_off[1] = desc->n_app[0]; a.app_off[2] = desc->n_app[0] + desc->n_app[1];
+    {
+        long long rpc = n_rays / (TVM_SM_COUNT * 8);
+        a.rays_per_cta = (int)(rpc < BWD_WARPS ? BWD_WARPS : (rpc > BWD_RAYS_PER_CTA ? BWD_RAYS_PER_CTA : rpc));
+    }
     int gmax = 0;
     for (int k = 0; k < 3; ++k) gmax = max(gmax, (desc->n_app[k] + 15) / 16);
     cudaStream_t st = (cudaStream_t)stream;

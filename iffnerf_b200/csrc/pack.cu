@@ -14,11 +14,19 @@ namespace {
 
 constexpr int TP = 32;   // pixels per tile
 
+// The 12 factor tensors are converted by ONE launch: blockIdx.y selects the tensor, blockIdx.x the pixel tile.
+struct TransposeJob { const float* src; float* dst; int C; long long P; };
+struct TransposeJobs { TransposeJob j[12]; int accumulate; };
+
 // src [C][P] -> dst [P][C]
-__global__ void __launch_bounds__(256) cp_to_pc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C,
-                                                       long long P) {
+__global__ void __launch_bounds__(256) cp_to_pc_kernel(const __grid_constant__ TransposeJobs jobs) {
     __shared__ float tile[TVM_MAX_APP_C][TP + 1];
+    const float* __restrict__ src = jobs.j[blockIdx.y].src;
+    float* __restrict__ dst = jobs.j[blockIdx.y].dst;
+    const int C = jobs.j[blockIdx.y].C;
+    const long long P = jobs.j[blockIdx.y].P;
     const long long p0 = (long long)blockIdx.x * TP;
+    if (p0 >= P) return;
     const int px = threadIdx.x & 31, cy = threadIdx.x >> 5;
     for (int c = cy; c < C; c += 8) {
         const long long p = p0 + px;
@@ -33,10 +41,15 @@ __global__ void __launch_bounds__(256) cp_to_pc_kernel(const float* __restrict__
 }
 
 // src [P][C] -> dst [C][P]  (dst = src^T, or dst += src^T)
-__global__ void __launch_bounds__(256) pc_to_cp_kernel(const float* __restrict__ src, float* __restrict__ dst, int C,
-                                                       long long P, int accumulate) {
+__global__ void __launch_bounds__(256) pc_to_cp_kernel(const __grid_constant__ TransposeJobs jobs) {
     __shared__ float tile[TVM_MAX_APP_C][TP + 1];
+    const float* __restrict__ src = jobs.j[blockIdx.y].src;
+    float* __restrict__ dst = jobs.j[blockIdx.y].dst;
+    if (dst == nullptr) return;
+    const int C = jobs.j[blockIdx.y].C, accumulate = jobs.accumulate;
+    const long long P = jobs.j[blockIdx.y].P;
     const long long p0 = (long long)blockIdx.x * TP;
+    if (p0 >= P) return;
     const long long lim = min((long long)TP, P - p0) * C;
     for (int i = threadIdx.x; i < lim; i += 256) {
         const int p = i / C, c = i - p * C;
@@ -141,12 +154,15 @@ extern "C" int tvm_pack_factors(const tvm_field_desc* desc, const float* const p
     if (!planes || !lines || !packed) return TVM_E_NULL;
     FactorView pv[6], lv[6];
     factor_views(desc, pv, lv);
-    cudaStream_t st = (cudaStream_t)stream;
+    TransposeJobs jobs{};
+    long long maxP = 0;
     for (int i = 0; i < 6; ++i) {
         if (!planes[i] || !lines[i]) return TVM_E_NULL;
-        cp_to_pc_kernel<<<(unsigned)((pv[i].P + TP - 1) / TP), 256, 0, st>>>(planes[i], packed + pv[i].off, pv[i].C, pv[i].P);
-        cp_to_pc_kernel<<<(unsigned)((lv[i].P + TP - 1) / TP), 256, 0, st>>>(lines[i], packed + lv[i].off, lv[i].C, lv[i].P);
+        jobs.j[i] = {planes[i], packed + pv[i].off, pv[i].C, pv[i].P};
+        jobs.j[6 + i] = {lines[i], packed + lv[i].off, lv[i].C, lv[i].P};
+        maxP = max(maxP, max(pv[i].P, lv[i].P));
     }
+    cp_to_pc_kernel<<<dim3((unsigned)((maxP + TP - 1) / TP), 12), 256, 0, (cudaStream_t)stream>>>(jobs);
     TVM_LAUNCH_CHECK();
     return 0;
 }
@@ -158,13 +174,15 @@ extern "C" int tvm_unpack_factor_grads(const tvm_field_desc* desc, const float* 
     if (!planes || !lines || !packed_grad) return TVM_E_NULL;
     FactorView pv[6], lv[6];
     factor_views(desc, pv, lv);
-    cudaStream_t st = (cudaStream_t)stream;
+    TransposeJobs jobs{};
+    jobs.accumulate = accumulate;
+    long long maxP = 0;
     for (int i = 0; i < 6; ++i) {
-        if (planes[i])
-            pc_to_cp_kernel<<<(unsigned)((pv[i].P + TP - 1) / TP), 256, 0, st>>>(packed_grad + pv[i].off, planes[i], pv[i].C, pv[i].P, accumulate);
-        if (lines[i])
-            pc_to_cp_kernel<<<(unsigned)((lv[i].P + TP - 1) / TP), 256, 0, st>>>(packed_grad + lv[i].off, lines[i], lv[i].C, lv[i].P, accumulate);
+        jobs.j[i] = {packed_grad + pv[i].off, planes[i], pv[i].C, pv[i].P};
+        jobs.j[6 + i] = {packed_grad + lv[i].off, lines[i], lv[i].C, lv[i].P};
+        maxP = max(maxP, max(pv[i].P, lv[i].P));
     }
+    pc_to_cp_kernel<<<dim3((unsigned)((maxP + TP - 1) / TP), 12), 256, 0, (cudaStream_t)stream>>>(jobs);
     TVM_LAUNCH_CHECK();
     return 0;
 }

@@ -34,6 +34,9 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
     rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
     depth = torch.empty((n,), dtype=torch.float32, device=dev)
     on_host = not rays.is_cuda
+    if on_host:
+        # host-resident rays: ~4 slices so the H2D copy of slice k+1 hides behind the kernels of slice k
+        step = min(step, max(1 << 16, -(-n // 4)))
     copy_stream = torch.cuda.Stream(device=dev) if on_host and n > step else None
     main = torch.cuda.current_stream(dev)
 
