@@ -34,10 +34,11 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
     rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
     depth = torch.empty((n,), dtype=torch.float32, device=dev)
     on_host = not rays.is_cuda
-    if on_host:
-        # host-resident rays: ~4 slices so the H2D copy of slice k+1 hides behind the kernels of slice k
-        step = min(step, max(1 << 16, -(-n // 4)))
-    copy_stream = torch.cuda.Stream(device=dev) if on_host and n > step else None
+    n_slices = int(getattr(tensorf, "host_ray_slices", 1))
+    if on_host and n_slices > 1:
+        # host-resident rays: the H2D copy of slice k+1 hides behind the kernels of slice k
+        step = min(step, max(1 << 16, -(-n // n_slices)))
+    copy_stream = _copy_stream(dev) if on_host and n > step else None
     main = torch.cuda.current_stream(dev)
 
     def fetch(a):
@@ -59,7 +60,16 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
         if ev is not None:
             main.wait_event(ev)
             cur.record_stream(main)
-        o = tensorf.render_eval(cur, N_samples=N_samples, white_bg=bool(white_bg), bg_color=bg_color)
-        rgb[a:a + step] = o["rgb_map"]
-        depth[a:a + step] = o["depth_map"]
+        tensorf.render_eval(cur, N_samples=N_samples, white_bg=bool(white_bg), bg_color=bg_color,
+                            out_rgb=rgb[a:a + step], out_depth=depth[a:a + step])
     return rgb, None, depth, None, None
+
+
+_streams = {}
+
+
+def _copy_stream(dev):
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _streams:
+        _streams[key] = torch.cuda.Stream(device=dev)
+    return _streams[key]

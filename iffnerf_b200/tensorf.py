@@ -434,7 +434,7 @@ class TensorVMSplit(torch.nn.Module):
 
     @torch.no_grad()
     def render_eval(self, rays, N_samples=-1, white_bg=False, bg_color=None, jitter=None, sample_outputs=False,
-                    early_term=True, want_counts=False, keep_workspace=False):
+                    early_term=True, want_counts=False, keep_workspace=False, out_rgb=None, out_depth=None):
         """One launch pair (march + shade) over `rays` [N,6|7] on the GPU; no autograd.
 
         Returns a dict with rgb_map [N,3], depth_map [N], acc_map [N] and, when `sample_outputs`, the
@@ -445,8 +445,12 @@ class TensorVMSplit(torch.nn.Module):
         n = rays.shape[0]
         d, keep = self.field_desc()
         lib = _lib.load()
-        out = {"rgb_map": torch.empty((n, 3), device=dev), "depth_map": torch.empty((n,), device=dev),
+        if n == 0:
+            out_rgb = out_depth = None
+        out = {"rgb_map": out_rgb if out_rgb is not None else torch.empty((n, 3), device=dev),
+               "depth_map": out_depth if out_depth is not None else torch.empty((n,), device=dev),
                "acc_map": torch.empty((n,), device=dev)}
+        assert out["rgb_map"].is_contiguous() and out["depth_map"].is_contiguous()
         alpha = z = dists = None
         if sample_outputs:
             alpha, z, dists = (torch.empty((n, S), device=dev) for _ in range(3))
