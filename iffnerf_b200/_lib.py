@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_B200_LIB lets the tuning scripts load a differently-compiled build of the SAME sources
 LIB_PATH = os.environ.get("TVM_B200_LIB") or os.path.join(_HERE, "libtvm_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 F_EARLY_TERM = 1 << 0
 F_MLP_BF16 = 1 << 1
@@ -68,6 +68,10 @@ _SIGNATURES = {
                                 C.c_size_t, _P]),
     "tvm_shade_fwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, _P, C.c_uint32, _P, _P, _P, _P,
                                 C.c_size_t, _P]),
+    "tvm_shade_bwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                C.c_size_t, _P]),
+    "tvm_mlp_grad_floats": (C.c_size_t, [C.POINTER(FieldDesc)]),
+    "tvm_unpack_mlp_grads": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "tvm_workspace_layout": (C.c_int, [C.POINTER(FieldDesc), C.c_int64] + [C.POINTER(C.c_size_t)] * 6),
 }
 

@@ -1,13 +1,13 @@
-"""Autograd glue: the march stage as a torch.autograd.Function over the C ABI.
+"""Autograd glue: the whole differentiable render as ONE torch.autograd.Function over the C ABI.
 
-forward  = tvm_render_fwd(TVM_F_NO_SHADE) -> ray_feat [N, sum(n_app)], acc [N], depth partial [N],
-           alpha / z_vals / dists [N,S]
-backward = tvm_march_bwd (re-march + vector-reduction scatter) -> gradients of the 12 factor tensors in the
-           reference [1,C,H,W] layout and, if the rays require grad (pose refinement), d(rays).
+forward  = tvm_render_fwd (march kernel + fp32 shade kernel) -> rgb_map, depth_map, acc_map, alpha, z_vals, dists
+backward = tvm_shade_bwd (d rgb_map -> d ray_feat, d acc, d viewdirs, d basis_mat, d MLP)
+           -> tvm_march_bwd (re-march; vector-reduction scatter into the packed factor-gradient buffer, d rays)
+           -> [optional data-parallel all-reduce of the packed buffer] -> tvm_unpack_factor_grads / tvm_unpack_mlp_grads
 
-The per-ray shading tail (basis_mat, MLPRender_Fea, background blend; models/tensorBase.py:886-904) runs as
-torch ops ON THE GPU in this differentiable path so that autograd provides d(basis_mat), d(MLP) and
-d(viewdirs); the eval path uses the fused shade kernel instead.
+No torch op touches the render path in either direction; torch only owns the tensors and the autograd graph edge.
+(`render_with_grad_torch_tail` keeps the earlier variant whose per-ray shading tail is torch autograd; it is used by
+tests as an independent cross-check of tvm_shade_bwd.)
 """
 from __future__ import annotations
 
@@ -19,6 +19,115 @@ import torch.nn.functional as F
 from . import _lib
 
 
+def _c(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+def _mlp_params(model):
+    mods = [model.renderModule.mlp[i] for i in (0, 2, 4)]
+    return [mods[0].weight, mods[0].bias, mods[1].weight, mods[1].bias, mods[2].weight, mods[2].bias]
+
+
+class _Render(torch.autograd.Function):
+    """inputs: model, rays, S, jitter, bg, 12 factors, basis, w1, b1, w2, b2, w3, b3"""
+
+    @staticmethod
+    def forward(ctx, model, rays, S, jitter, bg, *params):
+        from .tensorf import _stream
+        rays_c = model._prep_rays(rays)
+        dev = rays_c.device
+        n = rays_c.shape[0]
+        d, keep = model.field_desc()
+        lib = _lib.load()
+        need = C.c_size_t(0)
+        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need)), "tvm_workspace_bytes")
+        ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
+        rgb = torch.empty((n, 3), device=dev)
+        depth = torch.empty((n,), device=dev)
+        acc = torch.empty((n,), device=dev)
+        alpha, z, dists = (torch.empty((n, S), device=dev) for _ in range(3))
+        jit = None if jitter is None else jitter.detach().to(dev).float().reshape(-1).contiguous()
+        bg_c = _c(bg)
+        _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], S, _lib.ptr(jit),
+                                      _lib.ptr(bg_c), 0, _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc),
+                                      _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(dists), None, None, None,
+                                      _lib.ptr(ws), ws.numel(), _stream(dev)), "tvm_render_fwd")
+        ctx.model, ctx.S, ctx.jit, ctx.rays_c, ctx.ws, ctx.bg = model, S, jit, rays_c, ws, bg_c
+        ctx.ray_cols = rays.shape[1]
+        ctx.keys = (model._packed_key, model._mlp_key)
+        ctx.mark_non_differentiable(depth, z, dists)
+        return rgb, depth, acc, alpha, z, dists
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_acc, g_alpha, g_z, g_dists):
+        from .tensorf import _stream
+        model, rays_c = ctx.model, ctx.rays_c
+        dev = rays_c.device
+        n = rays_c.shape[0]
+        need = ctx.needs_input_grad
+        want_rays = need[1]
+        want_factors = any(need[5:17])
+        want_basis = need[17]
+        want_mlp = any(need[18:24])
+        if (model._packed_key, model._mlp_key) != ctx.keys:
+            raise _lib.TvmError("parameters were modified between forward and backward")
+        d, keep = model.field_desc()
+        lib = _lib.load()
+        st = _stream(dev)
+        ta = sum(model.app_n_comp)
+        g_rgb = _c(g_rgb) if g_rgb is not None else torch.zeros((n, 3), device=dev)
+        g_acc, g_alpha = _c(g_acc), _c(g_alpha)
+        d_feat = torch.empty((n, ta), device=dev)
+        d_acc = torch.empty((n,), device=dev)
+        d_view = torch.empty((n, 3), device=dev) if want_rays else None
+        g_basis = torch.zeros_like(model.basis_mat.weight) if want_basis else None
+        g_mlp = torch.zeros(int(lib.tvm_mlp_grad_floats(C.byref(d))), device=dev) if want_mlp else None
+        _lib.check(lib.tvm_shade_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], _lib.ptr(ctx.bg),
+                                     _lib.ptr(g_rgb), _lib.ptr(g_acc), _lib.ptr(d_feat), _lib.ptr(d_acc),
+                                     _lib.ptr(g_basis), _lib.ptr(g_mlp), _lib.ptr(d_view), _lib.ptr(ctx.ws),
+                                     ctx.ws.numel(), st), "tvm_shade_bwd")
+        g_packed = torch.zeros(int(d.n_factor_floats), device=dev) if want_factors else None
+        g_rays6 = torch.zeros((n, 6), device=dev) if want_rays else None
+        _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], ctx.S, _lib.ptr(ctx.jit),
+                                     _lib.ptr(d_feat), _lib.ptr(d_acc), _lib.ptr(g_alpha), _lib.ptr(g_packed),
+                                     _lib.ptr(g_rays6), _lib.ptr(ctx.ws), ctx.ws.numel(), st), "tvm_march_bwd")
+        factor_grads = [None] * 12
+        if want_factors:
+            sync = getattr(model, "grad_sync", None)
+            if sync is not None:
+                # data parallel: ONE all-reduce of the flat packed buffer, on this stream, before unpacking
+                sync.reduce_packed_factor_grads(g_packed)
+            planes, lines = model._factor_params()
+            gp = [torch.empty_like(p) for p in planes]
+            gl = [torch.empty_like(p) for p in lines]
+            _lib.check(lib.tvm_unpack_factor_grads(C.byref(d), _lib.ptr(g_packed), _lib.ptr_array(gp),
+                                                   _lib.ptr_array(gl), 0, st), "tvm_unpack_factor_grads")
+            factor_grads = gp + gl
+        mlp_grads = [None] * 6
+        if want_mlp:
+            mlp_grads = [torch.empty_like(p) for p in _mlp_params(model)]
+            _lib.check(lib.tvm_unpack_mlp_grads(C.byref(d), _lib.ptr(g_mlp), *[_lib.ptr(t) for t in mlp_grads], 0, st),
+                       "tvm_unpack_mlp_grads")
+        d_rays = None
+        if want_rays:
+            d_rays = torch.zeros((n, ctx.ray_cols), device=dev)
+            d_rays[:, :6] = g_rays6
+            d_rays[:, 3:6] += d_view
+        return (None, d_rays, None, None, None, *factor_grads, g_basis, *mlp_grads)
+
+
+def render_with_grad(model, rays_chunk, white_bg, bg_color, N_samples, jitter):
+    """Differentiable TensorBase.forward (models/tensorBase.py:775-917): 6-tuple, `depth_map` without grad."""
+    S = N_samples if N_samples > 0 else model.nSamples
+    planes, lines = model._factor_params()
+    rays = rays_chunk if rays_chunk.dtype == torch.float32 else rays_chunk.float()
+    bg = model._bg(bg_color, white_bg, rays.device)
+    return _Render.apply(model, rays, S, jitter, bg, *planes, *lines, model.basis_mat.weight, *_mlp_params(model))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# cross-check variant: march stage through the C ABI, shading tail as torch autograd (cuBLAS)
+# ----------------------------------------------------------------------------------------------------------------
 class _March(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, rays, S, jitter, *factors):
@@ -41,7 +150,6 @@ class _March(torch.autograd.Function):
         v = model.workspace_views(d, ws, n)
         ctx.model, ctx.S, ctx.jit, ctx.rays_c, ctx.ws = model, S, jit, rays_c, ws
         ctx.ray_cols = rays.shape[1]
-        ctx.packed_key = model._packed_key
         ctx.mark_non_differentiable(v["depth"], z, dists, v["app_count"])
         return v["ray_feat"], v["acc"], v["depth"], alpha, z, dists, v["app_count"]
 
@@ -53,26 +161,16 @@ class _March(torch.autograd.Function):
         n = rays_c.shape[0]
         want_rays = ctx.needs_input_grad[1]
         want_factors = any(ctx.needs_input_grad[4:])
-        if model._packed_key != ctx.packed_key:
-            raise _lib.TvmError("factor parameters were modified between forward and backward")
         d, keep = model.field_desc()
         lib = _lib.load()
         g_packed = torch.zeros(int(d.n_factor_floats), device=dev) if want_factors else None
         g_rays = torch.zeros((n, 6), device=dev) if want_rays else None
-
-        def c(t):
-            return None if t is None else t.detach().float().contiguous()
-        g_feat, g_acc, g_alpha = c(g_feat), c(g_acc), c(g_alpha)
         _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], ctx.S, _lib.ptr(ctx.jit),
-                                     _lib.ptr(g_feat), _lib.ptr(g_acc), _lib.ptr(g_alpha), _lib.ptr(g_packed),
-                                     _lib.ptr(g_rays), _lib.ptr(ctx.ws), ctx.ws.numel(), _stream(dev)),
-                   "tvm_march_bwd")
+                                     _lib.ptr(_c(g_feat)), _lib.ptr(_c(g_acc)), _lib.ptr(_c(g_alpha)),
+                                     _lib.ptr(g_packed), _lib.ptr(g_rays), _lib.ptr(ctx.ws), ctx.ws.numel(),
+                                     _stream(dev)), "tvm_march_bwd")
         grads = [None] * 12
         if want_factors:
-            sync = getattr(model, "grad_sync", None)
-            if sync is not None:
-                # data parallel: ONE all-reduce of the flat packed buffer, on this stream, before unpacking
-                sync.reduce_packed_factor_grads(g_packed)
             planes, lines = model._factor_params()
             gp = [torch.empty_like(p) for p in planes]
             gl = [torch.empty_like(p) for p in lines]
@@ -86,8 +184,7 @@ class _March(torch.autograd.Function):
         return (None, d_rays, None, None, *grads)
 
 
-def render_with_grad(model, rays_chunk, white_bg, bg_color, N_samples, jitter):
-    """Differentiable TensorBase.forward (models/tensorBase.py:775-917): 6-tuple, `depth_map` without grad."""
+def render_with_grad_torch_tail(model, rays_chunk, white_bg, bg_color, N_samples, jitter):
     S = N_samples if N_samples > 0 else model.nSamples
     planes, lines = model._factor_params()
     rays = rays_chunk if rays_chunk.dtype == torch.float32 else rays_chunk.float()
@@ -95,7 +192,7 @@ def render_with_grad(model, rays_chunk, white_bg, bg_color, N_samples, jitter):
     view = rays[:, 3:6]
     feat = F.linear(ray_feat, model.basis_mat.weight)
     rgb, _ = model.renderModule(None, view, feat, None)
-    rgb = rgb * (app_count > 0).to(rgb.dtype)[:, None]            # rays_to_consider (:886-896), no host sync
+    rgb = rgb * (app_count > 0).to(rgb.dtype)[:, None]
     if bg_color is None:
         bg_color = model._bg(None, white_bg, rays.device)
     rgb_map = (rgb * acc[..., None] + bg_color * (1.0 - acc[..., None])).clamp(0, 1)

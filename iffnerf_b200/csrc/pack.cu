@@ -111,6 +111,13 @@ __global__ void untranspose_small_kernel(const float* __restrict__ src, float* _
     const float v = __ldg(src + k * R + r);
     dst[i] = accumulate ? dst[i] + v : v;
 }
+// src [R][Cc] -> dst [R][kpad] (zero padded columns)
+__global__ void pad_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int Cc, int kpad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * kpad) return;
+    const int r = i / kpad, k = i - r * kpad;
+    dst[i] = (k < Cc) ? __ldg(src + r * Cc + k) : 0.f;
+}
 __global__ void copy_small_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int npad,
                                   int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -225,6 +232,30 @@ extern "C" int tvm_pack_mlp(const tvm_field_desc* desc, const float* w1, const f
     copy_small_kernel<<<1, 256, 0, st>>>(b2, packed + m.b2, FC, FC, 0);
     copy_small_kernel<<<2, 256, 0, st>>>(w3, packed + m.w3, 3 * FC, 3 * FC, 0);
     copy_small_kernel<<<1, 32, 0, st>>>(b3, packed + m.b3, 3, 4, 0);
+    pad_cols_kernel<<<(FC * m.k1 + 255) / 256, 256, 0, st>>>(w1, packed + m.w1n, FC, m.in_c, m.k1);
+    copy_small_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(w2, packed + m.w2n, FC * FC, FC * FC, 0);
+    TVM_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t tvm_mlp_grad_floats(const tvm_field_desc* desc) {
+    if (!desc) return 0;
+    return tvm_mlp_layout(desc).grad_total;
+}
+
+extern "C" int tvm_unpack_mlp_grads(const tvm_field_desc* desc, const float* packed_grad, float* w1, float* b1,
+                                    float* w2, float* b2, float* w3, float* b3, int accumulate, void* stream) {
+    if (!desc || !packed_grad) return TVM_E_NULL;
+    if (desc->feature_c != TVM_FEATURE_C) return TVM_E_SHAPE;
+    const TvmMlpLayout m = tvm_mlp_layout(desc);
+    const int FC = TVM_FEATURE_C;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (w1) untranspose_small_kernel<<<(FC * m.in_c + 255) / 256, 256, 0, st>>>(packed_grad + m.w1t, w1, FC, m.in_c, accumulate);
+    if (b1) copy_small_kernel<<<1, 256, 0, st>>>(packed_grad + m.b1, b1, FC, FC, accumulate);
+    if (w2) untranspose_small_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(packed_grad + m.w2t, w2, FC, FC, accumulate);
+    if (b2) copy_small_kernel<<<1, 256, 0, st>>>(packed_grad + m.b2, b2, FC, FC, accumulate);
+    if (w3) copy_small_kernel<<<2, 256, 0, st>>>(packed_grad + m.w3, w3, 3 * FC, 3 * FC, accumulate);
+    if (b3) copy_small_kernel<<<1, 32, 0, st>>>(packed_grad + m.b3, b3, 3, 3, accumulate);
     TVM_LAUNCH_CHECK();
     return 0;
 }

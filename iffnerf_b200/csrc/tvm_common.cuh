@@ -48,9 +48,10 @@ static inline TvmWorkspace tvm_ws_layout(const tvm_field_desc* d, int64_t n) {
 }
 
 // Packed MLP layout (floats): W1^T [k1][FC] (rows >= in_c are zero) | b1 [FC] | W2^T [FC][FC] | b2 [FC] | W3 [3][FC] | b3 [4]
+//   | W1 [FC][k1] (cols >= in_c zero) | W2 [FC][FC]
 struct TvmMlpLayout {
     int in_c, k1;
-    size_t w1t, b1, w2t, b2, w3, b3, total;
+    size_t w1t, b1, w2t, b2, w3, b3, grad_total, w1n, w2n, total;
 };
 static inline TvmMlpLayout tvm_mlp_layout(const tvm_field_desc* d) {
     TvmMlpLayout m;
@@ -64,6 +65,9 @@ static inline TvmMlpLayout tvm_mlp_layout(const tvm_field_desc* d) {
     m.b2 = off;  off += FC;
     m.w3 = off;  off += 3 * FC;
     m.b3 = off;  off += 4;
+    m.grad_total = off;                 // the gradient buffer of tvm_shade_bwd covers [0, grad_total)
+    m.w1n = off; off += FC * (size_t)m.k1;   // W1 [FC][k1] and W2 [FC][FC] in torch orientation (backward GEMMs)
+    m.w2n = off; off += FC * FC;
     m.total = off;
     return m;
 }

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 5
+#define TVM_ABI_VERSION 6
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define TVM_E_NULL        (-1)   /* required pointer is NULL                      */
@@ -156,6 +156,20 @@ int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays,
                   const float* bg /* device [3] */,
                   uint32_t flags, float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes,
                   void* stream);
+
+/* Backward of the shade stage (replaces autograd through basis_mat, MLPRender_Fea and the blend/clamp,
+ * tensorBase.py:886-904).  d_rgb [n][3] (+ optional upstream d_acc_in [n] on the acc_map output) ->
+ * d_ray_feat [n][sum(n_app)] and d_acc [n] (the inputs of tvm_march_bwd), optional d_view [n][3] (pose mode) and,
+ * when non-NULL, ACCUMULATED parameter gradients g_basis [app_dim][sum(n_app)] (torch layout) and g_mlp
+ * (tvm_mlp_grad_floats() floats, packed layout of tvm_pack_mlp; caller zeroes them). */
+int tvm_shade_bwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
+                  const float* bg /* device [3] */, const float* d_rgb, const float* d_acc_in, float* d_ray_feat,
+                  float* d_acc, float* g_basis, float* g_mlp, float* d_view, const void* ws, size_t ws_bytes,
+                  void* stream);
+size_t tvm_mlp_grad_floats(const tvm_field_desc* desc);
+/* packed MLP gradient -> torch-layout tensors (w1 [C,in], b1, w2 [C,C], b2, w3 [3,C], b3); accumulate != 0 adds */
+int tvm_unpack_mlp_grads(const tvm_field_desc* desc, const float* packed_grad, float* w1, float* b1, float* w2,
+                         float* b2, float* w3, float* b3, int accumulate, void* stream);
 
 /* workspace layout helpers (byte offsets inside ws for n_rays) so the host can view the march outputs */
 int tvm_workspace_layout(const tvm_field_desc* desc, int64_t n_rays, size_t* ray_feat_off, size_t* acc_off,
