@@ -12,11 +12,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_B200_LIB lets the tuning scripts load a differently-compiled build of the SAME sources
 LIB_PATH = os.environ.get("TVM_B200_LIB") or os.path.join(_HERE, "libtvm_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 F_EARLY_TERM = 1 << 0
 F_MLP_BF16 = 1 << 1
 F_NO_SHADE = 1 << 2
+F_POINT_SAMPLES = 1 << 3
 
 _f3 = C.c_float * 3
 _f6 = C.c_float * 6
@@ -60,18 +61,19 @@ _SIGNATURES = {
     "tvm_pack_mlp": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "tvm_mlp_tc_pack_bytes": (C.c_size_t, [C.POINTER(FieldDesc)]),
     "tvm_pack_mlp_tc": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P]),
-    "tvm_sample_mask": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "tvm_sample_mask": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_int, _P, C.c_uint32, _P, _P, _P]),
     "tvm_workspace_bytes": (C.c_int, [C.POINTER(FieldDesc), C.c_int64, C.c_uint32, C.POINTER(C.c_size_t)]),
     "tvm_render_fwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_uint32,
                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
-    "tvm_march_bwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P,
-                                C.c_size_t, _P]),
+    "tvm_march_bwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_int, _P, C.c_uint32, _P, _P, _P, _P,
+                                _P, _P, C.c_size_t, _P]),
     "tvm_shade_fwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, _P, C.c_uint32, _P, _P, _P, _P,
                                 C.c_size_t, _P]),
     "tvm_shade_bwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                 C.c_size_t, _P]),
     "tvm_mlp_grad_floats": (C.c_size_t, [C.POINTER(FieldDesc)]),
     "tvm_unpack_mlp_grads": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "tvm_point_density": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_float, _P, _P]),
     "tvm_workspace_layout": (C.c_int, [C.POINTER(FieldDesc), C.c_int64] + [C.POINTER(C.c_size_t)] * 6),
 }
 

@@ -29,10 +29,10 @@ def _mlp_params(model):
 
 
 class _Render(torch.autograd.Function):
-    """inputs: model, rays, S, jitter, bg, 12 factors, basis, w1, b1, w2, b2, w3, b3"""
+    """inputs: model, rays, S, jitter, bg, flags, 12 factors, basis, w1, b1, w2, b2, w3, b3"""
 
     @staticmethod
-    def forward(ctx, model, rays, S, jitter, bg, *params):
+    def forward(ctx, model, rays, S, jitter, bg, flags, *params):
         from .tensorf import _stream
         rays_c = model._prep_rays(rays)
         dev = rays_c.device
@@ -49,11 +49,12 @@ class _Render(torch.autograd.Function):
         jit = None if jitter is None else jitter.detach().to(dev).float().reshape(-1).contiguous()
         bg_c = _c(bg)
         _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], S, _lib.ptr(jit),
-                                      _lib.ptr(bg_c), 0, _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc),
+                                      _lib.ptr(bg_c), flags, _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc),
                                       _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(dists), None, None, None,
                                       _lib.ptr(ws), ws.numel(), _stream(dev)), "tvm_render_fwd")
         ctx.model, ctx.S, ctx.jit, ctx.rays_c, ctx.ws, ctx.bg = model, S, jit, rays_c, ws, bg_c
         ctx.ray_cols = rays.shape[1]
+        ctx.flags = flags
         ctx.keys = (model._packed_key, model._mlp_key)
         ctx.mark_non_differentiable(depth, z, dists)
         return rgb, depth, acc, alpha, z, dists
@@ -66,9 +67,9 @@ class _Render(torch.autograd.Function):
         n = rays_c.shape[0]
         need = ctx.needs_input_grad
         want_rays = need[1]
-        want_factors = any(need[5:17])
-        want_basis = need[17]
-        want_mlp = any(need[18:24])
+        want_factors = any(need[6:18])
+        want_basis = need[18]
+        want_mlp = any(need[19:25])
         if (model._packed_key, model._mlp_key) != ctx.keys:
             raise _lib.TvmError("parameters were modified between forward and backward")
         d, keep = model.field_desc()
@@ -89,7 +90,7 @@ class _Render(torch.autograd.Function):
         g_packed = torch.zeros(int(d.n_factor_floats), device=dev) if want_factors else None
         g_rays6 = torch.zeros((n, 6), device=dev) if want_rays else None
         _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], ctx.S, _lib.ptr(ctx.jit),
-                                     _lib.ptr(d_feat), _lib.ptr(d_acc), _lib.ptr(g_alpha), _lib.ptr(g_packed),
+                                     ctx.flags, _lib.ptr(d_feat), _lib.ptr(d_acc), _lib.ptr(g_alpha), _lib.ptr(g_packed),
                                      _lib.ptr(g_rays6), _lib.ptr(ctx.ws), ctx.ws.numel(), st), "tvm_march_bwd")
         factor_grads = [None] * 12
         if want_factors:
@@ -113,16 +114,18 @@ class _Render(torch.autograd.Function):
             d_rays = torch.zeros((n, ctx.ray_cols), device=dev)
             d_rays[:, :6] = g_rays6
             d_rays[:, 3:6] += d_view
-        return (None, d_rays, None, None, None, *factor_grads, g_basis, *mlp_grads)
+        return (None, d_rays, None, None, None, None, *factor_grads, g_basis, *mlp_grads)
 
 
-def render_with_grad(model, rays_chunk, white_bg, bg_color, N_samples, jitter):
+def render_with_grad(model, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples=False):
     """Differentiable TensorBase.forward (models/tensorBase.py:775-917): 6-tuple, `depth_map` without grad."""
     S = N_samples if N_samples > 0 else model.nSamples
     planes, lines = model._factor_params()
     rays = rays_chunk if rays_chunk.dtype == torch.float32 else rays_chunk.float()
     bg = model._bg(bg_color, white_bg, rays.device)
-    return _Render.apply(model, rays, S, jitter, bg, *planes, *lines, model.basis_mat.weight, *_mlp_params(model))
+    flags = _lib.F_POINT_SAMPLES if point_samples else 0
+    return _Render.apply(model, rays, S, jitter, bg, flags, *planes, *lines, model.basis_mat.weight,
+                         *_mlp_params(model))
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -165,7 +168,7 @@ class _March(torch.autograd.Function):
         lib = _lib.load()
         g_packed = torch.zeros(int(d.n_factor_floats), device=dev) if want_factors else None
         g_rays = torch.zeros((n, 6), device=dev) if want_rays else None
-        _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], ctx.S, _lib.ptr(ctx.jit),
+        _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], ctx.S, _lib.ptr(ctx.jit), 0,
                                      _lib.ptr(_c(g_feat)), _lib.ptr(_c(g_acc)), _lib.ptr(_c(g_alpha)),
                                      _lib.ptr(g_packed), _lib.ptr(g_rays), _lib.ptr(ctx.ws), ctx.ws.numel(),
                                      _stream(dev)), "tvm_march_bwd")

@@ -94,8 +94,7 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
 #pragma unroll
             for (int c = 0; c < 3; ++c) { ray.o[c] = __ldg(rp + c); ray.d[c] = __ldg(rp + 3 + c); }
         }
-        ray.t0 = tvm_ray_entry(f, ray.o, ray.d);
-        ray.jit = a.jitter ? __ldg(a.jitter + r) : 0.f;
+        tvm_init_ray(f, ray, a.jitter ? __ldg(a.jitter + r) : 0.f, a.S, (a.flags & TVM_F_POINT_SAMPLES) != 0);
 
         float T = 1.f, acc = 0.f, dep = 0.f;
         int n_valid = 0, n_sigma = 0, n_app = 0, n_occ = 0;
@@ -275,11 +274,12 @@ int launch(K kernel, MarchArgs& a, cudaStream_t st) {
 }  // namespace
 
 extern "C" int tvm_sample_mask(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
-                               int n_samples, const float* jitter, uint32_t* valid_bits, int32_t* counts,
-                               void* stream) {
+                               int n_samples, const float* jitter, uint32_t flags, uint32_t* valid_bits,
+                               int32_t* counts, void* stream) {
     MarchArgs a;
     int rc = fill_args(a, desc, rays, n_rays, ray_stride, n_samples, jitter);
     if (rc) return rc;
+    a.flags = flags;
     a.valid_bits = valid_bits;
     a.valid_count = counts;
     return launch(march_fwd_kernel<1, true, 0, 0>, a, (cudaStream_t)stream);

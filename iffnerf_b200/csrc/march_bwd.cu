@@ -29,6 +29,7 @@ struct BwdArgs {
     int ray_stride;
     int S;
     const float* jitter;
+    unsigned flags;
     const float* d_ray_feat;   // [n][ta] or NULL
     const float* d_acc;        // [n] or NULL
     const float* d_alpha;      // [n][S] or NULL
@@ -76,8 +77,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
 #pragma unroll
             for (int c = 0; c < 3; ++c) { ray.o[c] = __ldg(rp + c); ray.d[c] = __ldg(rp + 3 + c); }
         }
-        ray.t0 = tvm_ray_entry(f, ray.o, ray.d);
-        ray.jit = a.jitter ? __ldg(a.jitter + r) : 0.f;
+        tvm_init_ray(f, ray, a.jitter ? __ldg(a.jitter + r) : 0.f, a.S, (a.flags & TVM_F_POINT_SAMPLES) != 0);
 
         // upstream gradients of this ray, distributed like the forward's accumulator
         float4 gF[3][G];
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_
                     const float m = fminf(ra, rb);
                     if (m > best) { best = m; bc = cc; bv = v; bzero = zero; }
                 }
-                if (best >= f.near_t && best <= f.far_t) {         // clamp passes the gradient only inside [near, far]
+                if (!(a.flags & TVM_F_POINT_SAMPLES) && best >= f.near_t && best <= f.far_t) {   // clamp passes the gradient only inside [near, far]
                     const float inv = 1.f / bv;
                     go[bc] -= gt0 * inv;
                     if (!bzero) gd[bc] -= gt0 * best * inv;
@@ -284,9 +284,9 @@ int dispatch(const BwdArgs& a, cudaStream_t st) {
 }  // namespace
 
 extern "C" int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
-                             int n_samples, const float* jitter, const float* d_ray_feat, const float* d_acc,
-                             const float* d_alpha, float* g_factors, float* g_rays, const void* ws, size_t ws_bytes,
-                             void* stream) {
+                             int n_samples, const float* jitter, uint32_t flags, const float* d_ray_feat,
+                             const float* d_acc, const float* d_alpha, float* g_factors, float* g_rays,
+                             const void* ws, size_t ws_bytes, void* stream) {
     int rc = tvm_check_desc(desc);
     if (rc) return rc;
     if (ray_stride < 6 || n_samples <= 0 || n_samples > 32 * TVM_MAX_BLOCKS || n_rays < 0) return TVM_E_SHAPE;
@@ -297,6 +297,7 @@ extern "C" int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int6
     BwdArgs a{};
     a.f = *desc;
     a.rays = rays; a.n_rays = n_rays; a.ray_stride = ray_stride; a.S = n_samples; a.jitter = jitter;
+    a.flags = flags;
     a.d_ray_feat = d_ray_feat; a.d_acc = d_acc; a.d_alpha = d_alpha;
     a.g_factors = g_factors; a.g_rays = g_rays;
     a.ray_feat = (const float*)((const char*)ws + w.ray_feat);

@@ -42,6 +42,7 @@ struct TvmRay {
     float d[3];
     float t0;      // clamped slab-entry distance (sample 0)
     float jit;     // per-ray jitter (0 in eval)
+    int i_off;     // sample-index offset: 0 for sample_ray, -(S/2) for sample_point_color
 };
 
 // t_min of sample_ray (models/tensorBase.py:499-502):
@@ -61,9 +62,18 @@ TVM_HD float tvm_ray_entry(const tvm_field_desc& f, const float o[3], const floa
     return t;
 }
 
+// Sampler set-up.  sample_ray (models/tensorBase.py:494-536): t0 = clamped slab entry, indices 0..S-1 (+ jitter).
+// sample_point_color (:623-638, TVM_F_POINT_SAMPLES): S samples centred on the origin, z_i = stepSize*(i - S/2),
+// i.e. t0 = 0 (x + 0 is exact) and an index offset of -(S/2); no near/far clamp, no jitter.
+TVM_HD void tvm_init_ray(const tvm_field_desc& f, TvmRay& r, float jitter, int S, bool point_samples) {
+    r.t0 = point_samples ? 0.0f : tvm_ray_entry(f, r.o, r.d);
+    r.jit = point_samples ? 0.0f : jitter;
+    r.i_off = point_samples ? -(S / 2) : 0;
+}
+
 // z_i = t0 + stepSize * (float(i) + jitter)      (models/tensorBase.py:504-529)
 TVM_HD float tvm_sample_z(const tvm_field_desc& f, const TvmRay& r, int i) {
-    float rng = rn_add((float)i, r.jit);
+    float rng = rn_add((float)(i + r.i_off), r.jit);
     return rn_add(r.t0, rn_mul(f.step_size, rng));
 }
 

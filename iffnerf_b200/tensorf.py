@@ -19,6 +19,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from .field_ops import FieldOpsMixin
 
 MAT_MODE = [[0, 1], [0, 2], [1, 2]]
 VEC_MODE = [2, 1, 0]
@@ -108,7 +109,7 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-class TensorVMSplit(torch.nn.Module):
+class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
     """VM-decomposed radiance field with a B200-native renderer.
 
     Constructor signature and defaults follow TensorBase.__init__ (models/tensorBase.py:262-326)."""
@@ -417,7 +418,7 @@ class TensorVMSplit(torch.nn.Module):
 
     # ------------------------------------------------------------------ kernels
     @torch.no_grad()
-    def sample_mask(self, rays, N_samples=-1, jitter=None, want_bits=True):
+    def sample_mask(self, rays, N_samples=-1, jitter=None, want_bits=True, point_samples=False):
         """`ray_valid` of TensorBase.forward (sample_ray + aabb + alphaMask, tensorBase.py:820-837) as packed bits
         [N, ceil(S/32)] (int32 view of uint32 words) and per-ray counts.  Bit-exact w.r.t. the reference."""
         rays = self._prep_rays(rays)
@@ -428,13 +429,15 @@ class TensorVMSplit(torch.nn.Module):
         counts = torch.empty((n,), dtype=torch.int32, device=rays.device)
         jit = None if jitter is None else jitter.detach().float().reshape(-1).contiguous()
         lib = _lib.load()
-        _lib.check(lib.tvm_sample_mask(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, _lib.ptr(jit), _lib.ptr(bits),
+        _lib.check(lib.tvm_sample_mask(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, _lib.ptr(jit),
+                                       _lib.F_POINT_SAMPLES if point_samples else 0, _lib.ptr(bits),
                                        _lib.ptr(counts), _stream(rays.device)), "tvm_sample_mask")
         return bits, counts
 
     @torch.no_grad()
     def render_eval(self, rays, N_samples=-1, white_bg=False, bg_color=None, jitter=None, sample_outputs=False,
-                    early_term=True, want_counts=False, keep_workspace=False, out_rgb=None, out_depth=None):
+                    early_term=True, want_counts=False, keep_workspace=False, out_rgb=None, out_depth=None,
+                    point_samples=False):
         """One launch pair (march + shade) over `rays` [N,6|7] on the GPU; no autograd.
 
         Returns a dict with rgb_map [N,3], depth_map [N], acc_map [N] and, when `sample_outputs`, the
@@ -466,6 +469,8 @@ class TensorVMSplit(torch.nn.Module):
         flags = _lib.F_EARLY_TERM if (early_term and not sample_outputs) else 0
         if self.mlp_precision == "bf16":
             flags |= _lib.F_MLP_BF16
+        if point_samples:
+            flags |= _lib.F_POINT_SAMPLES
         jit = None if jitter is None else jitter.detach().to(dev).float().reshape(-1).contiguous()
         bg = self._bg(bg_color, white_bg, dev)
         _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, _lib.ptr(jit), _lib.ptr(bg),
@@ -501,8 +506,15 @@ class TensorVMSplit(torch.nn.Module):
         torch.rand on the rays' device, one value per ray, as the reference does (:507-509)."""
         if ndc_ray:
             raise NotImplementedError("ndc_ray sampling is outside the B200 render path (LLFF only, SURVEY.md 2.1)")
+        point_samples = False
         if sample_func is not None:
-            raise NotImplementedError("sample_func variants are not on the B200 render path yet (SURVEY.md 8f-2)")
+            if getattr(sample_func, "__func__", None) is not FieldOpsMixin.sample_point_color or \
+                    getattr(sample_func, "__self__", None) is not self:
+                raise NotImplementedError("only sample_func=model.sample_point_color is on the B200 render path")
+            point_samples = True                       # sample_point_color (tensorBase.py:623-638): no jitter
+            is_train = False
+            if N_samples <= 0:
+                N_samples = 20
         if is_train and jitter is None:
             jitter = torch.rand(rays_chunk.shape[0], device=rays_chunk.device)
         if not is_train:
@@ -511,7 +523,12 @@ class TensorVMSplit(torch.nn.Module):
             rays_chunk.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
             from .autograd import render_with_grad
-            return render_with_grad(self, rays_chunk, white_bg, bg_color, N_samples, jitter)
-        o = self.render_eval(rays_chunk, N_samples=N_samples, white_bg=white_bg, bg_color=bg_color, jitter=jitter,
-                             sample_outputs=True)
-        return o["rgb_map"], o["depth_map"], o["acc_map"], o["alpha"], o["z_vals"], o["dists"]
+            out = render_with_grad(self, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples)
+        else:
+            o = self.render_eval(rays_chunk, N_samples=N_samples, white_bg=white_bg, bg_color=bg_color, jitter=jitter,
+                                 sample_outputs=True, point_samples=point_samples)
+            out = (o["rgb_map"], o["depth_map"], o["acc_map"], o["alpha"], o["z_vals"], o["dists"])
+        if point_samples:
+            # the reference's sampler returns ONE broadcast row of z values ([1,S], tensorBase.py:628-638)
+            out = out[:4] + (out[4][:1], out[5][:1])
+        return out

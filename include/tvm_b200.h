@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 6
+#define TVM_ABI_VERSION 7
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define TVM_E_NULL        (-1)   /* required pointer is NULL                      */
@@ -37,6 +37,8 @@ extern "C" {
 #define TVM_F_EARLY_TERM   (1u << 0)  /* eval only: stop a ray once T < early_term_eps                      */
 #define TVM_F_MLP_BF16     (1u << 1)  /* shade with the bf16 tensor-core MLP (tolerance 1e-2) instead of fp32 */
 #define TVM_F_NO_SHADE     (1u << 2)  /* stop after the march stage: workspace holds ray_feat/acc/depth      */
+#define TVM_F_POINT_SAMPLES (1u << 3) /* sampler of sample_point_color (tensorBase.py:623-638): n_samples samples
+                                         centred on the ray origin, z_i = stepSize*(i - n_samples/2)          */
 
 /*
  * Field descriptor (POD, passed by pointer from the host; copied into kernel params).
@@ -124,7 +126,7 @@ int tvm_pack_mlp_tc(const tvm_field_desc* desc, const float* basis, const float*
  * (train, one U[0,1) per ray, :507-509).  valid_bits: [n_rays][ceil(n_samples/32)] little-endian bit i%32
  * of word i/32 = ray_valid[i] (nullable); counts: [n_rays] = popcount (nullable). */
 int tvm_sample_mask(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,
-                    const float* jitter, uint32_t* valid_bits, int32_t* counts, void* stream);
+                    const float* jitter, uint32_t flags, uint32_t* valid_bits, int32_t* counts, void* stream);
 
 /* bytes of scratch tvm_render_fwd needs for n_rays (ray_feat [n][sum(n_app)], acc, depth, counters). */
 int tvm_workspace_bytes(const tvm_field_desc* desc, int64_t n_rays, uint32_t flags, size_t* out);
@@ -147,8 +149,9 @@ int tvm_render_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays
  * (tvm_render_fwd with the same rays / n_samples / jitter; replaces autograd through grid_sampler_2d_backward,
  * cumprod, softplus ... driven by train.py:338 and inerf/estimate_pose_inerf.py:178). */
 int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,
-                  const float* jitter, const float* d_ray_feat, const float* d_acc, const float* d_alpha,
-                  float* g_factors, float* g_rays, const void* ws, size_t ws_bytes, void* stream);
+                  const float* jitter, uint32_t flags, const float* d_ray_feat, const float* d_acc,
+                  const float* d_alpha, float* g_factors, float* g_rays, const void* ws, size_t ws_bytes,
+                  void* stream);
 
 /* Shade stage alone (basis_mat + MLPRender_Fea + background blend + depth tail, tensorBase.py:886-908),
  * reading ray_feat/acc/depth partials from ws. */
@@ -170,6 +173,12 @@ size_t tvm_mlp_grad_floats(const tvm_field_desc* desc);
 /* packed MLP gradient -> torch-layout tensors (w1 [C,in], b1, w2 [C,C], b2, w3 [3,C], b3); accumulate != 0 adds */
 int tvm_unpack_mlp_grads(const tvm_field_desc* desc, const float* packed_grad, float* w1, float* b1, float* w2,
                          float* b2, float* w3, float* b3, int accumulate, void* stream);
+
+/* Point queries of the density field (no rays).  mode 0: `points` are normalised coordinates, out = raw sigma feature
+ * (TensorVMSplit.compute_densityfeature, tensoRF.py:216-235).  mode 1: `points` are world coordinates, out =
+ * 1 - exp(-sigma*length) gated by the alphaMask (TensorBase.compute_alpha, tensorBase.py:756-773). */
+int tvm_point_density(const tvm_field_desc* desc, const float* points /* [n][3] */, int64_t n_points, int mode,
+                      float length, float* out /* [n] */, void* stream);
 
 /* workspace layout helpers (byte offsets inside ws for n_rays) so the host can view the march outputs */
 int tvm_workspace_layout(const tvm_field_desc* desc, int64_t n_rays, size_t* ray_feat_off, size_t* acc_off,

@@ -170,6 +170,37 @@ def pose_case(R, name, fld, rays):
           f"oracle==reference bit-exact")
 
 
+def point_case(R, name, fld, rays6):
+    """model(rays, N_samples=20, sample_func=model.sample_point_color) and compute_alpha(points)."""
+    t = time.time()
+    m = build_reference_model(R, fld)
+    with torch.no_grad():
+        rgb, depth, acc, alpha, z, dists = m(rays6, N_samples=20, sample_func=m.sample_point_color, white_bg=True)
+        o = orc.render_chunk(fld, rays6, white_bg=True, n_samples=20, point_samples=True)
+        pts = rays6[:, :3] + 0.05 * rays6[:, 3:6]
+        a_ref = m.compute_alpha(pts, length=m.stepSize.item())
+        a_orc = orc.point_alpha(fld, pts, m.stepSize.item())
+        f_ref = m.compute_densityfeature(m.normalize_coord(pts))
+    assert torch.equal(rgb, o["rgb_map"]) and torch.equal(alpha, o["alpha"]) and torch.equal(depth, o["depth_map"])
+    assert z.shape == (1, 20) and torch.equal(z, o["z_vals"]) and torch.equal(a_ref, a_orc)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), rgb_map=rgb.numpy(), depth_map=depth.numpy(),
+                        acc_map=acc.numpy(), alpha=alpha.numpy(), z_vals=z.numpy(), dists=dists.numpy(),
+                        points=pts.numpy(), point_alpha=a_ref.numpy(), point_feature=f_ref.numpy(),
+                        param_checksum=fx.param_checksum(fld))
+    print(f"[golden] {name}: rays={rays6.shape[0]} lit={(acc > 0).float().mean():.3f} ({time.time()-t:.1f}s) "
+          f"oracle==reference bit-exact")
+
+
+def point_rays(fld, n, seed=11):
+    """Points near the occupied shell with isocell-like random directions (6-col rays)."""
+    g = torch.Generator().manual_seed(seed)
+    p = torch.randn(n, 3, generator=g)
+    p = p / p.norm(dim=-1, keepdim=True) * (0.55 + 0.5 * torch.rand(n, 1, generator=g))
+    d = torch.randn(n, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    return torch.cat([p, d], -1).contiguous()
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = import_reference()
@@ -200,6 +231,9 @@ def main():
         if want("c5_pose"):
             sub, idx = fx.subsample(rays, 512, seed=2)
             pose_case(R, "c5_pose", fld, sub)
+    if want("c1_point20"):
+        fld, _ = fx.config1(density_shift=0.0, occupancy="sphere", cols=6)
+        point_case(R, "c1_point20", fld, point_rays(fld, 4096))
     if want("c4_sub"):
         fld, rays = fx.config4()
         sub, idx = fx.subsample(rays, 2048, seed=0)

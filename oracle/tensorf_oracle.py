@@ -137,6 +137,46 @@ def sample_along_rays(fld: Field, o, d, n_samples: int, jitter=None):
     return pts, z, ~outside
 
 
+def sample_around_points(fld: Field, o, d, n_samples: int):
+    """sample_point_color, models/tensorBase.py:623-638: n samples centred on the origin, z = step*(i - n//2)."""
+    geo = step_geometry(fld.aabb, fld.grid, fld.step_ratio)
+    before = n_samples // 2
+    idx = torch.arange(-before, n_samples - before, dtype=o.dtype)[None]
+    z = geo["stepSize"] * idx
+    pts = o[..., None, :] + d[..., None, :] * z[..., None]
+    outside = ((fld.aabb[0] > pts) | (pts > fld.aabb[1])).any(dim=-1)
+    return pts, z, ~outside
+
+
+def point_alpha(fld: Field, pts, length=1.0):
+    """TensorBase.compute_alpha, models/tensorBase.py:756-773."""
+    if fld.occupancy is not None:
+        keep = occupancy_value(fld.occupancy, pts) > 0
+    else:
+        keep = torch.ones_like(pts[:, 0], dtype=bool)
+    sigma = torch.zeros(pts.shape[:-1])
+    if keep.any():
+        sigma[keep] = to_density(fld, density_feature(fld, normalize(fld, pts[keep])))
+    return 1 - torch.exp(-sigma * length).view(pts.shape[:-1])
+
+
+def dense_alpha_volume(fld: Field, grid=(200, 200, 200), thres=1e-4):
+    """getDenseAlpha + updateAlphaMask, models/tensorBase.py:643-696 -> ({0,1} volume [Dz,Dy,Dx], tight aabb)."""
+    geo = step_geometry(fld.aabb, fld.grid, fld.step_ratio)
+    samples = torch.stack(torch.meshgrid(torch.linspace(0, 1, grid[0]), torch.linspace(0, 1, grid[1]),
+                                         torch.linspace(0, 1, grid[2]), indexing="ij"), -1)
+    dense = fld.aabb[0] * (1 - samples) + fld.aabb[1] * samples
+    alpha = torch.zeros_like(dense[..., 0])
+    for i in range(grid[0]):
+        alpha[i] = point_alpha(fld, dense[i].view(-1, 3), geo["stepSize"]).view((grid[1], grid[2]))
+    dense = dense.transpose(0, 2).contiguous()
+    alpha = alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None]
+    alpha = F.max_pool3d(alpha, kernel_size=3, padding=1, stride=1).view(list(grid)[::-1])
+    vol = (alpha >= thres).float()
+    valid = dense[vol > 0.5]
+    return vol, torch.stack((valid.amin(0), valid.amax(0)))
+
+
 def occupancy_value(occ: OccupancyGrid, pts):
     """models/tensorBase.py:66-83: trilinear grid_sample of the {0,1} volume, align_corners=True."""
     n = (pts - occ.aabb[0]) * occ.inv_size - 1
@@ -216,12 +256,15 @@ def shade(fld: Field, viewdirs, feat):
 # --------------------------------------------------------------------------- #
 # the path
 # --------------------------------------------------------------------------- #
-def render_chunk(fld: Field, rays, white_bg=False, bg_color=None, n_samples=-1, jitter=None):
+def render_chunk(fld: Field, rays, white_bg=False, bg_color=None, n_samples=-1, jitter=None, point_samples=False):
     """TensorBase.forward, models/tensorBase.py:775-917 (aabb contraction, sample_ray branch).
 
     Returns a dict with the reference's 6 outputs plus the two masks."""
     view = rays[:, 3:6]
-    pts, z, valid = sample_along_rays(fld, rays[:, :3], view, n_samples, jitter)
+    if point_samples:                                               # sample_func=sample_point_color (:792-803)
+        pts, z, valid = sample_around_points(fld, rays[:, :3], view, n_samples)
+    else:
+        pts, z, valid = sample_along_rays(fld, rays[:, :3], view, n_samples, jitter)
     dists = torch.cat((z[:, 1:] - z[:, :-1], torch.zeros_like(z[:, :1])), dim=-1)
     if fld.occupancy is not None:                                   # :832-837
         keep = occupancy_value(fld.occupancy, pts[valid]) > 0

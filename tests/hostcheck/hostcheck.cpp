@@ -8,6 +8,9 @@
 #include <vector>
 #include "../../iffnerf_b200/csrc/tvm_gather.cuh"
 
+static int g_point_samples = 0;     // 1: sample_point_color sampler (TVM_F_POINT_SAMPLES)
+extern "C" void hc_set_point_samples(int on) { g_point_samples = on; }
+
 extern "C" void hc_pack_occupancy(const float* vol, int dx, int dy, int dz, uint8_t* cells) {
     for (int z = 0; z < dz; ++z)
         for (int y = 0; y < dy; ++y)
@@ -38,8 +41,7 @@ extern "C" void hc_block_flags(const tvm_field_desc* f, const float* rays, long 
     for (long long r = 0; r < n; ++r) {
         TvmRay ray;
         for (int c = 0; c < 3; ++c) { ray.o[c] = rays[r * stride + c]; ray.d[c] = rays[r * stride + 3 + c]; }
-        ray.t0 = tvm_ray_entry(*f, ray.o, ray.d);
-        ray.jit = jitter ? jitter[r] : 0.f;
+        tvm_init_ray(*f, ray, jitter ? jitter[r] : 0.f, S, g_point_samples != 0);
         for (int b = 0; b < nblk; ++b)
             flags[r * nblk + b] = tvm_block_may_be_valid(*f, ray, b * 32, (b * 32 + 31 < S - 1) ? b * 32 + 31 : S - 1);
     }
@@ -51,8 +53,7 @@ extern "C" void hc_sample_mask(const tvm_field_desc* f, const float* rays, long 
     for (long long r = 0; r < n; ++r) {
         TvmRay ray;
         for (int c = 0; c < 3; ++c) { ray.o[c] = rays[r * stride + c]; ray.d[c] = rays[r * stride + 3 + c]; }
-        ray.t0 = tvm_ray_entry(*f, ray.o, ray.d);
-        ray.jit = jitter ? jitter[r] : 0.f;
+        tvm_init_ray(*f, ray, jitter ? jitter[r] : 0.f, S, g_point_samples != 0);
         int cnt = 0;
         if (bits) memset(bits + r * words, 0, words * sizeof(uint32_t));
         for (int i = 0; i < S; ++i) {
@@ -77,8 +78,7 @@ extern "C" void hc_march(const tvm_field_desc* f, const float* rays, long long n
     for (long long r = 0; r < n; ++r) {
         TvmRay ray;
         for (int c = 0; c < 3; ++c) { ray.o[c] = rays[r * stride + c]; ray.d[c] = rays[r * stride + 3 + c]; }
-        ray.t0 = tvm_ray_entry(*f, ray.o, ray.d);
-        ray.jit = jitter ? jitter[r] : 0.f;
+        tvm_init_ray(*f, ray, jitter ? jitter[r] : 0.f, S, g_point_samples != 0);
         float T = 1.f, acc = 0.f, dep = 0.f;
         int napp = 0;
         float4 A[4][3][3];
@@ -129,8 +129,7 @@ extern "C" void hc_march_bwd(const tvm_field_desc* f, const float* rays, long lo
     for (long long r = 0; r < n; ++r) {
         TvmRay ray;
         for (int c = 0; c < 3; ++c) { ray.o[c] = rays[r * stride + c]; ray.d[c] = rays[r * stride + 3 + c]; }
-        ray.t0 = tvm_ray_entry(*f, ray.o, ray.d);
-        ray.jit = jitter ? jitter[r] : 0.f;
+        tvm_init_ray(*f, ray, jitter ? jitter[r] : 0.f, S, g_point_samples != 0);
         float4 gF[4][3][3];
         memset(gF, 0, sizeof(gF));
         float total = 0.f;
@@ -200,7 +199,7 @@ extern "C" void hc_march_bwd(const tvm_field_desc* f, const float* rays, long lo
                 const float m = fminf(rn_div(rn_sub(f->aabb[3 + cc], ray.o[cc]), v), rn_div(rn_sub(f->aabb[cc], ray.o[cc]), v));
                 if (m > best) { best = m; bc = cc; bv = v; bzero = zero; }
             }
-            if (best >= f->near_t && best <= f->far_t) {
+            if (!g_point_samples && best >= f->near_t && best <= f->far_t) {
                 go[bc] -= gt0 / bv;
                 if (!bzero) gd[bc] -= gt0 * best / bv;
             }

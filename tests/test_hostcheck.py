@@ -260,3 +260,21 @@ def test_march_backward_ray_grads_match_oracle_autograd(hc):
     scale = np.abs(ref).max()
     assert scale > 0
     assert np.abs(g_rays - ref).max() <= 5e-3 * scale, (np.abs(g_rays - ref).max(), scale)
+
+
+def test_point_sample_mode_mask_bit_exact(hc):
+    """sample_point_color sampler (TVM_F_POINT_SAMPLES): 20 samples centred on the origin, vs the oracle."""
+    from oracle.make_golden import point_rays
+    fld, _ = fx.config1(0.0, "sphere", 6)
+    rays = point_rays(fld, 2000)
+    m, d, keep = _host_desc(hc, fld)
+    pts, z, valid = orc.sample_around_points(fld, rays[:, :3], rays[:, 3:6], 20)
+    occ = torch.zeros_like(valid)
+    occ[valid] = orc.occupancy_value(fld.occupancy, pts[valid]) > 0
+    hc.hc_set_point_samples(1)
+    try:
+        bits, counts = _mask(hc, d, rays, 20)
+    finally:
+        hc.hc_set_point_samples(0)
+    assert np.array_equal(H.unpack_bits(bits, 20), occ.numpy())
+    assert counts.sum() > 0
