@@ -74,6 +74,7 @@ _SIGNATURES = {
     "tvm_mlp_grad_floats": (C.c_size_t, [C.POINTER(FieldDesc)]),
     "tvm_unpack_mlp_grads": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "tvm_point_density": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_float, _P, _P]),
+    "tvm_gather_microbench": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, _P, C.POINTER(C.c_ulonglong), _P]),
     "tvm_workspace_layout": (C.c_int, [C.POINTER(FieldDesc), C.c_int64] + [C.POINTER(C.c_size_t)] * 6),
 }
 

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtvm_b200.so")
-SOURCES = ["pack.cu", "march.cu", "march_bwd.cu", "shade.cu", "shade_bwd.cu", "shade_tc.cu", "query.cu"]
+SOURCES = ["pack.cu", "march.cu", "march_bwd.cu", "shade.cu", "shade_bwd.cu", "shade_tc.cu", "query.cu", "microbench.cu"]
 HEADERS = ["tvm_math.cuh", "tvm_common.cuh", "tvm_gather.cuh", "tvm_warp.cuh", os.path.join("..", "..", "include", "tvm_b200.h")]
 
 NVCC_FLAGS = [

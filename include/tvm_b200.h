@@ -180,6 +180,11 @@ int tvm_unpack_mlp_grads(const tvm_field_desc* desc, const float* packed_grad, f
 int tvm_point_density(const tvm_field_desc* desc, const float* points /* [n][3] */, int64_t n_points, int mode,
                       float length, float* out /* [n] */, void* stream);
 
+/* Measurement aid: random-granule gather over `bytes` of `buf` (64 B = density texel, 192 B = appearance texel);
+ * the caller times the launch with CUDA events; *bytes_moved = bytes requested.  Not used by the render path. */
+int tvm_gather_microbench(const void* buf, size_t bytes, int granule_bytes, int iters, float* sink,
+                          unsigned long long* bytes_moved, void* stream);
+
 /* workspace layout helpers (byte offsets inside ws for n_rays) so the host can view the march outputs */
 int tvm_workspace_layout(const tvm_field_desc* desc, int64_t n_rays, size_t* ray_feat_off, size_t* acc_off,
                          size_t* depth_off, size_t* sigma_count_off, size_t* app_count_off, size_t* occ_count_off);
