@@ -8,7 +8,7 @@
 // layout), fp32 accumulators in TMEM, `tcgen05.mma.cta_group::1.kind::f16` issued by one thread, completion
 // signalled through an mbarrier by `tcgen05.commit`, accumulators read back with `tcgen05.ld`.  One persistent
 // CTA per SM owns a 128-ray tile at a time (TMEM lane == ray), keeps all four weight images resident in shared
-// memory, and its 128 threads do the epilogues (positional encoding, bias, ReLU, bf16 repack) between MMAs.
+// memory, and its 512 threads (4 warps per TMEM lane quarter) do the epilogues (positional encoding, bias, ReLU, bf16 repack) between MMAs.
 // bf16 operands bound the result to the 1e-2 tolerance of BASELINE.json's "bf16 MLP mode"; the fp32 SIMT
 // kernel in shade.cu stays the default (1e-4).
 #include <cuda_bf16.h>
@@ -17,7 +17,7 @@
 namespace {
 
 constexpr int TC_RAYS = 128;
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 512;     // 16 warps: 4 per TMEM lane quarter, each a quarter of the columns
 constexpr int FC = TVM_FEATURE_C;
 constexpr int N0 = 32;                 // basis rows padded (app_dim <= 32)
 constexpr int N3 = 16;                 // rgb rows padded
@@ -151,15 +151,17 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_saddr, ui
 __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     const TcDims& d = a.d;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // 16 warps: warp w works on TMEM lane quarter (w & 3) — the only lanes it may read — i.e. on tile row
+    // `row`, and on column group `cg` (a quarter of every epilogue's columns / channels)
+    const int row = (warp & 3) * 32 + lane, cg = warp >> 2;
     // shared memory carve-up
     unsigned char* s_img = smem;                                        // weight images
     unsigned char* s_a = s_img + ((d.img_bytes + 127) & ~127);          // F tile (K0) / h1 (K=128)
     const int a_bytes = TC_RAYS * (d.k0 > FC ? d.k0 : FC) * 2;
     unsigned char* s_x = s_a + a_bytes;                                 // MLP input (K1) / h2 (K=128)
     const int x_bytes = TC_RAYS * (d.k1 > FC ? d.k1 : FC) * 2;
-    float* s_row = reinterpret_cast<float*>(s_x + x_bytes);             // [128][33] fp32 scratch: feat | viewdir
-    float* s_bias = s_row + TC_RAYS * 33;                               // b1[128] b2[128] b3[4]
+    float* s_bias = reinterpret_cast<float*>(s_x + x_bytes);            // b1[128] b2[128] b3[4]
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 2 * FC + 4);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
 
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's TMEM lane quarter
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's TMEM lane quarter
     const uint32_t bar = smem_u32(s_bar);
     const uint32_t sa = smem_u32(s_a), sx = smem_u32(s_x), simg = smem_u32(s_img);
     uint32_t phase = 0;
@@ -191,10 +193,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
     const int sin_v = cos_f + d.app_dim * d.fea_pe, cos_v = sin_v + 3 * d.view_pe;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long r = tile * TC_RAYS + tid;          // this thread's ray == its TMEM lane
+        const long long r = tile * TC_RAYS + row;          // this thread's ray == its TMEM lane
         const bool live = r < a.n_rays;
-        // ---- stage 0: ray_feat row -> bf16 A operand (K0 columns)
-        for (int kc = 0; kc < d.k0 / 8; ++kc) {
+        // ---- stage 0: ray_feat row -> bf16 A operand (K0 columns); the 4 column groups interleave the 16-B chunks
+        for (int kc = cg; kc < d.k0 / 8; kc += 4) {
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = 0.f;
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
                     v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
                 }
             }
-            *reinterpret_cast<uint4*>(s_a + canon_off(tid, kc * 8, d.k0)) =
+            *reinterpret_cast<uint4*>(s_a + canon_off(row, kc * 8, d.k0)) =
                 make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         }
         fence_async_smem();
@@ -217,32 +219,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
         {
+            // MLP input row (tensorBase.py:186-191): [feat | view | sin(feat 2^j) | cos | sin(view 2^j) | cos], zero pad.
+            // Every warp reads the 32 feature columns of its lanes; channel ch is encoded by column group ch & 3.
             float v[32];
             tmem_ld32(lane_base + COL0, v);
-            float* row = s_row + tid * 33;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) row[j] = v[j];
-            // viewdirs after the features
-            for (int c = 0; c < 3; ++c) row[d.app_dim + c] = live ? __ldg(a.rays + r * a.ray_stride + 3 + c) : 0.f;
-            // MLP input row (tensorBase.py:186-191): [feat | view | sin(feat 2^j) | cos | sin(view 2^j) | cos], zero pad
-            for (int ch = 0; ch < nbase; ++ch) {
-                const float x = row[ch];
-                *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(tid, ch, d.k1)) = __float2bfloat16_rn(x);
+            for (int ch = 0; ch < 32; ++ch) {
+                if ((ch & 3) != cg || ch >= nbase) continue;
                 const bool is_feat = ch < d.app_dim;
+                float x = v[ch];
+                if (!is_feat) x = live ? __ldg(a.rays + r * a.ray_stride + 3 + (ch - d.app_dim)) : 0.f;
+                *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(row, ch, d.k1)) = __float2bfloat16_rn(x);
                 const int nf = is_feat ? d.fea_pe : d.view_pe;
                 const int cc = is_feat ? ch : ch - d.app_dim;
                 const int sb = is_feat ? sin_f : sin_v, cb = is_feat ? cos_f : cos_v;
                 float scale = 1.f;
                 for (int j = 0; j < nf; ++j) {
-                    float s, c;
-                    sincosf(x * scale, &s, &c);
-                    *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(tid, sb + cc * nf + j, d.k1)) = __float2bfloat16_rn(s);
-                    *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(tid, cb + cc * nf + j, d.k1)) = __float2bfloat16_rn(c);
+                    float sn, cs;
+                    sincosf(x * scale, &sn, &cs);
+                    *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(row, sb + cc * nf + j, d.k1)) = __float2bfloat16_rn(sn);
+                    *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(row, cb + cc * nf + j, d.k1)) = __float2bfloat16_rn(cs);
                     scale *= 2.f;
                 }
             }
-            for (int k = d.in_c; k < d.k1; ++k)
-                *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(tid, k, d.k1)) = __float2bfloat16_rn(0.f);
+            if (cg == 3)
+                for (int k = d.in_c; k < d.k1; ++k)
+                    *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(row, k, d.k1)) = __float2bfloat16_rn(0.f);
         }
         fence_async_smem();
         tc_fence_before();
@@ -251,8 +253,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
         if (tid == 0) { tc_fence_after(); issue_gemm(tmem + COL1, sx, simg + d.img1, d.k1, FC, bar); }
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
-#pragma unroll 1
-        for (int cb = 0; cb < FC; cb += 32) {              // bias + ReLU -> bf16 A operand (K = 128) in s_a
+        {                                                   // bias + ReLU -> bf16 A operand (K = 128) in s_a
+            const int cb = cg * 32;
             float v[32];
             tmem_ld32(lane_base + COL1 + cb, v);
 #pragma unroll
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
                     const int j = q * 8 + e * 2;
                     w[e] = pack_bf16x2(fmaxf(v[j] + s_bias[cb + j], 0.f), fmaxf(v[j + 1] + s_bias[cb + j + 1], 0.f));
                 }
-                *reinterpret_cast<uint4*>(s_a + canon_off(tid, cb + q * 8, FC)) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(s_a + canon_off(row, cb + q * 8, FC)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
         fence_async_smem();
@@ -273,8 +275,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
         if (tid == 0) { tc_fence_after(); issue_gemm(tmem + COL2, sa, simg + d.img2, FC, FC, bar); }
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
-#pragma unroll 1
-        for (int cb = 0; cb < FC; cb += 32) {              // bias + ReLU -> bf16 A operand (K = 128) in s_x
+        {                                                   // bias + ReLU -> bf16 A operand (K = 128) in s_x
+            const int cb = cg * 32;
             float v[32];
             tmem_ld32(lane_base + COL2 + cb, v);
 #pragma unroll
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
                     const int j = q * 8 + e * 2;
                     w[e] = pack_bf16x2(fmaxf(v[j] + s_bias[FC + cb + j], 0.f), fmaxf(v[j + 1] + s_bias[FC + cb + j + 1], 0.f));
                 }
-                *reinterpret_cast<uint4*>(s_x + canon_off(tid, cb + q * 8, FC)) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(s_x + canon_off(row, cb + q * 8, FC)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
         fence_async_smem();
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
         if (tid == 0) { tc_fence_after(); issue_gemm(tmem + COL3, sx, simg + d.img3, FC, N3, bar); }
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
-        {
+        if (cg == 0) {
             float v[32];
             tmem_ld32(lane_base + COL3, v);               // columns 3.. are padding / neighbouring accumulators
             if (live) {
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
 size_t tc_smem_bytes(const TcDims& d) {
     const size_t a_bytes = (size_t)TC_RAYS * (d.k0 > FC ? d.k0 : FC) * 2;
     const size_t x_bytes = (size_t)TC_RAYS * (d.k1 > FC ? d.k1 : FC) * 2;
-    return ((d.img_bytes + 127) & ~127) + a_bytes + x_bytes + (size_t)TC_RAYS * 33 * 4 + (2 * FC + 4) * 4 + 16;
+    return ((d.img_bytes + 127) & ~127) + a_bytes + x_bytes + (2 * FC + 4) * 4 + 16;
 }
 
 }  // namespace
