@@ -167,6 +167,57 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def extra_configs(model, dev, fx):
+    """Informational timings of BASELINE configs 3 and 5 on the same field (their parity is in tests/):
+    config 3 = train.py-style step (4096 rays, S=1039, fwd+bwd into every parameter gradient);
+    config 5 = pose mode, 64 candidate poses x 1024 rays in ONE call, fwd + gradient w.r.t. the rays."""
+    import torch
+    out = {}
+    allrays = fx.config2_rays()
+    g = torch.Generator().manual_seed(0)
+
+    def timeit(fn, steps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / steps
+
+    rays = allrays[torch.randint(0, allrays.shape[0], (4096,), generator=g)].to(dev)
+    target = torch.rand(4096, 3, device=dev)
+    ones = torch.ones(3, device=dev)
+
+    def train_step():
+        model.zero_grad(set_to_none=True)
+        rgb, _, _, alpha, _, _ = model(rays, bg_color=ones, is_train=True, N_samples=1039)
+        (torch.mean((rgb - target) ** 2) + 0.1 * torch.mean(torch.exp(torch.abs(alpha)))).backward()
+    model.train()
+    ms = timeit(train_step)
+    out["config3_train_step"] = {"rays": 4096, "n_samples": 1039, "ms_fwd_bwd": ms, "rays_per_s": 4096 / (ms / 1e3)}
+    model.eval()
+    model.zero_grad(set_to_none=True)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    prays = allrays[torch.randint(0, allrays.shape[0], (64 * 1024,), generator=g)].to(dev)
+    ptarget = torch.rand(64 * 1024, 3, device=dev)
+    bg = torch.rand(3, device=dev)
+
+    def pose_step():
+        r = prays.clone().requires_grad_(True)
+        rgb = model(r, bg_color=bg, is_train=False)[0]
+        torch.mean((rgb - ptarget) ** 2).backward()
+    ms = timeit(pose_step, steps=5, warm=2)
+    out["config5_pose_step_64x1024"] = {"rays": 64 * 1024, "ms_fwd_bwd_to_rays": ms, "rays_per_s": 65536 / (ms / 1e3)}
+    for p in model.parameters():
+        p.requires_grad_(True)
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -322,6 +373,8 @@ def run_ours(args, rank, world, local_rank):
                                   "shade_tflops": 2 * 39856 * n * 1e-12 / max((ms_dev_tc - ms_march) / K / 1e3, 1e-9),
                                   "note": "tcgen05 bf16 shade kernel; march stage unchanged"},
                 "clocks": clk.result}
+        if world == 1:
+            line["other_configs"] = extra_configs(model, dev, fx)
         if not args.no_cpu_baseline and world == 1:
             rate, cores, desc = cpu_oracle_rate(args.cpu_rays)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
