@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
     float* sX = sF + SB_RAYS * fs;             // MLP input [64][k1]
     float* sH1 = sX + SB_RAYS * k1;            // [64][FC]
     float* sH2 = sH1 + SB_RAYS * FC;           // [64][FC]
-    float* sG = sH2 + SB_RAYS * FC;            // gradient scratch [64][k1]  (g_h2 / g_h1 use stride FC, g_x stride k1)
-    float* sS = sG + SB_RAYS * k1;             // per-ray scalars [64][8]: rgb[3], g_z3[3], acc, lit
+    float* sG = sH2 + SB_RAYS * FC;            // gradient scratch [64][max(k1,FC)]  (g_h2 / g_h1: stride FC)
+    float* sS = sG + SB_RAYS * (k1 > FC ? k1 : FC);   // per-ray scalars [64][8]: rgb[3], g_z3[3], acc, lit
     const long long r0 = (long long)blockIdx.x * SB_RAYS;
     const float* w1t = a.mlp + a.m.w1t; const float* b1 = a.mlp + a.m.b1;
     const float* w2t = a.mlp + a.m.w2t; const float* b2 = a.mlp + a.m.b2;
@@ -311,13 +311,16 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
         float gx2[8][4];
 #pragma unroll
         for (int r = 0; r < 8; ++r) { gx[r][0] = gx[r][1] = gx[r][2] = gx[r][3] = 0.f; gx2[r][0] = gx2[r][1] = gx2[r][2] = gx2[r][3] = 0.f; }
-        rows8_gemm(gx, sG, FC, ty * 8, FC, w1n, k1, tx * 4);
+        const bool head = tx * 4 < k1;           // k1 may be smaller than FC (fea_pe = view_pe = 0 -> k1 = 32)
+        if (head) rows8_gemm(gx, sG, FC, ty * 8, FC, w1n, k1, tx * 4);
         const bool tail = FC + tx * 4 < k1;
         if (tail) rows8_gemm(gx2, sG, FC, ty * 8, FC, w1n, k1, FC + tx * 4);
         __syncthreads();                         // all reads of h1 (outer product) and g_h1 are done
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            *reinterpret_cast<float4*>(sGX + (ty * 8 + r) * k1 + tx * 4) = make_float4(gx[r][0], gx[r][1], gx[r][2], gx[r][3]);
+            if (head)
+                *reinterpret_cast<float4*>(sGX + (ty * 8 + r) * k1 + tx * 4) =
+                    make_float4(gx[r][0], gx[r][1], gx[r][2], gx[r][3]);
             if (tail)
                 *reinterpret_cast<float4*>(sGX + (ty * 8 + r) * k1 + FC + tx * 4) =
                     make_float4(gx2[r][0], gx2[r][1], gx2[r][2], gx2[r][3]);
@@ -394,8 +397,8 @@ extern "C" int tvm_shade_bwd(const tvm_field_desc* desc, const float* rays, int6
     a.m = tvm_mlp_layout(desc);
     a.ta = tvm_total_app(desc); a.app_dim = desc->app_dim; a.fea_pe = desc->fea_pe; a.view_pe = desc->view_pe;
     if (a.m.k1 > 2 * FC || a.m.k1 % 8) return TVM_E_SHAPE;       // g_x reuses the h1|h2 span; 8-wide outer blocks
-    const size_t floats = (size_t)a.ta * 32 + (size_t)SB_RAYS * (a.ta + 4) + (size_t)SB_RAYS * a.m.k1 * 2 +
-                          (size_t)SB_RAYS * FC * 2 + SB_RAYS * 8;
+    const size_t floats = (size_t)a.ta * 32 + (size_t)SB_RAYS * (a.ta + 4) + (size_t)SB_RAYS * a.m.k1 +
+                          (size_t)SB_RAYS * (a.m.k1 > FC ? a.m.k1 : FC) + (size_t)SB_RAYS * FC * 2 + SB_RAYS * 8;
     const size_t smem = floats * sizeof(float);
     if (smem > 227 * 1024) return TVM_E_SHAPE;
     TVM_CUDA_OK(cudaFuncSetAttribute(shade_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

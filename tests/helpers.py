@@ -20,8 +20,10 @@ def module_from_field(fld, device):
     """Builds the product TensorVMSplit holding exactly the oracle field's parameters."""
     import iffnerf_b200 as I
     with contextlib.redirect_stdout(io.StringIO()):
-        m = I.TensorVMSplit(fld.aabb.clone().to(device), list(fld.grid), device, density_n_comp=[16] * 3,
-                            appearance_n_comp=[48] * 3, app_dim=27, near_far=list(fld.near_far),
+        m = I.TensorVMSplit(fld.aabb.clone().to(device), list(fld.grid), device,
+                            density_n_comp=[p.shape[1] for p in fld.density_plane],
+                            appearance_n_comp=[p.shape[1] for p in fld.app_plane], app_dim=fld.basis.shape[0],
+                            near_far=list(fld.near_far),
                             shadingMode="MLP_Fea", alphaMask_thres=1e-4, density_shift=fld.density_shift,
                             distance_scale=fld.distance_scale, rayMarch_weight_thres=fld.weight_thres, pos_pe=6,
                             view_pe=fld.view_pe, fea_pe=fld.fea_pe, featureC=128, step_ratio=fld.step_ratio,
