@@ -339,7 +339,7 @@ extern "C" size_t tvm_mlp_tc_pack_bytes(const tvm_field_desc* desc) {
 extern "C" int tvm_pack_mlp_tc(const tvm_field_desc* desc, const float* basis, const float* w1, const float* w2,
                                const float* w3, void* packed, void* stream) {
     if (!desc || !basis || !w1 || !w2 || !w3 || !packed) return TVM_E_NULL;
-    if (desc->feature_c != FC || desc->app_dim > N0 || desc->app_dim <= 0) return TVM_E_SHAPE;
+    if (desc->feature_c != FC || desc->app_dim + 3 > N0 || desc->app_dim <= 0) return TVM_E_SHAPE;
     const TcDims d = tc_dims(desc);
     if (tc_smem_bytes(d) > 227 * 1024) return TVM_E_SHAPE;
     unsigned char* out = (unsigned char*)packed;
@@ -356,7 +356,7 @@ extern "C" int tvm_pack_mlp_tc(const tvm_field_desc* desc, const float* basis, c
 int tvm_shade_tc_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, const float* bg,
                         float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes, cudaStream_t st) {
     if (!desc->mlp_tc || !desc->mlp) return TVM_E_NULL;
-    if (desc->feature_c != FC || desc->app_dim > N0 || desc->app_dim <= 0) return TVM_E_SHAPE;
+    if (desc->feature_c != FC || desc->app_dim + 3 > N0 || desc->app_dim <= 0) return TVM_E_SHAPE;   // feat|view fit 32 cols
     const TcDims d = tc_dims(desc);
     const size_t smem = tc_smem_bytes(d);
     if (smem > 227 * 1024) return TVM_E_SHAPE;
