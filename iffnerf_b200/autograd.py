@@ -129,11 +129,12 @@ def render_with_grad(model, rays_chunk, white_bg, bg_color, N_samples, jitter, p
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# cross-check variant: march stage through the C ABI, shading tail as torch autograd (cuBLAS)
+# march stage through the C ABI, shading tail as torch autograd: the path of the `Ref` head (no fused kernel yet) and
+# an independent cross-check of tvm_shade_bwd for MLP_Fea
 # ----------------------------------------------------------------------------------------------------------------
 class _March(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, rays, S, jitter, *factors):
+    def forward(ctx, model, rays, S, jitter, flags, *factors):
         from .tensorf import _stream
         rays_c = model._prep_rays(rays)
         dev = rays_c.device
@@ -147,11 +148,11 @@ class _March(torch.autograd.Function):
         jit = None if jitter is None else jitter.detach().to(dev).float().reshape(-1).contiguous()
         bg = model._bg(None, False, dev)
         _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], S, _lib.ptr(jit),
-                                      _lib.ptr(bg), _lib.F_NO_SHADE, None, None, None, _lib.ptr(alpha), _lib.ptr(z),
+                                      _lib.ptr(bg), _lib.F_NO_SHADE | flags, None, None, None, _lib.ptr(alpha), _lib.ptr(z),
                                       _lib.ptr(dists), None, None, None, _lib.ptr(ws), ws.numel(), _stream(dev)),
                    "tvm_render_fwd")
         v = model.workspace_views(d, ws, n)
-        ctx.model, ctx.S, ctx.jit, ctx.rays_c, ctx.ws = model, S, jit, rays_c, ws
+        ctx.model, ctx.S, ctx.jit, ctx.rays_c, ctx.ws, ctx.flags = model, S, jit, rays_c, ws, flags
         ctx.ray_cols = rays.shape[1]
         ctx.mark_non_differentiable(v["depth"], z, dists, v["app_count"])
         return v["ray_feat"], v["acc"], v["depth"], alpha, z, dists, v["app_count"]
@@ -163,17 +164,20 @@ class _March(torch.autograd.Function):
         dev = rays_c.device
         n = rays_c.shape[0]
         want_rays = ctx.needs_input_grad[1]
-        want_factors = any(ctx.needs_input_grad[4:])
+        want_factors = any(ctx.needs_input_grad[5:])
         d, keep = model.field_desc()
         lib = _lib.load()
         g_packed = torch.zeros(int(d.n_factor_floats), device=dev) if want_factors else None
         g_rays = torch.zeros((n, 6), device=dev) if want_rays else None
-        _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], ctx.S, _lib.ptr(ctx.jit), 0,
-                                     _lib.ptr(_c(g_feat)), _lib.ptr(_c(g_acc)), _lib.ptr(_c(g_alpha)),
+        _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], ctx.S, _lib.ptr(ctx.jit),
+                                     ctx.flags, _lib.ptr(_c(g_feat)), _lib.ptr(_c(g_acc)), _lib.ptr(_c(g_alpha)),
                                      _lib.ptr(g_packed), _lib.ptr(g_rays), _lib.ptr(ctx.ws), ctx.ws.numel(),
                                      _stream(dev)), "tvm_march_bwd")
         grads = [None] * 12
         if want_factors:
+            sync = getattr(model, "grad_sync", None)
+            if sync is not None:
+                sync.reduce_packed_factor_grads(g_packed)
             planes, lines = model._factor_params()
             gp = [torch.empty_like(p) for p in planes]
             gl = [torch.empty_like(p) for p in lines]
@@ -184,14 +188,15 @@ class _March(torch.autograd.Function):
         if want_rays:
             d_rays = torch.zeros((n, ctx.ray_cols), device=dev)
             d_rays[:, :6] = g_rays
-        return (None, d_rays, None, None, *grads)
+        return (None, d_rays, None, None, None, *grads)
 
 
-def render_with_grad_torch_tail(model, rays_chunk, white_bg, bg_color, N_samples, jitter):
+def render_with_grad_torch_tail(model, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples=False):
     S = N_samples if N_samples > 0 else model.nSamples
     planes, lines = model._factor_params()
     rays = rays_chunk if rays_chunk.dtype == torch.float32 else rays_chunk.float()
-    ray_feat, acc, depth_p, alpha, z, dists, app_count = _March.apply(model, rays, S, jitter, *planes, *lines)
+    flags = _lib.F_POINT_SAMPLES if point_samples else 0
+    ray_feat, acc, depth_p, alpha, z, dists, app_count = _March.apply(model, rays, S, jitter, flags, *planes, *lines)
     view = rays[:, 3:6]
     feat = F.linear(ray_feat, model.basis_mat.weight)
     rgb, _ = model.renderModule(None, view, feat, None)

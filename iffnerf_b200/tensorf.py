@@ -130,8 +130,8 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         super().__init__()
         if contraction_type != "aabb":
             raise NotImplementedError("contraction_type='unisphere' is outside the B200 render path (SURVEY.md 8a)")
-        if shadingMode != "MLP_Fea":
-            raise NotImplementedError(f"shadingMode={shadingMode!r}: only 'MLP_Fea' is on the B200 render path")
+        if shadingMode not in ("MLP_Fea", "Ref"):
+            raise NotImplementedError(f"shadingMode={shadingMode!r}: only 'MLP_Fea' and 'Ref' are on the B200 render path")
         if fea2denseAct not in ("softplus", "relu"):
             raise ValueError(f"unknown fea2denseAct {fea2denseAct!r}")
         if isinstance(density_n_comp, int):
@@ -160,7 +160,12 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         self.init_svd_volume(gridSize[0], device)
         self.shadingMode, self.pos_pe, self.view_pe, self.fea_pe, self.featureC = \
             shadingMode, pos_pe, view_pe, fea_pe, featureC
-        self.renderModule = MLPRender_Fea(self.app_dim, view_pe, fea_pe, featureC).to(device)
+        if shadingMode == "MLP_Fea":
+            self.renderModule = MLPRender_Fea(self.app_dim, view_pe, fea_pe, featureC).to(device)
+        else:       # "Ref": march stage on the kernels, the ~4 kFLOP/ray head as torch ops (ref_head.py)
+            from .ref_head import Ref
+            self.renderModule = Ref(self.app_dim, viewpe=view_pe, feature_c=featureC).to(device)
+        self.native_shade = shadingMode == "MLP_Fea"
         self.it = 0
         self._packed = None
         self._packed_key = None
@@ -378,11 +383,16 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         keep = []
         if need_params:
             pf = self.packed_factors()
-            pm = self.packed_mlp()
             basis = self.basis_mat.weight.detach().contiguous()
-            d.factors, d.mlp, d.basis = pf.data_ptr(), pm.data_ptr(), basis.data_ptr()
-            keep += [pf, pm, basis]
-            if self.mlp_precision == "bf16":
+            d.factors, d.basis = pf.data_ptr(), basis.data_ptr()
+            keep += [pf, basis]
+            if self.native_shade:
+                pm = self.packed_mlp()
+                d.mlp = pm.data_ptr()
+                keep.append(pm)
+            if not self.native_shade:
+                pass
+            elif self.mlp_precision == "bf16":
                 tc = self.packed_mlp_tc()
                 d.mlp_tc = tc.data_ptr()
                 keep.append(tc)
@@ -467,7 +477,9 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need)), "tvm_workspace_bytes")
         ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
         flags = _lib.F_EARLY_TERM if (early_term and not sample_outputs) else 0
-        if self.mlp_precision == "bf16":
+        if not self.native_shade:
+            flags |= _lib.F_NO_SHADE
+        elif self.mlp_precision == "bf16":
             flags |= _lib.F_MLP_BF16
         if point_samples:
             flags |= _lib.F_POINT_SAMPLES
@@ -478,9 +490,23 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
                                       _lib.ptr(out["acc_map"]), _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(dists),
                                       None, _lib.ptr(vcount), _lib.ptr(acount), _lib.ptr(ws), ws.numel(),
                                       _stream(dev)), "tvm_render_fwd")
-        if keep_workspace:
-            out["workspace"] = self.workspace_views(d, ws, n)
+        if keep_workspace or not self.native_shade:
+            views = self.workspace_views(d, ws, n)
+            if keep_workspace:
+                out["workspace"] = views
+            if not self.native_shade and n > 0:
+                self._torch_shade_tail(rays, views, bg, out)
         return out
+
+    def _torch_shade_tail(self, rays, views, bg, out):
+        """Per-ray tail of TensorBase.forward (tensorBase.py:886-908) for heads without a fused kernel (`Ref`)."""
+        feat = F.linear(views["ray_feat"], self.basis_mat.weight)
+        rgb, _ = self.renderModule(None, rays[:, 3:6], feat, None)
+        rgb = rgb * (views["app_count"] > 0).to(rgb.dtype)[:, None]
+        acc = views["acc"]
+        out["rgb_map"].copy_((rgb * acc[..., None] + bg * (1.0 - acc[..., None])).clamp(0, 1))
+        out["depth_map"].copy_(views["depth"] + (1.0 - acc) * rays[..., -1])
+        out["acc_map"].copy_(acc)
 
     def workspace_views(self, d, ws, n):
         """Typed views of the march-stage outputs inside a workspace buffer."""
@@ -522,8 +548,9 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         needs_grad = torch.is_grad_enabled() and (
             rays_chunk.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
-            from .autograd import render_with_grad
-            out = render_with_grad(self, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples)
+            from .autograd import render_with_grad, render_with_grad_torch_tail
+            fn = render_with_grad if self.native_shade else render_with_grad_torch_tail
+            out = fn(self, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples)
         else:
             o = self.render_eval(rays_chunk, N_samples=N_samples, white_bg=white_bg, bg_color=bg_color, jitter=jitter,
                                  sample_outputs=True, point_samples=point_samples)

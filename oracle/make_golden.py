@@ -191,6 +191,52 @@ def point_case(R, name, fld, rays6):
           f"oracle==reference bit-exact")
 
 
+REF_KW = dict(density_n_comp=[16] * 3, appearance_n_comp=[48] * 3, app_dim=27, near_far=[2.0, 6.0],
+              shadingMode="Ref", alphaMask_thres=1e-4, density_shift=0.0, distance_scale=25, pos_pe=6, view_pe=2,
+              fea_pe=2, featureC=128, step_ratio=0.5, fea2denseAct="softplus")
+
+
+def ref_head_case(R, name):
+    """shadingMode='Ref' (configs/lego.txt:25).  No oracle restatement of this head: the goldens are
+    the reference's own outputs and pin the product directly (eval render + one train step with all gradients)."""
+    t = time.time()
+    aabb = torch.tensor([[-1.5] * 3, [1.5] * 3])
+    torch.manual_seed(fx.SEED)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = R.TensorVMSplit(aabb.clone(), [128] * 3, "cpu", **REF_KW)
+    occ = fx.sphere_occupancy(aabb, 200, radius=1.0, holes_seed=1)
+    m.alphaMask = R.AlphaGridMask("cpu", occ.aabb.clone(), occ.volume.clone())
+    _, rays = fx.config1(0.0, None, 7)
+    sub, idx = fx.subsample(rays, 2048, seed=4)
+    with torch.no_grad():
+        rgb, _, depth, _, _ = R.OctreeRender_trilinear_fast(sub, m, chunk=4096, N_samples=-1, white_bg=True,
+                                                          ndc_ray=False, device="cpu")
+    tr, tidx = fx.subsample(rays, 512, seed=5)
+    torch.manual_seed(99)
+    jitter = torch.rand(512, 1)
+    target = torch.rand(512, 3)
+    torch.manual_seed(99)
+    out = m(tr, bg_color=torch.ones(3), is_train=True, N_samples=443)
+    loss = torch.mean((out[0] - target) ** 2) + 0.1 * torch.mean(torch.exp(torch.abs(out[3])))
+    m.zero_grad()
+    loss.backward()
+    rec = dict(ray_index=idx.numpy(), rgb_map=rgb.numpy(), depth_map=depth.numpy(), train_index=tidx.numpy(),
+               jitter=jitter.numpy(), target=target.numpy(), train_rgb=out[0].detach().numpy(),
+               loss=np.float64(loss.item()),
+               param_checksum=np.array([p.double().sum().item() for p in m.state_dict().values()]))
+    for nme, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        g = p.grad
+        top = torch.topk(g.abs().reshape(-1), min(128, g.numel())).indices
+        rec[f"g_idx/{nme}"] = top.numpy()
+        rec[f"g_val/{nme}"] = g.reshape(-1)[top].numpy()
+        rec[f"g_l2/{nme}"] = np.float64(g.double().norm().item())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(f"[golden] {name}: eval rays=2048 rgb_mean={rgb.mean():.4f}, train loss={loss.item():.6f} "
+          f"({time.time()-t:.1f}s) reference outputs stored")
+
+
 def point_rays(fld, n, seed=11):
     """Points near the occupied shell with isocell-like random directions (6-col rays)."""
     g = torch.Generator().manual_seed(seed)
@@ -234,6 +280,8 @@ def main():
     if want("c1_point20"):
         fld, _ = fx.config1(density_shift=0.0, occupancy="sphere", cols=6)
         point_case(R, "c1_point20", fld, point_rays(fld, 4096))
+    if want("c1_ref_head"):
+        ref_head_case(R, "c1_ref_head")
     if want("c4_sub"):
         fld, rays = fx.config4()
         sub, idx = fx.subsample(rays, 2048, seed=0)
