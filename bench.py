@@ -232,7 +232,20 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly ONE JSON line: NCCL prints its version banner to stdout at VERSION/INFO level,
+        # so run it at WARN and keep fd 1 pointed at stderr while the communicator is created
+        os.environ["NCCL_DEBUG"] = "WARN"
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     fld = fx.make_field(GRID, density_shift=0.0)
     model = Hh.module_from_field(fld, dev)
