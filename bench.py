@@ -167,6 +167,45 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def dp_train_step(model, dev, fx, world, rank):
+    """Informational: config-3 train step under ray-sharded data parallelism — 4096 rays PER RANK (global batch
+    4096*N), packed factor-gradient bucket + MLP bucket all-reduced over NCCL inside/after backward."""
+    import torch
+    import torch.distributed as dist
+    from iffnerf_b200 import sharding
+    allrays = fx.config2_rays()
+    g = torch.Generator().manual_seed(100 + rank)
+    rays = allrays[torch.randint(0, allrays.shape[0], (4096,), generator=g)].to(dev)
+    target = torch.rand(4096, 3, device=dev)
+    ones = torch.ones(3, device=dev)
+    sync = sharding.GradSync(model, average=True).install()
+    model.train()
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        rgb, _, _, alpha, _, _ = model(rays, bg_color=ones, is_train=True, N_samples=1039)
+        (torch.mean((rgb - target) ** 2) + 0.1 * torch.mean(torch.exp(torch.abs(alpha)))).backward()
+        sync.finish()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sync.remove()
+    model.eval()
+    model.zero_grad(set_to_none=True)
+    ms = t.item()
+    return {"rays_global": 4096 * world, "ms_fwd_bwd_allreduce": ms, "rays_per_s": 4096 * world / (ms / 1e3),
+            "allreduce_bytes_per_step": sync.bytes // max(sync.calls // 2, 1)}
+
+
 def extra_configs(model, dev, fx):
     """Informational timings of BASELINE configs 3 and 5 on the same field (their parity is in tests/):
     config 3 = train.py-style step (4096 rays, S=1039, fwd+bwd into every parameter gradient);
@@ -345,6 +384,8 @@ def run_ours(args, rank, world, local_rank):
                     best = max(best, moved.value / (e0.elapsed_time(e1) / 1e3) / 1e9)
             gather_peak[f"l2_random_{gran}B_gbs"] = best
 
+    dp = dp_train_step(model, dev, fx, world, rank) if world > 1 else None
+
     t = torch.tensor([ms_dev, ms_march, ms_e2e, ms_dev_tc, ms_e2e_tc], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -388,6 +429,8 @@ def run_ours(args, rank, world, local_rank):
                 "clocks": clk.result}
         if world == 1:
             line["other_configs"] = extra_configs(model, dev, fx)
+        else:
+            line["other_configs"] = {"config3_train_step_data_parallel": dp}
         if not args.no_cpu_baseline and world == 1:
             rate, cores, desc = cpu_oracle_rate(args.cpu_rays)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
