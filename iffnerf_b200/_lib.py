@@ -12,12 +12,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_B200_LIB lets the tuning scripts load a differently-compiled build of the SAME sources
 LIB_PATH = os.environ.get("TVM_B200_LIB") or os.path.join(_HERE, "libtvm_b200.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 F_EARLY_TERM = 1 << 0
 F_MLP_BF16 = 1 << 1
 F_NO_SHADE = 1 << 2
 F_POINT_SAMPLES = 1 << 3
+F_MLP_TC3 = 1 << 4
 
 _f3 = C.c_float * 3
 _f6 = C.c_float * 6
@@ -38,7 +39,7 @@ class FieldDesc(C.Structure):
         ("n_factor_floats", C.c_int64),
         ("occ_cells", C.c_void_p), ("occ_dims", _i3), ("occ_lo", _f3), ("occ_inv", _f3),
         ("occ_coarse", C.c_void_p), ("occ_cdims", _i3),
-        ("factors", C.c_void_p), ("basis", C.c_void_p), ("mlp", C.c_void_p), ("mlp_tc", C.c_void_p),
+        ("factors", C.c_void_p), ("basis", C.c_void_p), ("mlp", C.c_void_p), ("mlp_tc", C.c_void_p), ("mlp_tc3", C.c_void_p),
     ]
 
 
@@ -61,6 +62,8 @@ _SIGNATURES = {
     "tvm_pack_mlp": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "tvm_mlp_tc_pack_bytes": (C.c_size_t, [C.POINTER(FieldDesc)]),
     "tvm_pack_mlp_tc": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P]),
+    "tvm_mlp_tc3_pack_bytes": (C.c_size_t, [C.POINTER(FieldDesc)]),
+    "tvm_pack_mlp_tc3": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P]),
     "tvm_sample_mask": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_int, _P, C.c_uint32, _P, _P, _P]),
     "tvm_workspace_bytes": (C.c_int, [C.POINTER(FieldDesc), C.c_int64, C.c_uint32, C.POINTER(C.c_size_t)]),
     "tvm_render_fwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_int, _P, _P, C.c_uint32,

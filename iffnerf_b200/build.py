@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtvm_b200.so")
-SOURCES = ["pack.cu", "march.cu", "march_bwd.cu", "shade.cu", "shade_bwd.cu", "shade_tc.cu", "query.cu", "microbench.cu"]
-HEADERS = ["tvm_math.cuh", "tvm_common.cuh", "tvm_gather.cuh", "tvm_warp.cuh", os.path.join("..", "..", "include", "tvm_b200.h")]
+SOURCES = ["pack.cu", "march.cu", "march_bwd.cu", "shade.cu", "shade_bwd.cu", "shade_tc.cu", "shade_tc3.cu", "query.cu", "microbench.cu"]
+HEADERS = ["tvm_math.cuh", "tvm_common.cuh", "tvm_gather.cuh", "tvm_warp.cuh", "tvm_tc.cuh", os.path.join("..", "..", "include", "tvm_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -21,6 +21,10 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
 int tvm_shade_tc_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, const float* bg,
                         float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes, cudaStream_t st);
 
+int tvm_shade_tc3_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
+                         const float* bg, float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes,
+                         cudaStream_t st);
+
 namespace {
 
 constexpr int SH_RAYS = 64;
@@ -241,6 +245,9 @@ extern "C" int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int6
     if (!rays || !rgb || !ws || !desc->basis || !desc->mlp || !bg) return TVM_E_NULL;
     if (desc->feature_c != FC) return TVM_E_SHAPE;
     if (desc->app_dim > 32 || desc->app_dim <= 0) return TVM_E_SHAPE;
+    if (flags & TVM_F_MLP_TC3)                        // tcgen05 bf16x3 split variant (shade_tc3.cu), fp32-equivalent
+        return tvm_shade_tc3_launch(desc, rays, n_rays, ray_stride, bg, rgb, depth, acc, ws, ws_bytes,
+                                    (cudaStream_t)stream);
     if (flags & TVM_F_MLP_BF16)                       // tcgen05 bf16 variant (shade_tc.cu), tolerance 1e-2
         return tvm_shade_tc_launch(desc, rays, n_rays, ray_stride, bg, rgb, depth, acc, ws, ws_bytes,
                                    (cudaStream_t)stream);

@@ -1,0 +1,327 @@
+// shade_tc3.cu — tensor-core shading with bf16x3 SPLIT operands (flag TVM_F_MLP_TC3): fp32-equivalent results.
+//
+// Same stage as shade.cu / shade_tc.cu (basis_mat models/tensoRF.py:158,256; MLPRender_Fea
+// models/tensorBase.py:165-195; blend + depth tail :898-908).  Every fp32 operand value v is split into
+// hi = bf16(v) and lo = bf16(v - hi); each K-step issues THREE tcgen05 MMAs into the same fp32 TMEM accumulator,
+//     A_hi.B_hi + A_hi.B_lo + A_lo.B_hi          (the dropped lo.lo term is <= 2^-18 relative)
+// which reproduces the fp32 FFMA result to ~1e-6 on rgb while running on the 5th-gen tensor cores.  Operand
+// footprint doubles, so only basis_mat and W3 stay resident in shared memory; W1 / W2 (hi+lo images, 80 / 64 KB)
+// are streamed from L2 into one weight buffer per tile, W1 while the ray_feat tile is being staged and W2 under the
+// first hidden layer's epilogue.  One persistent CTA (16 warps) per SM, 128 rays per tile, TMEM lane == ray.
+#include "tvm_tc.cuh"
+
+namespace {
+using namespace tvmtc;
+
+struct Tc3Args {
+    const float* rays;
+    long long n_rays;
+    int ray_stride;
+    const float* bg;
+    float* rgb;
+    float* depth_out;
+    float* acc_out;
+    const float* ray_feat;
+    const float* acc;
+    const float* depth;
+    const int* app_count;
+    const unsigned char* wimg;     // [b0h|b0l|w1h|w1l|w2h|w2l|w3h|w3l] bf16 canonical images (tvm_pack_mlp_tc3)
+    const float* b1; const float* b2; const float* b3;
+    TcDims d;
+};
+
+struct Tc3Layout {
+    int b0, w1, w2, w3, total;      // byte offsets of the (hi|lo) image pairs inside wimg; each pair = 2 * size
+    int sz_b0, sz_w1, sz_w2, sz_w3;
+};
+__host__ __device__ inline Tc3Layout tc3_layout(const TcDims& d) {
+    Tc3Layout L;
+    L.sz_b0 = N0 * d.k0 * 2; L.sz_w1 = FC * d.k1 * 2; L.sz_w2 = FC * FC * 2; L.sz_w3 = N3 * FC * 2;
+    L.b0 = 0;
+    L.w1 = L.b0 + 2 * L.sz_b0;
+    L.w2 = L.w1 + 2 * L.sz_w1;
+    L.w3 = L.w2 + 2 * L.sz_w2;
+    L.total = L.w3 + 2 * L.sz_w3;
+    return L;
+}
+
+// D[128 x N] = A . B^T with 2-term split operands: hi.hi + hi.lo + lo.hi per K-step
+__device__ __forceinline__ void issue_gemm3(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                            int K, int N, uint32_t bar) {
+    const uint64_t dah = make_desc(a_hi, K), dal = make_desc(a_lo, K);
+    const uint64_t dbh = make_desc(b_hi, K), dbl = make_desc(b_lo, K);
+    const uint32_t idesc = make_idesc(128, N);
+    for (int j = 0; j < K / 16; ++j) {
+        const uint64_t o = (uint64_t)(j * 16);
+        umma_bf16(tmem_d, dah + o, dbh + o, idesc, j > 0 ? 1u : 0u);
+        umma_bf16(tmem_d, dah + o, dbl + o, idesc, 1u);
+        umma_bf16(tmem_d, dal + o, dbh + o, idesc, 1u);
+    }
+    umma_commit(bar);
+}
+
+__device__ __forceinline__ void split_store8(unsigned char* hi_base, unsigned char* lo_base, int off, const float (&v)[8]) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * e]), h1 = __float2bfloat16_rn(v[2 * e + 1]);
+        const __nv_bfloat162 hp = __halves2bfloat162(h0, h1);
+        h[e] = *reinterpret_cast<const uint32_t*>(&hp);
+        l[e] = pack_bf16x2(v[2 * e] - __bfloat162float(h0), v[2 * e + 1] - __bfloat162float(h1));
+    }
+    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void split_store1(unsigned char* hi_base, unsigned char* lo_base, int off, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    *reinterpret_cast<__nv_bfloat16*>(hi_base + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(lo_base + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ void coop_copy(unsigned char* dst, const unsigned char* __restrict__ src, int bytes, int tid) {
+    for (int i = tid * 16; i < bytes; i += TC_THREADS * 16)
+        *reinterpret_cast<uint4*>(dst + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_constant__ Tc3Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TcDims& d = a.d;
+    const Tc3Layout L = tc3_layout(d);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = (warp & 3) * 32 + lane, cg = warp >> 2;
+    const int kmax = d.k0 > d.k1 ? (d.k0 > FC ? d.k0 : FC) : (d.k1 > FC ? d.k1 : FC);
+    const int a_half = TC_RAYS * kmax * 2;                     // one A image (hi or lo)
+    const int w_half = FC * (d.k1 > FC ? d.k1 : FC) * 2;       // one streamed weight image (hi or lo)
+    unsigned char* s_b0 = smem;                                // basis hi | lo (resident)
+    unsigned char* s_w3 = s_b0 + 2 * L.sz_b0;                  // W3 hi | lo (resident)
+    unsigned char* s_w = s_w3 + 2 * L.sz_w3;                   // streamed W1 / W2: hi | lo
+    unsigned char* s_a = s_w + 2 * w_half;                     // A operand: hi | lo
+    float* s_bias = reinterpret_cast<float*>(s_a + 2 * a_half);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 2 * FC + 4);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+    unsigned char* s_ah = s_a;
+    unsigned char* s_al = s_a + a_half;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(s_tmem)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(s_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    coop_copy(s_b0, a.wimg + L.b0, 2 * L.sz_b0, tid);
+    coop_copy(s_w3, a.wimg + L.w3, 2 * L.sz_w3, tid);
+    for (int i = tid; i < 2 * FC + 4; i += TC_THREADS)
+        s_bias[i] = i < FC ? __ldg(a.b1 + i) : (i < 2 * FC ? __ldg(a.b2 + i - FC) : (i - 2 * FC < 3 ? __ldg(a.b3 + i - 2 * FC) : 0.f));
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t bar = smem_u32(s_bar);
+    const uint32_t sah = smem_u32(s_ah), sal = smem_u32(s_al);
+    const uint32_t swh = smem_u32(s_w), swl = smem_u32(s_w + w_half);
+    const uint32_t sb0h = smem_u32(s_b0), sb0l = smem_u32(s_b0 + L.sz_b0);
+    const uint32_t sw3h = smem_u32(s_w3), sw3l = smem_u32(s_w3 + L.sz_w3);
+    uint32_t phase = 0;
+    const long long n_tiles = (a.n_rays + TC_RAYS - 1) / TC_RAYS;
+    const int nbase = d.app_dim + 3;
+    const int sin_f = nbase, cos_f = sin_f + d.app_dim * d.fea_pe;
+    const int sin_v = cos_f + d.app_dim * d.fea_pe, cos_v = sin_v + 3 * d.view_pe;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long r = tile * TC_RAYS + row;
+        const bool live = r < a.n_rays;
+        // ---- stream W1 (hi|lo) into the weight buffer; stage the ray_feat tile as split A operand (K0)
+        coop_copy(s_w, a.wimg + L.w1, L.sz_w1, tid);
+        coop_copy(s_w + w_half, a.wimg + L.w1 + L.sz_w1, L.sz_w1, tid);
+        for (int kc = cg; kc < d.k0 / 8; kc += 4) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            if (live && kc * 8 < d.ta) {
+                const float4 lo = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8));
+                v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+                if (kc * 8 + 4 < d.ta) {
+                    const float4 hi = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8 + 4));
+                    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+                }
+            }
+            split_store8(s_ah, s_al, canon_off(row, kc * 8, d.k0), v);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMA 1: feat = F . B^T
+        if (tid == 0) { tc_fence_after(); issue_gemm3(tmem + COL0, sah, sal, sb0h, sb0l, d.k0, N0, bar); }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        {
+            float v[32];
+            tmem_ld32(lane_base + COL0, v);
+#pragma unroll
+            for (int ch = 0; ch < 32; ++ch) {
+                if ((ch & 3) != cg || ch >= nbase) continue;
+                const bool is_feat = ch < d.app_dim;
+                float x = v[ch];
+                if (!is_feat) x = live ? __ldg(a.rays + r * a.ray_stride + 3 + (ch - d.app_dim)) : 0.f;
+                split_store1(s_ah, s_al, canon_off(row, ch, d.k1), x);
+                const int nf = is_feat ? d.fea_pe : d.view_pe;
+                const int cc = is_feat ? ch : ch - d.app_dim;
+                const int sb = is_feat ? sin_f : sin_v, cb = is_feat ? cos_f : cos_v;
+                float scale = 1.f;
+                for (int j = 0; j < nf; ++j) {
+                    float sn, cs;
+                    sincosf(x * scale, &sn, &cs);
+                    split_store1(s_ah, s_al, canon_off(row, sb + cc * nf + j, d.k1), sn);
+                    split_store1(s_ah, s_al, canon_off(row, cb + cc * nf + j, d.k1), cs);
+                    scale *= 2.f;
+                }
+            }
+            if (cg == 3)
+                for (int k = d.in_c; k < d.k1; ++k) split_store1(s_ah, s_al, canon_off(row, k, d.k1), 0.f);
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMA 2: h1 = X . W1^T
+        if (tid == 0) { tc_fence_after(); issue_gemm3(tmem + COL1, sah, sal, swh, swl, d.k1, FC, bar); }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        // W1 and X are consumed: stream W2 into the weight buffer under the epilogue
+        coop_copy(s_w, a.wimg + L.w2, L.sz_w2, tid);
+        coop_copy(s_w + w_half, a.wimg + L.w2 + L.sz_w2, L.sz_w2, tid);
+        {
+            const int cb = cg * 32;
+            float v[32];
+            tmem_ld32(lane_base + COL1 + cb, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float u[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) u[e] = fmaxf(v[q * 8 + e] + s_bias[cb + q * 8 + e], 0.f);
+                split_store8(s_ah, s_al, canon_off(row, cb + q * 8, FC), u);
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMA 3: h2 = h1 . W2^T
+        if (tid == 0) { tc_fence_after(); issue_gemm3(tmem + COL2, sah, sal, swh, swl, FC, FC, bar); }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        {
+            const int cb = cg * 32;
+            float v[32];
+            tmem_ld32(lane_base + COL2 + cb, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float u[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) u[e] = fmaxf(v[q * 8 + e] + s_bias[FC + cb + q * 8 + e], 0.f);
+                split_store8(s_ah, s_al, canon_off(row, cb + q * 8, FC), u);
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        // ---- MMA 4: rgb_raw = h2 . W3^T (N padded to 16)
+        if (tid == 0) { tc_fence_after(); issue_gemm3(tmem + COL3, sah, sal, sw3h, sw3l, FC, N3, bar); }
+        mbar_wait(bar, phase); phase ^= 1;
+        tc_fence_after();
+        if (cg == 0) {
+            float v[32];
+            tmem_ld32(lane_base + COL3, v);
+            if (live) {
+                const bool lit = __ldg(a.app_count + r) > 0;
+                const float ac = __ldg(a.acc + r);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float col = lit ? 1.f / (1.f + expf(-(v[c] + s_bias[2 * FC + c]))) : 0.f;
+                    const float out = col * ac + __ldg(a.bg + c) * (1.f - ac);
+                    a.rgb[r * 3 + c] = fminf(fmaxf(out, 0.f), 1.f);
+                }
+                const float last = __ldg(a.rays + r * a.ray_stride + a.ray_stride - 1);
+                if (a.depth_out) a.depth_out[r] = __ldg(a.depth + r) + (1.f - ac) * last;
+                if (a.acc_out) a.acc_out[r] = ac;
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+size_t tc3_smem_bytes(const TcDims& d) {
+    const Tc3Layout L = tc3_layout(d);
+    const int kmax = d.k0 > d.k1 ? (d.k0 > FC ? d.k0 : FC) : (d.k1 > FC ? d.k1 : FC);
+    const size_t a_half = (size_t)TC_RAYS * kmax * 2;
+    const size_t w_half = (size_t)FC * (d.k1 > FC ? d.k1 : FC) * 2;
+    return 2 * (size_t)L.sz_b0 + 2 * (size_t)L.sz_w3 + 2 * w_half + 2 * a_half + (2 * FC + 4) * 4 + 16;
+}
+
+}  // namespace
+
+extern "C" size_t tvm_mlp_tc3_pack_bytes(const tvm_field_desc* desc) {
+    if (!desc) return 0;
+    return (size_t)tc3_layout(tc_dims(desc)).total;
+}
+
+extern "C" int tvm_pack_mlp_tc3(const tvm_field_desc* desc, const float* basis, const float* w1, const float* w2,
+                                const float* w3, void* packed, void* stream) {
+    if (!desc || !basis || !w1 || !w2 || !w3 || !packed) return TVM_E_NULL;
+    if (desc->feature_c != FC || desc->app_dim + 3 > N0 || desc->app_dim <= 0) return TVM_E_SHAPE;
+    const TcDims d = tc_dims(desc);
+    if (tc3_smem_bytes(d) > 227 * 1024) return TVM_E_SHAPE;
+    const Tc3Layout L = tc3_layout(d);
+    unsigned char* out = (unsigned char*)packed;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int part = 0; part < 2; ++part) {
+        pack_bf16_operand_kernel<<<(N0 * d.k0 + 255) / 256, 256, 0, st>>>(basis, d.app_dim, d.ta, N0, d.k0,
+                                                                         out + L.b0 + part * L.sz_b0, part);
+        pack_bf16_operand_kernel<<<(FC * d.k1 + 255) / 256, 256, 0, st>>>(w1, FC, d.in_c, FC, d.k1,
+                                                                         out + L.w1 + part * L.sz_w1, part);
+        pack_bf16_operand_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(w2, FC, FC, FC, FC,
+                                                                       out + L.w2 + part * L.sz_w2, part);
+        pack_bf16_operand_kernel<<<(N3 * FC + 255) / 256, 256, 0, st>>>(w3, 3, FC, N3, FC,
+                                                                       out + L.w3 + part * L.sz_w3, part);
+    }
+    TVM_LAUNCH_CHECK();
+    return 0;
+}
+
+// called by tvm_shade_fwd when TVM_F_MLP_TC3 is set
+int tvm_shade_tc3_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
+                         const float* bg, float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes,
+                         cudaStream_t st) {
+    if (!desc->mlp_tc3 || !desc->mlp) return TVM_E_NULL;
+    if (desc->feature_c != FC || desc->app_dim + 3 > N0 || desc->app_dim <= 0) return TVM_E_SHAPE;
+    const TcDims d = tc_dims(desc);
+    const size_t smem = tc3_smem_bytes(d);
+    if (smem > 227 * 1024) return TVM_E_SHAPE;
+    const TvmWorkspace w = tvm_ws_layout(desc, n_rays);
+    if (ws_bytes < w.total) return TVM_E_WORKSPACE;
+    const TvmMlpLayout m = tvm_mlp_layout(desc);
+    const char* base = (const char*)ws;
+    Tc3Args a{};
+    a.rays = rays; a.n_rays = n_rays; a.ray_stride = ray_stride; a.bg = bg;
+    a.rgb = rgb; a.depth_out = depth; a.acc_out = acc;
+    a.ray_feat = (const float*)(base + w.ray_feat);
+    a.acc = (const float*)(base + w.acc);
+    a.depth = (const float*)(base + w.depth);
+    a.app_count = (const int*)(base + w.app_count);
+    a.wimg = (const unsigned char*)desc->mlp_tc3;
+    a.b1 = desc->mlp + m.b1; a.b2 = desc->mlp + m.b2; a.b3 = desc->mlp + m.b3;
+    a.d = d;
+    TVM_CUDA_OK(cudaFuncSetAttribute(shade_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long tiles = (n_rays + TC_RAYS - 1) / TC_RAYS;
+    const unsigned grid = (unsigned)(tiles < TVM_SM_COUNT ? tiles : TVM_SM_COUNT);
+    shade_tc3_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+    TVM_LAUNCH_CHECK();
+    return 0;
+}

@@ -118,8 +118,10 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
     max_launch_rays = 1 << 20
     # transmittance below which an eval ray stops marching (error on rgb/acc <= this value)
     early_term_eps = 1e-5
-    # shading-stage arithmetic on the no-grad path: "fp32" (SIMT FFMA kernel, rgb within 1e-4 of the reference) or
-    # "bf16" (tcgen05 tensor-core kernel, rgb within 1e-2 — BASELINE.json's "bf16 MLP mode")
+    # shading-stage arithmetic on the no-grad path:
+    #   "fp32"  SIMT FFMA kernel (rgb within 1e-4 of the reference)
+    #   "tc3"   tcgen05 tensor-core kernel, bf16x3 split operands + fp32 accumulate (fp32-equivalent: ~1e-6 of "fp32")
+    #   "bf16"  tcgen05 tensor-core kernel, plain bf16 operands (rgb within 1e-2 — BASELINE.json's "bf16 MLP mode")
     mlp_precision = "fp32"
 
     def __init__(self, aabb, gridSize, device, density_n_comp=8, appearance_n_comp=24, app_dim=27,
@@ -359,21 +361,23 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
             self._mlp_key = key
         return self._mlp_packed
 
-    def packed_mlp_tc(self):
-        """bf16 operand images of basis_mat + MLP weights for the tcgen05 shade kernel."""
+    def packed_mlp_tc(self, split=False):
+        """bf16 operand images of basis_mat + MLP weights for the tcgen05 shade kernels (split: hi|lo pairs)."""
         mods = [self.renderModule.mlp[i] for i in (0, 2, 4)]
         ps = [self.basis_mat.weight] + [m.weight for m in mods]
-        key = tuple((p.data_ptr(), p._version) for p in ps)
+        key = (split,) + tuple((p.data_ptr(), p._version) for p in ps)
         if self._mlp_tc is None or self._mlp_tc_key != key:
             dev = ps[0].device
             d = self._base_desc()
             lib = _lib.load()
-            n = lib.tvm_mlp_tc_pack_bytes(C.byref(d))
+            size_fn = lib.tvm_mlp_tc3_pack_bytes if split else lib.tvm_mlp_tc_pack_bytes
+            pack_fn = lib.tvm_pack_mlp_tc3 if split else lib.tvm_pack_mlp_tc
+            n = size_fn(C.byref(d))
             if self._mlp_tc is None or self._mlp_tc.numel() != n or self._mlp_tc.device != dev:
                 self._mlp_tc = torch.zeros(int(n), dtype=torch.uint8, device=dev)
             b, w1, w2, w3 = [p.detach().contiguous() for p in ps]
-            _lib.check(lib.tvm_pack_mlp_tc(C.byref(d), _lib.ptr(b), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3),
-                                           _lib.ptr(self._mlp_tc), _stream(dev)), "tvm_pack_mlp_tc")
+            _lib.check(pack_fn(C.byref(d), _lib.ptr(b), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3),
+                               _lib.ptr(self._mlp_tc), _stream(dev)), "tvm_pack_mlp_tc")
             self._mlp_tc_key = key
         return self._mlp_tc
 
@@ -390,14 +394,16 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
                 pm = self.packed_mlp()
                 d.mlp = pm.data_ptr()
                 keep.append(pm)
-            if not self.native_shade:
-                pass
-            elif self.mlp_precision == "bf16":
+            if self.native_shade and self.mlp_precision == "bf16":
                 tc = self.packed_mlp_tc()
                 d.mlp_tc = tc.data_ptr()
                 keep.append(tc)
+            elif self.native_shade and self.mlp_precision == "tc3":
+                tc = self.packed_mlp_tc(split=True)
+                d.mlp_tc3 = tc.data_ptr()
+                keep.append(tc)
             elif self.mlp_precision != "fp32":
-                raise ValueError(f"mlp_precision must be 'fp32' or 'bf16', got {self.mlp_precision!r}")
+                raise ValueError(f"mlp_precision must be 'fp32', 'tc3' or 'bf16', got {self.mlp_precision!r}")
         if self.alphaMask is not None:
             cells = self.alphaMask.cells()
             dx, dy, dz = self.alphaMask._cells_dims
@@ -481,6 +487,8 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
             flags |= _lib.F_NO_SHADE
         elif self.mlp_precision == "bf16":
             flags |= _lib.F_MLP_BF16
+        elif self.mlp_precision == "tc3":
+            flags |= _lib.F_MLP_TC3
         if point_samples:
             flags |= _lib.F_POINT_SAMPLES
         jit = None if jitter is None else jitter.detach().to(dev).float().reshape(-1).contiguous()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 7
+#define TVM_ABI_VERSION 8
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define TVM_E_NULL        (-1)   /* required pointer is NULL                      */
@@ -37,6 +37,8 @@ extern "C" {
 #define TVM_F_EARLY_TERM   (1u << 0)  /* eval only: stop a ray once T < early_term_eps                      */
 #define TVM_F_MLP_BF16     (1u << 1)  /* shade with the bf16 tensor-core MLP (tolerance 1e-2) instead of fp32 */
 #define TVM_F_NO_SHADE     (1u << 2)  /* stop after the march stage: workspace holds ray_feat/acc/depth      */
+#define TVM_F_MLP_TC3      (1u << 4)  /* shade on the tensor cores with bf16x3 SPLIT operands (hi.hi + hi.lo + lo.hi,
+                                         fp32 accumulate): fp32-equivalent, rgb within ~1e-6 of the FFMA kernel   */
 #define TVM_F_POINT_SAMPLES (1u << 3) /* sampler of sample_point_color (tensorBase.py:623-638): n_samples samples
                                          centred on the ray origin, z_i = stepSize*(i - n_samples/2)          */
 
@@ -86,6 +88,7 @@ typedef struct tvm_field_desc {
     const float* mlp;            /* packed MLP from tvm_pack_mlp                                           */
     const void*  mlp_tc;         /* bf16 tensor-core weight images from tvm_pack_mlp_tc (NULL unless
                                     TVM_F_MLP_BF16 is used)                                                */
+    const void*  mlp_tc3;        /* split (hi|lo) bf16 images from tvm_pack_mlp_tc3 (NULL unless TVM_F_MLP_TC3) */
 } tvm_field_desc;
 
 int  tvm_abi_version(void);
@@ -118,6 +121,11 @@ int tvm_pack_mlp(const tvm_field_desc* desc, const float* w1, const float* b1, c
 size_t tvm_mlp_tc_pack_bytes(const tvm_field_desc* desc);
 int tvm_pack_mlp_tc(const tvm_field_desc* desc, const float* basis, const float* w1, const float* w2, const float* w3,
                     void* packed, void* stream);
+
+/* the same four operands as 2-term bf16 splits (hi|lo image pairs) for TVM_F_MLP_TC3 */
+size_t tvm_mlp_tc3_pack_bytes(const tvm_field_desc* desc);
+int tvm_pack_mlp_tc3(const tvm_field_desc* desc, const float* basis, const float* w1, const float* w2, const float* w3,
+                     void* packed, void* stream);
 
 /* ---- the hot path ---------------------------------------------------------------------------------- */
 

@@ -54,4 +54,12 @@ march()
 ref_rgb = torch.empty_like(rgb); shade(); ref_rgb.copy_(rgb)
 tc_ms = round(timeit(shade_tc), 4)
 tc_err = float((rgb - ref_rgb).abs().max())
+m.mlp_precision = "tc3"
+d3, keep3 = m.field_desc()
+def shade_tc3():
+    _lib.check(lib.tvm_shade_fwd(C.byref(d3), _lib.ptr(rays), n, rays.shape[1], _lib.ptr(bg), _lib.F_MLP_TC3, _lib.ptr(rgb),
+                                 _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(ws), ws.numel(), st), "shade_tc3")
+tc3_ms = round(timeit(shade_tc3), 4)
+tc3_err = float((rgb - ref_rgb).abs().max())
+print(json.dumps({"shade_tc3_ms": tc3_ms, "shade_tc3_max_abs_vs_fp32": tc3_err}))
 print(json.dumps({"tag": a.tag, "shade_tc_ms": tc_ms, "shade_tc_max_abs_vs_fp32": tc_err, "march_ms": round(timeit(march), 4), "shade_ms": round(timeit(shade), 4), "early": not a.no_early}))

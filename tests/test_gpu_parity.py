@@ -86,6 +86,23 @@ def test_bf16_tensor_core_mlp_mode(name, dev):
     assert np.abs(o["acc_map"].cpu().numpy() - g["acc_map"]).max() <= TOL
 
 
+@pytest.mark.parametrize("name", ["c1_dense_mask", "c2_sub", "c4_sub"])
+def test_split_operand_tensor_core_mlp_mode(name, dev):
+    """TVM_F_MLP_TC3: tcgen05 shading with bf16x3 split operands — fp32-equivalent: inside the fp32 parity bound
+    against the reference and within 1e-5 of the FFMA kernel."""
+    fld, rays, g, white, m = _case(name, dev)
+    ref = m.render_eval(rays.to(dev), white_bg=bool(white))["rgb_map"].clone()
+    m.mlp_precision = "tc3"
+    try:
+        o = m.render_eval(rays.to(dev), white_bg=bool(white))
+        torch.cuda.synchronize()
+    finally:
+        m.mlp_precision = "fp32"
+    assert np.abs(o["rgb_map"].cpu().numpy() - g["rgb_map"]).max() <= TOL
+    assert (o["rgb_map"] - ref).abs().max().item() <= 1e-5
+    assert np.abs(o["depth_map"].cpu().numpy() - g["depth_map"]).max() <= TOL
+
+
 def test_forward_six_tuple_matches_oracle(dev):
     fld, rays, g, white, m = _case("c1_dense_mask", dev)
     sub = rays[3000:3700].contiguous()
