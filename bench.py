@@ -345,13 +345,18 @@ def run_ours(args, rank, world, local_rank):
         ms_dev = timed(step_device, args.steps, args.warmup)
     ms_march = timed(step_march_only, args.steps, 1)
     ms_e2e = timed(step_e2e, args.steps, 1)
-    # the same step with the tcgen05 bf16 shading kernel (north_star's "bf16 MLP mode", rgb within 1e-2)
+    shade_default = model._shade_mode()          # "tc3": tensor cores, bf16x3 split operands, fp32 accumulate
+    # the same step with the other shading kernels: fp32 SIMT FFMA, and plain-bf16 tensor cores (1e-2 mode)
+    model.mlp_precision = "fp32"
     ref_rgb = step_device()["rgb_map"].clone()
+    ms_dev_simt = timed(step_device, args.steps, 1)
+    model.mlp_precision = "auto"
+    def_err = float((step_device()["rgb_map"] - ref_rgb).abs().max())
     model.mlp_precision = "bf16"
     ms_dev_tc = timed(step_device, args.steps, 1)
     ms_e2e_tc = timed(step_e2e, args.steps, 1)
     tc_err = float((step_device()["rgb_map"] - ref_rgb).abs().max())
-    model.mlp_precision = "fp32"
+    model.mlp_precision = "auto"
 
     # work counters of one step (from the march workspace) for the algorithmic-bytes roofline
     o = model.render_eval(rays_dev, white_bg=True, keep_workspace=True)
@@ -386,10 +391,10 @@ def run_ours(args, rank, world, local_rank):
 
     dp = dp_train_step(model, dev, fx, world, rank) if world > 1 else None
 
-    t = torch.tensor([ms_dev, ms_march, ms_e2e, ms_dev_tc, ms_e2e_tc], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_dev, ms_march, ms_e2e, ms_dev_tc, ms_e2e_tc, ms_dev_simt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_march, ms_e2e, ms_dev_tc, ms_e2e_tc = t.tolist()
+    ms_dev, ms_march, ms_e2e, ms_dev_tc, ms_e2e_tc, ms_dev_simt = t.tolist()
     if rank == 0:
         K = args.steps
         peak, peak_src = peaks()
@@ -403,7 +408,9 @@ def run_ours(args, rank, world, local_rank):
                 "steps": K, "warmup": args.warmup, "ms_per_step": ms_dev / K, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config({"parallelism": f"ray-sharded views x{world}", "early_term_eps":
-                                           model.early_term_eps}),
+                                           model.early_term_eps, "shading_kernel": shade_default,
+                                           "mlp_arithmetic": "tcgen05 MMA on bf16x3 split operands (hi.hi+hi.lo+lo.hi), "
+                                                             "fp32 accumulate; max|rgb - fp32 FFMA kernel| = %.1e" % def_err}),
                 "samples_per_s_nominal": world * n * S * K / (ms_dev / 1e3),
                 "sigma_samples_per_s": world * v * K / (ms_dev / 1e3),
                 "app_samples_per_s": world * a * K / (ms_dev / 1e3),
@@ -422,6 +429,9 @@ def run_ours(args, rank, world, local_rank):
                                                        if gather_peak.get("l2_random_64B_gbs") else None),
                              "note": "factor set (69 MB) is L2-resident and mostly L1-hit: achieved algorithmic "
                                      "bytes/s exceeds the HBM copy peak; DRAM traffic per launch is in `traffic`"},
+                "fp32_simt_mlp_mode": {"value": world * n * K / (ms_dev_simt / 1e3), "unit": UNIT,
+                                       "ms_per_step": ms_dev_simt / K,
+                                       "note": "shade_fwd_kernel (FFMA) instead of the tensor-core kernel"},
                 "bf16_mlp_mode": {"value": world * n * K / (ms_dev_tc / 1e3), "e2e": world * n * K / (ms_e2e_tc / 1e3),
                                   "unit": UNIT, "ms_per_step": ms_dev_tc / K, "max_abs_rgb_vs_fp32": tc_err,
                                   "shade_tflops": 2 * 39856 * n * 1e-12 / max((ms_dev_tc - ms_march) / K / 1e3, 1e-9),

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "tvm_pack_mlp": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "tvm_mlp_tc_pack_bytes": (C.c_size_t, [C.POINTER(FieldDesc)]),
     "tvm_pack_mlp_tc": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P]),
+    "tvm_mlp_tc3_supported": (C.c_int, [C.POINTER(FieldDesc)]),
     "tvm_mlp_tc3_pack_bytes": (C.c_size_t, [C.POINTER(FieldDesc)]),
     "tvm_pack_mlp_tc3": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P]),
     "tvm_sample_mask": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_int, _P, C.c_uint32, _P, _P, _P]),

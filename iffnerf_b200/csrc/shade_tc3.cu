@@ -267,6 +267,11 @@ size_t tc3_smem_bytes(const TcDims& d) {
 
 }  // namespace
 
+extern "C" int tvm_mlp_tc3_supported(const tvm_field_desc* desc) {
+    if (!desc || desc->feature_c != FC || desc->app_dim + 3 > N0 || desc->app_dim <= 0) return 0;
+    return tc3_smem_bytes(tc_dims(desc)) <= 227 * 1024 ? 1 : 0;
+}
+
 extern "C" size_t tvm_mlp_tc3_pack_bytes(const tvm_field_desc* desc) {
     if (!desc) return 0;
     return (size_t)tc3_layout(tc_dims(desc)).total;

@@ -122,7 +122,8 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
     #   "fp32"  SIMT FFMA kernel (rgb within 1e-4 of the reference)
     #   "tc3"   tcgen05 tensor-core kernel, bf16x3 split operands + fp32 accumulate (fp32-equivalent: ~1e-6 of "fp32")
     #   "bf16"  tcgen05 tensor-core kernel, plain bf16 operands (rgb within 1e-2 — BASELINE.json's "bf16 MLP mode")
-    mlp_precision = "fp32"
+    #   "auto"  (default) "tc3" when the head's shape fits that kernel (fea_pe = view_pe = 2 does), else "fp32"
+    mlp_precision = "auto"
 
     def __init__(self, aabb, gridSize, device, density_n_comp=8, appearance_n_comp=24, app_dim=27,
                  shadingMode="MLP_PE", alphaMask=None, near_far=[2.0, 6.0], density_shift=-10,
@@ -361,6 +362,20 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
             self._mlp_key = key
         return self._mlp_packed
 
+    def _shade_mode(self):
+        """Resolves mlp_precision to the shading kernel actually used: 'fp32' | 'tc3' | 'bf16'."""
+        mode = self.mlp_precision
+        if mode not in ("auto", "fp32", "tc3", "bf16"):
+            raise ValueError(f"mlp_precision must be 'auto', 'fp32', 'tc3' or 'bf16', got {mode!r}")
+        if mode != "auto":
+            return mode
+        key = (self.app_dim, self.fea_pe, self.view_pe, self.featureC, tuple(self.app_n_comp))
+        if getattr(self, "_auto_key", None) != key:
+            d = self._base_desc()
+            ok = _lib.load().tvm_mlp_tc3_supported(C.byref(d)) != 0
+            self._auto_key, self._auto_mode = key, ("tc3" if ok else "fp32")
+        return self._auto_mode
+
     def packed_mlp_tc(self, split=False):
         """bf16 operand images of basis_mat + MLP weights for the tcgen05 shade kernels (split: hi|lo pairs)."""
         mods = [self.renderModule.mlp[i] for i in (0, 2, 4)]
@@ -394,16 +409,16 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
                 pm = self.packed_mlp()
                 d.mlp = pm.data_ptr()
                 keep.append(pm)
-            if self.native_shade and self.mlp_precision == "bf16":
+            mode = self._shade_mode() if self.native_shade else "fp32"
+            if self.native_shade and mode == "bf16":
                 tc = self.packed_mlp_tc()
                 d.mlp_tc = tc.data_ptr()
                 keep.append(tc)
-            elif self.native_shade and self.mlp_precision == "tc3":
+            elif self.native_shade and mode == "tc3":
                 tc = self.packed_mlp_tc(split=True)
                 d.mlp_tc3 = tc.data_ptr()
                 keep.append(tc)
-            elif self.mlp_precision != "fp32":
-                raise ValueError(f"mlp_precision must be 'fp32', 'tc3' or 'bf16', got {self.mlp_precision!r}")
+
         if self.alphaMask is not None:
             cells = self.alphaMask.cells()
             dx, dy, dz = self.alphaMask._cells_dims
@@ -485,9 +500,9 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         flags = _lib.F_EARLY_TERM if (early_term and not sample_outputs) else 0
         if not self.native_shade:
             flags |= _lib.F_NO_SHADE
-        elif self.mlp_precision == "bf16":
+        elif self._shade_mode() == "bf16":
             flags |= _lib.F_MLP_BF16
-        elif self.mlp_precision == "tc3":
+        elif self._shade_mode() == "tc3":
             flags |= _lib.F_MLP_TC3
         if point_samples:
             flags |= _lib.F_POINT_SAMPLES

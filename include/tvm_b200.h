@@ -123,6 +123,7 @@ int tvm_pack_mlp_tc(const tvm_field_desc* desc, const float* basis, const float*
                     void* packed, void* stream);
 
 /* the same four operands as 2-term bf16 splits (hi|lo image pairs) for TVM_F_MLP_TC3 */
+int tvm_mlp_tc3_supported(const tvm_field_desc* desc);   /* 1 if the head's shape fits the split kernel's smem */
 size_t tvm_mlp_tc3_pack_bytes(const tvm_field_desc* desc);
 int tvm_pack_mlp_tc3(const tvm_field_desc* desc, const float* basis, const float* w1, const float* w2, const float* w3,
                      void* packed, void* stream);

@@ -21,6 +21,7 @@ rays = fx.config2_rays().to(dev)
 n, S = rays.shape[0], m.nSamples
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 lib = _lib.load()
+m.mlp_precision = "fp32"
 d, keep = m.field_desc()
 need = C.c_size_t(0)
 lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need))

@@ -53,12 +53,19 @@ def test_valid_mask_and_counts_bit_exact(name, dev):
     assert np.array_equal(counts.cpu().numpy(), g["valid_count"])
 
 
+@pytest.mark.parametrize("mlp", ["auto", "fp32"])
 @pytest.mark.parametrize("early_term", [False, True])
 @pytest.mark.parametrize("name", sorted(EVAL_CASES))
-def test_render_matches_reference_golden(name, early_term, dev):
+def test_render_matches_reference_golden(name, early_term, mlp, dev):
+    """mlp='auto' is the default shading kernel (tensor cores, bf16x3 split operands); 'fp32' the SIMT FFMA kernel."""
     fld, rays, g, white, m = _case(name, dev)
-    o = m.render_eval(rays.to(dev), white_bg=bool(white), early_term=early_term, want_counts=True)
-    torch.cuda.synchronize()
+    m.mlp_precision = mlp
+    try:
+        assert m._shade_mode() == ("tc3" if mlp == "auto" else "fp32")
+        o = m.render_eval(rays.to(dev), white_bg=bool(white), early_term=early_term, want_counts=True)
+        torch.cuda.synchronize()
+    finally:
+        m.mlp_precision = type(m).mlp_precision
     assert np.abs(o["rgb_map"].cpu().numpy() - g["rgb_map"]).max() <= TOL
     assert np.abs(o["depth_map"].cpu().numpy() - g["depth_map"]).max() <= TOL
     assert np.abs(o["acc_map"].cpu().numpy() - g["acc_map"]).max() <= TOL
@@ -78,7 +85,7 @@ def test_bf16_tensor_core_mlp_mode(name, dev):
         o = m.render_eval(rays.to(dev), white_bg=bool(white))
         torch.cuda.synchronize()
     finally:
-        m.mlp_precision = "fp32"
+        m.mlp_precision = type(m).mlp_precision
     err = np.abs(o["rgb_map"].cpu().numpy() - g["rgb_map"]).max()
     assert err <= 1e-2, err
     assert err > 0                                            # it really is the reduced-precision path
@@ -91,13 +98,14 @@ def test_split_operand_tensor_core_mlp_mode(name, dev):
     """TVM_F_MLP_TC3: tcgen05 shading with bf16x3 split operands — fp32-equivalent: inside the fp32 parity bound
     against the reference and within 1e-5 of the FFMA kernel."""
     fld, rays, g, white, m = _case(name, dev)
-    ref = m.render_eval(rays.to(dev), white_bg=bool(white))["rgb_map"].clone()
-    m.mlp_precision = "tc3"
+    m.mlp_precision = "fp32"
     try:
+        ref = m.render_eval(rays.to(dev), white_bg=bool(white))["rgb_map"].clone()
+        m.mlp_precision = "tc3"
         o = m.render_eval(rays.to(dev), white_bg=bool(white))
         torch.cuda.synchronize()
     finally:
-        m.mlp_precision = "fp32"
+        m.mlp_precision = type(m).mlp_precision
     assert np.abs(o["rgb_map"].cpu().numpy() - g["rgb_map"]).max() <= TOL
     assert (o["rgb_map"] - ref).abs().max().item() <= 1e-5
     assert np.abs(o["depth_map"].cpu().numpy() - g["depth_map"]).max() <= TOL
