@@ -13,5 +13,5 @@ BENCH="python bench.py --steps 2 --warmup 1 --no-cpu-baseline"
 timeout 600 $BENCH > gpurun_out/plain_${TAG}.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_${TAG}.csv $BENCH > gpurun_out/ncu_list_${TAG}.log 2>&1
 timeout 600 $BENCH > gpurun_out/plain2_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k 'regex:march_fwd|shade' -s 2 -c 6 -f -o gpurun_out/prof_march_${TAG} $BENCH > gpurun_out/ncu_full_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:march_fwd|shade_tc3' -s 2 -c 4 -f -o gpurun_out/prof_march_${TAG} $BENCH > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out | tail -20
