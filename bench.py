@@ -295,7 +295,8 @@ def run_ours(args, rank, world, local_rank):
     n = rays_dev.shape[0]
     S = model.nSamples
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
-    out_host = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    rgb_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()      # contiguous pinned destinations
+    depth_host = torch.empty((n,), dtype=torch.float32).pin_memory()
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -337,8 +338,8 @@ def run_ours(args, rank, world, local_rank):
     def step_e2e():
         rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(rays_host, model, chunk=4096, N_samples=-1, white_bg=True,
                                                           ndc_ray=False, device=dev)
-        out_host[:, :3].copy_(rgb, non_blocking=True)
-        out_host[:, 3].copy_(depth, non_blocking=True)
+        rgb_host.copy_(rgb, non_blocking=True)
+        depth_host.copy_(depth, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
 
     with ClockSampler(local_rank) as clk:
