@@ -59,6 +59,7 @@ struct MarchArgs {
     int ta;
     int app_off[3];
     int rays_per_cta;
+    TvmSections sec;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -111,9 +112,17 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
             for (int w = lane; w < words; w += 32)
                 if (!bm.test(w)) a.valid_bits[r * words + w] = 0u;
 
-        for (int i0 = 0; i0 < S; i0 += 32) {
-            const bool flagged = bm.test(i0 >> 5);
-            if (!flagged && !sample_out) continue;
+        // visit the flagged blocks only (find-next-set-bit); per-sample outputs force a visit of every block
+        const int nblk = words;
+        int wi = 0;
+        unsigned todo = sample_out ? tvm_all_blocks_word(0, nblk) : bm.word(0);
+        for (;;) {
+            while (todo == 0u && ++wi < ((nblk + 31) >> 5)) todo = sample_out ? tvm_all_blocks_word(wi, nblk) : bm.word(wi);
+            if (todo == 0u) break;
+            const int blk = (wi << 5) + (__ffs(todo) - 1);
+            todo &= todo - 1u;
+            const int i0 = blk << 5;
+            const bool flagged = !sample_out || bm.test(blk);
             const int i = i0 + lane;
             const bool in_range = i < S;
             const float z = tvm_sample_z(f, ray, i);
@@ -136,6 +145,9 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                 if (!dead && vmask) {
                     float n[3];
                     tvm_normalize(f, p, n);
+                    // fractional texel indices, once per sample (the quads rebuild taps from them)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) n[c] = tvm_unnormalize(n[c], f.grid[c]);
                     // ---- density: compact valid samples, 8 per pass, one quad per sample
                     const int nv = __popc(vmask), rank = __popc(vmask & lt_mask);
                     if (keep) s_slot[warp][rank] = make_float4(n[0], n[1], n[2], 0.f);
@@ -146,7 +158,7 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                         if (ci < nv) {
                             const float4 s = s_slot[warp][ci];
                             const float q[3] = {s.x, s.y, s.z};
-                            part = density_partial<CS4>(f, q, sub);
+                            part = density_partial_taps<CS4>(f, a.sec, make_sample_taps_idx(f, q), sub);
                         }
                         part += __shfl_xor_sync(FULL, part, 1);
                         part += __shfl_xor_sync(FULL, part, 2);
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                             if (ci < na) {
                                 const float4 s = s_slot[warp][ci];
                                 const float q[3] = {s.x, s.y, s.z};
-                                app_accumulate<G, CA4>(f, q, s.w, sub, A);
+                                app_accumulate_taps<G, CA4>(f, a.sec, make_sample_taps_idx(f, q), s.w, sub, A);
                             }
                         }
                         __syncwarp();
@@ -212,10 +224,12 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     float4 v = A[k][g];
+                    if (n_app > 0) {            // warp-uniform; rays without appearance samples store their zeros
 #pragma unroll
-                    for (int o = 4; o < 32; o <<= 1) {
-                        v.x += __shfl_xor_sync(FULL, v.x, o); v.y += __shfl_xor_sync(FULL, v.y, o);
-                        v.z += __shfl_xor_sync(FULL, v.z, o); v.w += __shfl_xor_sync(FULL, v.w, o);
+                        for (int o = 4; o < 32; o <<= 1) {
+                            v.x += __shfl_xor_sync(FULL, v.x, o); v.y += __shfl_xor_sync(FULL, v.y, o);
+                            v.z += __shfl_xor_sync(FULL, v.z, o); v.w += __shfl_xor_sync(FULL, v.w, o);
+                        }
                     }
                     const int j = sub + 4 * g;
                     if (quad == 0 && j < (CA4 > 0 ? CA4 : (f.n_app[k] >> 2)))
@@ -245,6 +259,7 @@ int fill_args(MarchArgs& a, const tvm_field_desc* desc, const float* rays, int64
     a.f = *desc;
     a.rays = rays; a.n_rays = n_rays; a.ray_stride = ray_stride; a.S = n_samples; a.jitter = jitter;
     a.ta = tvm_total_app(desc);
+    a.sec = tvm_sections(*desc);
     a.app_off[0] = 0; a.app_off[1] = desc->n_app[0]; a.app_off[2] = desc->n_app[0] + desc->n_app[1];
     return 0;
 }

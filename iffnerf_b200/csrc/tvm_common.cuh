@@ -80,6 +80,7 @@ static inline int tvm_check_desc(const tvm_field_desc* d) {
         if (d->grid[k] < 2) return TVM_E_SHAPE;
         if ((d->dplane_off[k] | d->dline_off[k] | d->aplane_off[k] | d->aline_off[k]) & 3) return TVM_E_SHAPE;
     }
+    if (d->n_factor_floats < 0 || d->n_factor_floats > (int64_t(1) << 33)) return TVM_E_SHAPE;   // 32-bit float4 indices
     if (d->act != 0 && d->act != 1) return TVM_E_MODE;
     return 0;
 }

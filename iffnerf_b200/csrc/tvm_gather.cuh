@@ -36,14 +36,15 @@ struct AxisTap {
     int i0;
     float w0, w1;
 };
-TVM_HD AxisTap tvm_axis_tap_inbox(float coord, int size) {
-    const float idx = ((coord + 1.0f) * 0.5f) * (float)(size - 1);
+TVM_HD float tvm_unnormalize(float coord, int size) { return ((coord + 1.0f) * 0.5f) * (float)(size - 1); }
+TVM_HD AxisTap tvm_axis_tap_idx(float idx, int size) {
     AxisTap t;
     t.i0 = min(max((int)idx, 0), size - 2);
     t.w1 = idx - (float)t.i0;
     t.w0 = 1.0f - t.w1;
     return t;
 }
+TVM_HD AxisTap tvm_axis_tap_inbox(float coord, int size) { return tvm_axis_tap_idx(tvm_unnormalize(coord, size), size); }
 struct SampleTaps {
     AxisTap a[3];        // x, y, z axis of the field grid
 };
@@ -53,43 +54,76 @@ TVM_HD SampleTaps make_sample_taps(const tvm_field_desc& f, const float n[3]) {
     for (int c = 0; c < 3; ++c) s.a[c] = tvm_axis_tap_inbox(n[c], f.grid[c]);
     return s;
 }
+// same from the fractional texel indices idx[c] = tvm_unnormalize(n[c], grid[c]) (computed once by the lane that owns
+// the sample and handed to the quad through shared memory)
+TVM_HD SampleTaps make_sample_taps_idx(const tvm_field_desc& f, const float idx[3]) {
+    SampleTaps s;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s.a[c] = tvm_axis_tap_idx(idx[c], f.grid[c]);
+    return s;
+}
 
-// texel offsets (in float4 units, before adding the channel slice j) and weights of plane/line pair k
+// float4 offsets of the 12 factor sections inside the packed buffer (32-bit: one base pointer + one IMAD.WIDE.U32 per
+// address instead of a 64-bit section pointer per plane / line).  Built on the host by the launchers.
+struct TvmSections {
+    unsigned dP[3], dL[3], aP[3], aL[3];
+};
+TVM_HD TvmSections tvm_sections(const tvm_field_desc& f) {
+    TvmSections s;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s.dP[k] = (unsigned)(f.dplane_off[k] >> 2); s.dL[k] = (unsigned)(f.dline_off[k] >> 2);
+        s.aP[k] = (unsigned)(f.aplane_off[k] >> 2); s.aL[k] = (unsigned)(f.aline_off[k] >> 2);
+    }
+    return s;
+}
+
+// texel offsets (in float4 units, before adding the channel slice j) and weights of plane/line pair k.
+// Offsets are UNSIGNED 32-bit float4 indices so an address is one IMAD.WIDE.U32 off the section pointer
+// (signed ints cost a sign-extension + LEA pair per load in SASS).
 struct PlaneTaps {
-    int pbase, prow, lbase;      // plane: (y0*W+x0)*C4, W*C4 ; line: l0*C4
-    float w00, w01, w10, w11;    // bilinear weights (ATen: nw, ne, sw, se)
+    unsigned pbase, prow, lbase;  // plane: (y0*W+x0)*C4, W*C4 ; line: l0*C4
+    float w00, w01, w10, w11;     // bilinear weights (ATen: nw, ne, sw, se)
     float lw0, lw1;
 };
 TVM_HD PlaneTaps make_taps(const tvm_field_desc& f, const SampleTaps& s, int k, int C4) {
     const AxisTap& tx = s.a[TVM_M0(k)];
     const AxisTap& ty = s.a[TVM_M1(k)];
     const AxisTap& tl = s.a[TVM_V(k)];
-    const int W = f.grid[TVM_M0(k)];
+    const unsigned W = (unsigned)f.grid[TVM_M0(k)];
     PlaneTaps p;
-    p.pbase = (ty.i0 * W + tx.i0) * C4;
-    p.prow = W * C4;
-    p.lbase = tl.i0 * C4;
+    p.pbase = ((unsigned)ty.i0 * W + (unsigned)tx.i0) * (unsigned)C4;
+    p.prow = W * (unsigned)C4;
+    p.lbase = (unsigned)tl.i0 * (unsigned)C4;
     p.w00 = tx.w0 * ty.w0; p.w01 = tx.w1 * ty.w0; p.w10 = tx.w0 * ty.w1; p.w11 = tx.w1 * ty.w1;
     p.lw0 = tl.w0; p.lw1 = tl.w1;
     return p;
 }
 
-// (plane (x) line) for one float4 channel slice j of a texel with C4 float4s
-TVM_HD float4 vm_product(const float4* __restrict__ P, const float4* __restrict__ Ln, const PlaneTaps& t, int C4,
-                         int j) {
-    const float4* pb = P + t.pbase + j;
-    const float4* lb = Ln + t.lbase + j;
-    const float4 a = TVM_LDG4(pb);
-    const float4 b = TVM_LDG4(pb + C4);
-    const float4 c = TVM_LDG4(pb + t.prow);
-    const float4 d = TVM_LDG4(pb + t.prow + C4);
-    const float4 l0 = TVM_LDG4(lb);
-    const float4 l1 = TVM_LDG4(lb + C4);
+// bilinear plane value and linear line value for one float4 channel slice of a texel with C4 float4s.
+// r0 / r1 point at this lane's slice of the (x0,y0) and (x0,y0+1) texels, lb at the l0 line texel; `o` is a
+// further slice offset (4*g float4s) that stays an immediate in the unrolled callers.
+TVM_HD float4 vm_plane(const float4* __restrict__ r0, const float4* __restrict__ r1, const PlaneTaps& t, int C4, int o) {
+    const float4 a = TVM_LDG4(r0 + o);
+    const float4 b = TVM_LDG4(r0 + o + C4);
+    const float4 c = TVM_LDG4(r1 + o);
+    const float4 d = TVM_LDG4(r1 + o + C4);
     float4 pl = f4_scale(t.w00, a);
     pl = f4_fma(t.w01, b, pl); pl = f4_fma(t.w10, c, pl); pl = f4_fma(t.w11, d, pl);
-    float4 ln = f4_scale(t.lw0, l0);
-    ln = f4_fma(t.lw1, l1, ln);
-    return f4_mul(pl, ln);
+    return pl;
+}
+TVM_HD float4 vm_line(const float4* __restrict__ lb, float lw0, float lw1, int C4, int o) {
+    const float4 l0 = TVM_LDG4(lb + o);
+    const float4 l1 = TVM_LDG4(lb + o + C4);
+    return f4_fma(lw1, l1, f4_scale(lw0, l0));
+}
+// (plane (x) line) for slice j
+TVM_HD float4 vm_product(const float4* __restrict__ P, const float4* __restrict__ Ln, const PlaneTaps& t, int C4,
+                         int j) {
+    const float4* r0 = P + (t.pbase + (unsigned)j);
+    const float4* r1 = P + (t.pbase + t.prow + (unsigned)j);
+    const float4* lb = Ln + (t.lbase + (unsigned)j);
+    return f4_mul(vm_plane(r0, r1, t, C4, 0), vm_line(lb, t.lw0, t.lw1, C4, 0));
 }
 
 // this lane's share of sigma_feature = sum_k sum_c plane_k[c] * line_k[c]   (tensoRF.py:227-233)
@@ -97,38 +131,60 @@ TVM_HD float4 vm_product(const float4* __restrict__ P, const float4* __restrict_
 // lego/truck configs: 16 -> 4, 48 -> 12), which turns the corner / channel-slice offsets into immediates;
 // 0 = read the per-plane counts from the descriptor.
 template <int CS4 = 0>
-TVM_HD float density_partial(const tvm_field_desc& f, const float n[3], int sub) {
+TVM_HD float density_partial_taps(const tvm_field_desc& f, const TvmSections& sec, const SampleTaps& st, int sub) {
     float tot = 0.f;
-    const SampleTaps st = make_sample_taps(f, n);
+    const float4* F4 = reinterpret_cast<const float4*>(f.factors);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int C4 = CS4 > 0 ? CS4 : (f.n_sigma[k] >> 2);
         if (sub < C4) {
             const PlaneTaps t = make_taps(f, st, k, C4);
-            const float4 v = vm_product(reinterpret_cast<const float4*>(f.factors + f.dplane_off[k]),
-                                        reinterpret_cast<const float4*>(f.factors + f.dline_off[k]), t, C4, sub);
-            tot += (v.x + v.y) + (v.z + v.w);
+            const unsigned po = sec.dP[k] + (unsigned)sub, lo = sec.dL[k] + (unsigned)sub;
+            const float4* r0 = F4 + (t.pbase + po);
+            const float4* r1 = F4 + (t.pbase + t.prow + po);
+            const float4* lb = F4 + (t.lbase + lo);
+            const float4 v = f4_mul(vm_plane(r0, r1, t, C4, 0), vm_line(lb, t.lw0, t.lw1, C4, 0));
+            const float s = (v.x + v.y) + (v.z + v.w);
+            tot = (k == 0) ? s : tot + s;
         }
     }
     return tot;
 }
+template <int CS4 = 0>
+TVM_HD float density_partial(const tvm_field_desc& f, const float n[3], int sub) {
+    return density_partial_taps<CS4>(f, tvm_sections(f), make_sample_taps(f, n), sub);
+}
 
-// A[k][g] += w * (app_plane_k (x) app_line_k)[channels of this lane]   (tensoRF.py:237-254, weighted by :888)
+// A[k][g] += w * (app_plane_k (x) app_line_k)[channels of this lane]   (tensoRF.py:237-254, weighted by :888).
+// The sample weight is folded into the two line-tap weights, so a slice costs plane(16) + line(8) + 4 FFMA.
 template <int G, int CA4 = 0>
-TVM_HD void app_accumulate(const tvm_field_desc& f, const float n[3], float w, int sub, float4 (&A)[3][G]) {
-    const SampleTaps st = make_sample_taps(f, n);
+TVM_HD void app_accumulate_taps(const tvm_field_desc& f, const TvmSections& sec, const SampleTaps& st, float w, int sub,
+                                float4 (&A)[3][G]) {
+    const float4* F4 = reinterpret_cast<const float4*>(f.factors);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const int C4 = CA4 > 0 ? CA4 : (f.n_app[k] >> 2);
         const PlaneTaps t = make_taps(f, st, k, C4);
-        const float4* P = reinterpret_cast<const float4*>(f.factors + f.aplane_off[k]);
-        const float4* Ln = reinterpret_cast<const float4*>(f.factors + f.aline_off[k]);
+        const float wl0 = w * t.lw0, wl1 = w * t.lw1;
+        const unsigned po = sec.aP[k] + (unsigned)sub, lo = sec.aL[k] + (unsigned)sub;
+        const float4* r0 = F4 + (t.pbase + po);
+        const float4* r1 = F4 + (t.pbase + t.prow + po);
+        const float4* lb = F4 + (t.lbase + lo);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const int j = sub + 4 * g;
-            if (j < C4) A[k][g] = f4_fma(w, vm_product(P, Ln, t, C4, j), A[k][g]);
+            if (j < C4) {
+                const float4 pl = vm_plane(r0, r1, t, C4, 4 * g);
+                const float4 ln = vm_line(lb, wl0, wl1, C4, 4 * g);
+                A[k][g].x = fmaf(pl.x, ln.x, A[k][g].x); A[k][g].y = fmaf(pl.y, ln.y, A[k][g].y);
+                A[k][g].z = fmaf(pl.z, ln.z, A[k][g].z); A[k][g].w = fmaf(pl.w, ln.w, A[k][g].w);
+            }
         }
     }
+}
+template <int G, int CA4 = 0>
+TVM_HD void app_accumulate(const tvm_field_desc& f, const float n[3], float w, int sub, float4 (&A)[3][G]) {
+    app_accumulate_taps<G, CA4>(f, tvm_sections(f), make_sample_taps(f, n), w, sub, A);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -150,12 +206,13 @@ template <bool SCATTER, bool POSE>
 TVM_HD float4 vm_slice_bwd(const tvm_field_desc& f, const float4* __restrict__ P, const float4* __restrict__ Ln,
                            float4* __restrict__ gP, float4* __restrict__ gL, const SampleTaps& s, const PlaneTaps& t,
                            int C4, int j, float4 up, int k, float dn[3]) {
-    const float4* pb = P + t.pbase + j;
-    const float4* lb = Ln + t.lbase + j;
+    const float4* pb = P + (t.pbase + (unsigned)j);
+    const float4* pb1 = P + (t.pbase + t.prow + (unsigned)j);
+    const float4* lb = Ln + (t.lbase + (unsigned)j);
     const float4 a = TVM_LDG4(pb);
     const float4 b = TVM_LDG4(pb + C4);
-    const float4 c = TVM_LDG4(pb + t.prow);
-    const float4 d = TVM_LDG4(pb + t.prow + C4);
+    const float4 c = TVM_LDG4(pb1);
+    const float4 d = TVM_LDG4(pb1 + C4);
     const float4 l0 = TVM_LDG4(lb);
     const float4 l1 = TVM_LDG4(lb + C4);
     float4 pl = f4_scale(t.w00, a);
@@ -165,12 +222,13 @@ TVM_HD float4 vm_slice_bwd(const tvm_field_desc& f, const float4* __restrict__ P
     const float4 up_ln = f4_mul(up, ln);        // d/d(plane value)
     const float4 up_pl = f4_mul(up, pl);        // d/d(line value)
     if (SCATTER) {
-        float4* gpb = gP + t.pbase + j;
-        float4* glb = gL + t.lbase + j;
+        float4* gpb = gP + (t.pbase + (unsigned)j);
+        float4* gpb1 = gP + (t.pbase + t.prow + (unsigned)j);
+        float4* glb = gL + (t.lbase + (unsigned)j);
         TVM_RED4(gpb, f4_scale(t.w00, up_ln));
         TVM_RED4(gpb + C4, f4_scale(t.w01, up_ln));
-        TVM_RED4(gpb + t.prow, f4_scale(t.w10, up_ln));
-        TVM_RED4(gpb + t.prow + C4, f4_scale(t.w11, up_ln));
+        TVM_RED4(gpb1, f4_scale(t.w10, up_ln));
+        TVM_RED4(gpb1 + C4, f4_scale(t.w11, up_ln));
         TVM_RED4(glb, f4_scale(t.lw0, up_pl));
         TVM_RED4(glb + C4, f4_scale(t.lw1, up_pl));
     }

@@ -3,7 +3,8 @@
 The reference slices the rays into `chunk`-sized pieces because its forward materialises
 [chunk, S, 27] temporaries (459 MB at 4096 x 1036).  The fused kernels keep per-ray state in
 registers, so the eval path launches over as many rays as the caller hands over (capped by
-`tensorf.max_launch_rays`), double-buffering the host->device copies of CPU-resident rays.
+`tensorf.max_launch_rays`); CPU-resident rays are pipelined in slices (H2D copy stream + two alternating
+compute streams, `tensorf.host_ray_slices`, 0 = auto).
 `chunk` is honoured only where results could depend on it (the autograd / is_train path).
 """
 from __future__ import annotations
@@ -34,42 +35,56 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
     rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
     depth = torch.empty((n,), dtype=torch.float32, device=dev)
     on_host = not rays.is_cuda
-    n_slices = int(getattr(tensorf, "host_ray_slices", 1))
-    if on_host and n_slices > 1:
-        # host-resident rays: the H2D copy of slice k+1 hides behind the kernels of slice k
-        step = min(step, max(1 << 16, -(-n // n_slices)))
-    copy_stream = _copy_stream(dev) if on_host and n > step else None
+    if on_host and n > 0:
+        # host-resident rays are cut into slices: the H2D copy of slice k+1 runs on a copy stream behind the kernels
+        # of slice k, and consecutive slices launch on two alternating compute streams so the straggler CTAs at the
+        # end of one slice's march overlap the start of the next instead of leaving SMs idle
+        n_slices = int(getattr(tensorf, "host_ray_slices", 0)) or (4 if n >= (1 << 18) else 1)
+        step = min(step, max(1 << 14, -(-n // n_slices)))
     main = torch.cuda.current_stream(dev)
+    if not on_host or n <= step:
+        for a in range(0, n, step):
+            cur = rays[a:a + step]
+            if on_host:
+                cur = cur.to(dev, non_blocking=True)
+            tensorf.render_eval(cur, N_samples=N_samples, white_bg=bool(white_bg), bg_color=bg_color,
+                                out_rgb=rgb[a:a + step], out_depth=depth[a:a + step])
+        return rgb, None, depth, None, None
 
-    def fetch(a):
-        piece = rays[a:a + step]
-        if not on_host:
-            return piece, None
-        if copy_stream is None:
-            return piece.to(dev, non_blocking=True), None
+    copy_stream, compute = _side_streams(dev)
+    tensorf.field_desc()                       # (re)pack parameter shadows on the caller's stream before forking
+    tensorf._bg(bg_color, bool(white_bg), dev)  # ... and create the cached background constant there too
+    fork = torch.cuda.Event()
+    fork.record(main)
+    copy_stream.wait_event(fork)
+    done = []
+    for k, a in enumerate(range(0, n, step)):
         with torch.cuda.stream(copy_stream):
-            t = piece.to(dev, non_blocking=True)
+            cur = rays[a:a + step].to(dev, non_blocking=True)
+            arrived = torch.cuda.Event()
+            arrived.record(copy_stream)
+        cs = compute[k % len(compute)]
+        if k < len(compute):
+            cs.wait_event(fork)
+        cs.wait_event(arrived)
+        with torch.cuda.stream(cs):
+            cur.record_stream(cs)
+            tensorf.render_eval(cur, N_samples=N_samples, white_bg=bool(white_bg), bg_color=bg_color,
+                                out_rgb=rgb[a:a + step], out_depth=depth[a:a + step])
             ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return t, ev
-
-    nxt = fetch(0) if n > 0 else None
-    for a in range(0, n, step):
-        cur, ev = nxt
-        nxt = fetch(a + step) if a + step < n else None
-        if ev is not None:
-            main.wait_event(ev)
-            cur.record_stream(main)
-        tensorf.render_eval(cur, N_samples=N_samples, white_bg=bool(white_bg), bg_color=bg_color,
-                            out_rgb=rgb[a:a + step], out_depth=depth[a:a + step])
+            ev.record(cs)
+        done.append(ev)
+    for ev in done[-len(compute):]:
+        main.wait_event(ev)
     return rgb, None, depth, None, None
 
 
 _streams = {}
 
 
-def _copy_stream(dev):
+def _side_streams(dev):
+    """(copy stream, [two compute streams]) of a device, created once."""
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
     if key not in _streams:
-        _streams[key] = torch.cuda.Stream(device=dev)
+        _streams[key] = (torch.cuda.Stream(device=dev), [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)])
     return _streams[key]

@@ -14,9 +14,9 @@ rays = fx.config2_rays().pin_memory()
 n = rays.shape[0]
 out = torch.empty((n, 4)).pin_memory()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for prec in ("fp32", "bf16"):
+for prec in ("auto",):
     m.mlp_precision = prec
-    for slices in (1, 2, 3, 4, 8):
+    for slices in (1, 2, 4, 6, 8, 16):
         m.host_ray_slices = slices
         def step():
             rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(rays, m, white_bg=True, device=dev)

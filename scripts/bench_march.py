@@ -13,11 +13,18 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--no-early", action="store_true")
 ap.add_argument("--tag", default=os.environ.get("TVM_B200_LIB", "default"))
+ap.add_argument("--tile", default="", help="WxH: reorder the 800x800 rays so 32 consecutive rays form a WxH pixel tile (locality probe)")
+ap.add_argument("--march-only", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 fld = fx.make_field([300] * 3, density_shift=0.0)
 m = H.module_from_field(fld, dev)
-rays = fx.config2_rays().to(dev)
+rays = fx.config2_rays()
+if a.tile:
+    tw, th = (int(v) for v in a.tile.split("x"))
+    img = rays.view(800, 800, -1)
+    rays = img.view(800 // th, th, 800 // tw, tw, -1).permute(0, 2, 1, 3, 4).reshape(-1, img.shape[-1]).contiguous()
+rays = rays.to(dev)
 n, S = rays.shape[0], m.nSamples
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 lib = _lib.load()
@@ -51,6 +58,9 @@ d2, keep2 = m.field_desc()
 def shade_tc():
     _lib.check(lib.tvm_shade_fwd(C.byref(d2), _lib.ptr(rays), n, rays.shape[1], _lib.ptr(bg), _lib.F_MLP_BF16, _lib.ptr(rgb),
                                  _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(ws), ws.numel(), st), "shade_tc")
+if a.march_only:
+    print(json.dumps({"tag": a.tag, "tile": a.tile, "march_ms": round(timeit(march), 4)}))
+    sys.exit(0)
 march()
 ref_rgb = torch.empty_like(rgb); shade(); ref_rgb.copy_(rgb)
 tc_ms = round(timeit(shade_tc), 4)

@@ -7,7 +7,7 @@ from iffnerf_b200 import build
 
 out_dir = os.path.join(ROOT, "iffnerf_b200", "variants")
 os.makedirs(out_dir, exist_ok=True)
-combos = [(4, 32, 4), (4, 32, 5), (4, 16, 4), (4, 64, 4), (8, 32, 2), (2, 32, 8), (4, 8, 4)]
+combos = [(4, 32, 3), (4, 32, 4), (8, 32, 2), (8, 64, 2)]
 for warps, rpc, mb in combos:
     tag = f"w{warps}_r{rpc}_b{mb}"
     out = os.path.join(out_dir, f"libtvm_{tag}.so")

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python scripts/bench_e2e.py > gpurun_out/e2e_sweep.jsonl 2> gpurun_out/e2e_sweep.err; cat gpurun_out/e2e_sweep.jsonl; tail -3 gpurun_out/e2e_sweep.err
+timeout 300 python scripts/bench_l1_gather.py > gpurun_out/l1_gather.jsonl 2> gpurun_out/l1_gather.err; cat gpurun_out/l1_gather.jsonl; tail -3 gpurun_out/l1_gather.err
+M=smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed,gpu__time_duration.sum,l1tex__t_sector_hit_rate.pct,l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed,l1tex__data_pipe_lsu_wavefronts_mem_lgds.sum,l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum
+ncu --metrics $M --clock-control none -k regex:gather_bench -c 12 --csv --log-file gpurun_out/ncu_l1_gather.csv python scripts/bench_l1_gather.py > /dev/null 2>&1
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
