@@ -368,27 +368,29 @@ def run_ours(args, rank, world, local_rank):
     has_occ = model.alphaMask is not None
     alg_bytes = 44 * n + (32 * v0 if has_occ else 0) + 1152 * v + 3456 * a
 
-    # measured L2 random-gather ceiling over the resident factor set: 64 B and 192 B granules
+    # measured gather ceilings for the kernel's access shape — quads of lanes, LDG.128, random 64-B
+    # pieces: over the resident factor set (L2 -> SM ceiling) and over an L1-resident 64 KB set (L1 data-pipe ceiling)
     gather_peak = {}
     if rank == 0:
         import ctypes as C
         lib = _lib.load()
         pf = model.packed_factors()
         sink = torch.zeros(4, device=dev)
-        for gran in (64, 192):
+        for name, nbytes, gran in (("l2_resident_64B_gbs", pf.numel() * 4, 64), ("l2_resident_192B_gbs", pf.numel() * 4, 192),
+                                   ("l1_resident_64B_gbs", 64 << 10, 64)):
             moved = C.c_ulonglong(0)
             best = 0.0
             for rep in range(4):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                _lib.check(lib.tvm_gather_microbench(_lib.ptr(pf), pf.numel() * 4, gran, 64, _lib.ptr(sink),
+                _lib.check(lib.tvm_gather_microbench(_lib.ptr(pf), nbytes // gran * gran, gran, 128, _lib.ptr(sink),
                                                      C.byref(moved), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
                            "tvm_gather_microbench")
                 e1.record()
                 torch.cuda.synchronize(dev)
                 if rep > 0:
                     best = max(best, moved.value / (e0.elapsed_time(e1) / 1e3) / 1e9)
-            gather_peak[f"l2_random_{gran}B_gbs"] = best
+            gather_peak[name] = best
 
     dp = dp_train_step(model, dev, fx, world, rank) if world > 1 else None
 
@@ -426,10 +428,16 @@ def run_ours(args, rank, world, local_rank):
                              "units_per_launch": {"rays": n, "occupancy_tests": v0, "sigma_samples": v,
                                                   "app_samples": a},
                              "measured_gather_ceilings": gather_peak,
-                             "frac_of_l2_gather_64B": (achieved / gather_peak["l2_random_64B_gbs"]
-                                                       if gather_peak.get("l2_random_64B_gbs") else None),
-                             "note": "factor set (69 MB) is L2-resident and mostly L1-hit: achieved algorithmic "
-                                     "bytes/s exceeds the HBM copy peak; DRAM traffic per launch is in `traffic`"},
+                             "frac_of_l2_gather": (achieved / gather_peak["l2_resident_64B_gbs"]
+                                                   if gather_peak.get("l2_resident_64B_gbs") else None),
+                             "frac_of_l1_gather": (achieved / gather_peak["l1_resident_64B_gbs"]
+                                                   if gather_peak.get("l1_resident_64B_gbs") else None),
+                             "l1_data_pipe_peak_gbs": 148 * 128 * (clk.result.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
+                             "note": "factor set (69 MB) is L2-resident and 87 % L1-hit, so the binding resource is the "
+                                     "SM's L1 data pipe (128 B/clk/SM of register fill), not HBM: the algorithmic rate "
+                                     "exceeds the HBM copy peak (frac > 1 by construction); `frac_of_l1_gather` is the "
+                                     "fraction of the measured L1-resident quad-gather ceiling; DRAM traffic per "
+                                     "launch is in `traffic`"},
                 "fp32_simt_mlp_mode": {"value": world * n * K / (ms_dev_simt / 1e3), "unit": UNIT,
                                        "ms_per_step": ms_dev_simt / K,
                                        "note": "shade_fwd_kernel (FFMA) instead of the tensor-core kernel"},

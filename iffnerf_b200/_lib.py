@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_B200_LIB lets the tuning scripts load a differently-compiled build of the SAME sources
 LIB_PATH = os.environ.get("TVM_B200_LIB") or os.path.join(_HERE, "libtvm_b200.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 F_EARLY_TERM = 1 << 0
 F_MLP_BF16 = 1 << 1
@@ -40,6 +40,16 @@ class FieldDesc(C.Structure):
         ("occ_cells", C.c_void_p), ("occ_dims", _i3), ("occ_lo", _f3), ("occ_inv", _f3),
         ("occ_coarse", C.c_void_p), ("occ_cdims", _i3),
         ("factors", C.c_void_p), ("basis", C.c_void_p), ("mlp", C.c_void_p), ("mlp_tc", C.c_void_p), ("mlp_tc3", C.c_void_p),
+    ]
+
+
+class RefHead(C.Structure):
+    """Mirror of `tvm_ref_head` (include/tvm_b200.h)."""
+    _fields_ = [
+        ("params", C.c_void_p), ("in_c", C.c_int32), ("feature_c", C.c_int32), ("n_pairs", C.c_int32),
+        ("l_max", C.c_int32), ("m", C.c_int32 * 32), ("l", C.c_int32 * 32),
+        ("rgb_premultiplier", C.c_float), ("rgb_bias", C.c_float), ("rgb_padding", C.c_float),
+        ("diffuse_shift", C.c_float), ("rough_shift", C.c_float),
     ]
 
 
@@ -78,6 +88,14 @@ _SIGNATURES = {
     "tvm_mlp_grad_floats": (C.c_size_t, [C.POINTER(FieldDesc)]),
     "tvm_unpack_mlp_grads": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "tvm_point_density": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, C.c_float, _P, _P]),
+    "tvm_ref_head_floats": (C.c_size_t, [C.POINTER(RefHead)]),
+    "tvm_ref_head_layout": (C.c_int, [C.POINTER(RefHead), C.POINTER(C.c_int32)]),
+    "tvm_shade_ref_fwd": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(RefHead), _P, C.c_int64, C.c_int, _P, _P, _P, _P, _P,
+                                    C.c_size_t, _P]),
+    "tvm_point_appfeature": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, _P, _P]),
+    "tvm_pixel_rays_fwd": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _P, _P, C.c_int, C.c_int64, C.c_int, _P, _P]),
+    "tvm_pixel_rays_bwd": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _P, _P, C.c_int, C.c_int64, C.c_int, _P, C.c_int,
+                                     _P, _P]),
     "tvm_gather_microbench": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, _P, C.POINTER(C.c_ulonglong), _P]),
     "tvm_workspace_layout": (C.c_int, [C.POINTER(FieldDesc), C.c_int64] + [C.POINTER(C.c_size_t)] * 6),
 }

@@ -1,33 +1,35 @@
-// microbench.cu — measured ceilings for the gather stages ("fraction of a MEASURED L2 gather
-// peak: random 64 B and 192 B granule reads over the resident factor set").
-// Each quad (4 lanes x 16 B) fetches pseudo-random granules of `granule_bytes` (64 or 192) from a buffer with the
-// size of the packed factor set, which stays L2-resident (69 MB < 126 MB L2) but defeats L1 (random, 28 MB of L1
-// in total).  The result is the L2->SM random-gather bandwidth the march kernel would be bound by if it had no L1
-// reuse at all; its achieved algorithmic rate is reported against it next to the HBM figure.
+// microbench.cu — measured ceilings for the gather stages ("fraction of a MEASURED gather peak:
+// random 64 B and 192 B granule reads over the resident factor set").
+// Each quad (4 lanes x 16 B, LDG.128 like the march kernel) fetches pseudo-random granules of `granule_bytes`
+// (64 = density texel, 192 = appearance texel) from `bytes` of `buf`:
+//   * bytes = the packed factor set (69 MB): L2-resident, random => defeats L1: the L2 -> SM gather ceiling;
+//   * bytes = a few KB: every SM re-reads an L1-resident set: the L1 data-pipe ceiling for this access shape
+//     (8 different texels per warp request, ~6 wavefronts per LDG.128 including bank conflicts).
+// The loop is load-dense (about 8 instructions per LDG.128: 32-bit LCG, multiply-high range reduction, one
+// IMAD.WIDE address, 4 FADDs) and keeps 8 independent loads in flight per lane, so the memory pipe, not the
+// issue slots, is what saturates.
 #include "tvm_common.cuh"
 
 namespace {
 
-__global__ void __launch_bounds__(256) gather_bench_kernel(const float4* __restrict__ buf, unsigned long long n_granules,
+__global__ void __launch_bounds__(256) gather_bench_kernel(const float4* __restrict__ buf, unsigned n_granules,
                                                            int f4_per_granule, int iters, float* __restrict__ sink) {
-    const int lane = threadIdx.x & 31, sub = lane & 3;
-    unsigned long long quad = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    unsigned long long state = quad * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    const unsigned sub = threadIdx.x & 3;
+    const unsigned quad = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    unsigned state = quad * 0x9E3779B9u + 0x1234567u;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int it = 0; it < iters; ++it) {
-        // 4 independent granules per iteration (memory-level parallelism like the kernel's 4 bilinear corners)
-        unsigned long long g[4];
+        float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            state = state * 6364136223846793005ull + 1442695040888963407ull;
-            g[u] = (state >> 20) % n_granules;
+        for (int u = 0; u < 8; ++u) {
+            state = state * 1664525u + 1013904223u;
+            const unsigned g = __umulhi(state, n_granules);
+            // one slice per lane per granule: a 64-B granule is read once by the quad, a 192-B granule in 3 rounds
+            const unsigned j = sub + 4u * ((unsigned)u % (unsigned)(f4_per_granule >> 2));
+            v[u] = __ldg(buf + (g * (unsigned)f4_per_granule + j));
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            for (int j = sub; j < f4_per_granule; j += 4) {
-                const float4 v = __ldg(buf + g[u] * f4_per_granule + j);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
+        for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
     }
     if (acc.x + acc.y + acc.z + acc.w == 123.456f) sink[0] = acc.x;      // keep the loads alive
 }
@@ -39,11 +41,13 @@ extern "C" int tvm_gather_microbench(const void* buf, size_t bytes, int granule_
                                      unsigned long long* bytes_moved, void* stream) {
     if (!buf || !sink) return TVM_E_NULL;
     if (granule_bytes % 16 || granule_bytes <= 0 || bytes < (size_t)granule_bytes) return TVM_E_SHAPE;
-    const unsigned long long n_granules = bytes / granule_bytes;
+    if (granule_bytes % 64 || bytes / granule_bytes > 0xffffffffull / (granule_bytes / 16)) return TVM_E_SHAPE;
+    const unsigned n_granules = (unsigned)(bytes / granule_bytes);
     const int ctas = TVM_SM_COUNT * 16, threads = 256;
     gather_bench_kernel<<<ctas, threads, 0, (cudaStream_t)stream>>>((const float4*)buf, n_granules, granule_bytes / 16,
                                                                    iters, sink);
     TVM_LAUNCH_CHECK();
-    if (bytes_moved) *bytes_moved = (unsigned long long)ctas * threads / 4 * iters * 4ull * granule_bytes;
+    // every lane requests 16 B per load, 8 loads per iteration
+    if (bytes_moved) *bytes_moved = (unsigned long long)ctas * threads * (unsigned long long)iters * 8ull * 16ull;
     return 0;
 }

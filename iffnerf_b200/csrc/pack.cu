@@ -15,7 +15,12 @@ namespace {
 constexpr int TP = 32;   // pixels per tile
 
 // The 12 factor tensors are converted by ONE launch: blockIdx.y selects the tensor, blockIdx.x the pixel tile.
-struct TransposeJob { const float* src; float* dst; int C; long long P; };
+// P pixels in rows of W; the channel-last side pads each row to `pitch` texels (tvm_plane_pitch; lines: W = pitch = P)
+struct TransposeJob { const float* src; float* dst; int C; long long P; int W; int pitch; };
+__device__ __forceinline__ long long padded_pixel(long long p, int W, int pitch) {
+    const long long y = p / W;
+    return y * pitch + (p - y * W);
+}
 struct TransposeJobs { TransposeJob j[12]; int accumulate; };
 
 // src [C][P] -> dst [P][C]
@@ -34,9 +39,10 @@ __global__ void __launch_bounds__(256) cp_to_pc_kernel(const __grid_constant__ T
     }
     __syncthreads();
     const long long lim = min((long long)TP, P - p0) * C;
+    const int W = jobs.j[blockIdx.y].W, pitch = jobs.j[blockIdx.y].pitch;
     for (int i = threadIdx.x; i < lim; i += 256) {
         const int p = i / C, c = i - p * C;
-        dst[p0 * C + i] = tile[c][p];
+        dst[padded_pixel(p0 + p, W, pitch) * C + c] = tile[c][p];
     }
 }
 
@@ -51,9 +57,10 @@ __global__ void __launch_bounds__(256) pc_to_cp_kernel(const __grid_constant__ T
     const long long p0 = (long long)blockIdx.x * TP;
     if (p0 >= P) return;
     const long long lim = min((long long)TP, P - p0) * C;
+    const int W = jobs.j[blockIdx.y].W, pitch = jobs.j[blockIdx.y].pitch;
     for (int i = threadIdx.x; i < lim; i += 256) {
         const int p = i / C, c = i - p * C;
-        tile[c][p] = __ldg(src + p0 * C + i);
+        tile[c][p] = __ldg(src + padded_pixel(p0 + p, W, pitch) * C + c);
     }
     __syncthreads();
     const int px = threadIdx.x & 31, cy = threadIdx.x >> 5;
@@ -126,16 +133,17 @@ __global__ void copy_small_kernel(const float* __restrict__ src, float* __restri
     else if (!accumulate) dst[i] = 0.f;
 }
 
-struct FactorView { long long off; int C; long long P; };
+struct FactorView { long long off; int C; long long P; int W; int pitch; };
 
 void factor_views(const tvm_field_desc* d, FactorView planes[6], FactorView lines[6]) {
     for (int k = 0; k < 3; ++k) {
         const long long hw = (long long)d->grid[TVM_M0(k)] * d->grid[TVM_M1(k)];
         const long long l = d->grid[TVM_V(k)];
-        planes[k] = {d->dplane_off[k], d->n_sigma[k], hw};
-        planes[3 + k] = {d->aplane_off[k], d->n_app[k], hw};
-        lines[k] = {d->dline_off[k], d->n_sigma[k], l};
-        lines[3 + k] = {d->aline_off[k], d->n_app[k], l};
+        const int W = d->grid[TVM_M0(k)], pitch = tvm_plane_pitch(W);
+        planes[k] = {d->dplane_off[k], d->n_sigma[k], hw, W, pitch};
+        planes[3 + k] = {d->aplane_off[k], d->n_app[k], hw, W, pitch};
+        lines[k] = {d->dline_off[k], d->n_sigma[k], l, (int)l, (int)l};
+        lines[3 + k] = {d->aline_off[k], d->n_app[k], l, (int)l, (int)l};
     }
 }
 
@@ -165,8 +173,8 @@ extern "C" int tvm_pack_factors(const tvm_field_desc* desc, const float* const p
     long long maxP = 0;
     for (int i = 0; i < 6; ++i) {
         if (!planes[i] || !lines[i]) return TVM_E_NULL;
-        jobs.j[i] = {planes[i], packed + pv[i].off, pv[i].C, pv[i].P};
-        jobs.j[6 + i] = {lines[i], packed + lv[i].off, lv[i].C, lv[i].P};
+        jobs.j[i] = {planes[i], packed + pv[i].off, pv[i].C, pv[i].P, pv[i].W, pv[i].pitch};
+        jobs.j[6 + i] = {lines[i], packed + lv[i].off, lv[i].C, lv[i].P, lv[i].W, lv[i].pitch};
         maxP = max(maxP, max(pv[i].P, lv[i].P));
     }
     cp_to_pc_kernel<<<dim3((unsigned)((maxP + TP - 1) / TP), 12), 256, 0, (cudaStream_t)stream>>>(jobs);
@@ -185,8 +193,8 @@ extern "C" int tvm_unpack_factor_grads(const tvm_field_desc* desc, const float* 
     jobs.accumulate = accumulate;
     long long maxP = 0;
     for (int i = 0; i < 6; ++i) {
-        jobs.j[i] = {packed_grad + pv[i].off, planes[i], pv[i].C, pv[i].P};
-        jobs.j[6 + i] = {packed_grad + lv[i].off, lines[i], lv[i].C, lv[i].P};
+        jobs.j[i] = {packed_grad + pv[i].off, planes[i], pv[i].C, pv[i].P, pv[i].W, pv[i].pitch};
+        jobs.j[6 + i] = {packed_grad + lv[i].off, lines[i], lv[i].C, lv[i].P, lv[i].W, lv[i].pitch};
         maxP = max(maxP, max(pv[i].P, lv[i].P));
     }
     pc_to_cp_kernel<<<dim3((unsigned)((maxP + TP - 1) / TP), 12), 256, 0, (cudaStream_t)stream>>>(jobs);

@@ -82,7 +82,7 @@ TVM_HD TvmSections tvm_sections(const tvm_field_desc& f) {
 // Offsets are UNSIGNED 32-bit float4 indices so an address is one IMAD.WIDE.U32 off the section pointer
 // (signed ints cost a sign-extension + LEA pair per load in SASS).
 struct PlaneTaps {
-    unsigned pbase, prow, lbase;  // plane: (y0*W+x0)*C4, W*C4 ; line: l0*C4
+    unsigned pbase, prow, lbase;  // plane: (y0*pitch+x0)*C4, pitch*C4 ; line: l0*C4
     float w00, w01, w10, w11;     // bilinear weights (ATen: nw, ne, sw, se)
     float lw0, lw1;
 };
@@ -90,7 +90,7 @@ TVM_HD PlaneTaps make_taps(const tvm_field_desc& f, const SampleTaps& s, int k, 
     const AxisTap& tx = s.a[TVM_M0(k)];
     const AxisTap& ty = s.a[TVM_M1(k)];
     const AxisTap& tl = s.a[TVM_V(k)];
-    const unsigned W = (unsigned)f.grid[TVM_M0(k)];
+    const unsigned W = (unsigned)tvm_plane_pitch(f.grid[TVM_M0(k)]);     // row pitch in texels
     PlaneTaps p;
     p.pbase = ((unsigned)ty.i0 * W + (unsigned)tx.i0) * (unsigned)C4;
     p.prow = W * (unsigned)C4;

@@ -32,6 +32,12 @@ TVM_HD float rn_mul(float a, float b) { volatile float r = a * b; return r; }
 TVM_HD float rn_div(float a, float b) { volatile float r = a / b; return r; }
 #endif
 
+// Row pitch (in texels) of a packed plane whose rows hold W texels: W rounded up to odd.  Texels are 64 B (density)
+// or 192 B (appearance), so an odd pitch puts vertically adjacent texels into different halves of the 128-B L1 line
+// span (bank groups); with an even pitch (300) the two quads of an 8-lane wavefront group that fetch samples one row
+// apart collide on the same banks and the request takes an extra wavefront (measured 4.68 instead of 4 per LDG.128).
+TVM_HD int tvm_plane_pitch(int W) { return W | 1; }
+
 // matMode / vecMode of the VM decomposition (models/tensorBase.py:311-312)
 #define TVM_M0(k) ((k) == 2 ? 1 : 0)
 #define TVM_M1(k) ((k) == 0 ? 1 : 2)

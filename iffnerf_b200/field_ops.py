@@ -74,6 +74,21 @@ class FieldOpsMixin:
         """models/tensorBase.py:756-773: 1 - exp(-sigma*length) at world points, gated by the alphaMask."""
         return self._point_density(xyz_locs, 1, float(length))
 
+    @torch.no_grad()
+    def compute_appfeature(self, xyz_sampled):
+        """models/tensoRF.py:237-256: basis_mat(app_plane (x) app_line) at NORMALISED coordinates [M,3] -> [M, app_dim]
+        (inference only; pose_estimation/sampling.py:535-541 feeds it to Ref.compute_normals)."""
+        from .tensorf import _stream
+        if not xyz_sampled.is_cuda:
+            raise _lib.TvmError("point queries run on CUDA tensors only (no CPU path)")
+        shape = xyz_sampled.shape[:-1]
+        p = xyz_sampled.detach().reshape(-1, 3).float().contiguous()
+        out = torch.empty((p.shape[0], self.app_dim), device=p.device)
+        d, keep = self.field_desc()
+        _lib.check(_lib.load().tvm_point_appfeature(C.byref(d), _lib.ptr(p), p.shape[0], _lib.ptr(out),
+                                                    _stream(p.device)), "tvm_point_appfeature")
+        return out.view(*shape, self.app_dim)
+
     def feature2density(self, density_features):
         if self.fea2denseAct == "softplus":
             return F.softplus(density_features + self.density_shift)

@@ -116,6 +116,7 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
 
     # launch-size cap for the chunk-free eval path (rays per kernel launch)
     max_launch_rays = 1 << 20
+    ref_kernel = True            # `Ref` head, eval: fused tail kernel (False: the torch-op tail, kept for cross-checks)
     # transmittance below which an eval ray stops marching (error on rgb/acc <= this value)
     early_term_eps = 1e-5
     # shading-stage arithmetic on the no-grad path:
@@ -266,7 +267,8 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         return (list(self.density_plane) + list(self.app_plane), list(self.density_line) + list(self.app_line))
 
     def _factor_layout(self):
-        """Float offsets of the 12 packed sections (each 64-float aligned)."""
+        """Float offsets of the 12 packed sections (each 64-float aligned).  Plane rows are padded to an odd number of
+        texels (tvm_plane_pitch in csrc/tvm_math.cuh: L1 bank spreading of vertically adjacent texels)."""
         g = self._host["grid"]
         off, out = 0, {"dplane": [], "dline": [], "aplane": [], "aline": []}
 
@@ -277,11 +279,11 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
             return start
         for k in range(3):
             m0, m1 = MAT_MODE[k]
-            out["dplane"].append(take(g[m0] * g[m1] * self.density_n_comp[k]))
+            out["dplane"].append(take((g[m0] | 1) * g[m1] * self.density_n_comp[k]))   # rows padded to an odd pitch
             out["dline"].append(take(g[VEC_MODE[k]] * self.density_n_comp[k]))
         for k in range(3):
             m0, m1 = MAT_MODE[k]
-            out["aplane"].append(take(g[m0] * g[m1] * self.app_n_comp[k]))
+            out["aplane"].append(take((g[m0] | 1) * g[m1] * self.app_n_comp[k]))
             out["aline"].append(take(g[VEC_MODE[k]] * self.app_n_comp[k]))
         out["total"] = off
         return out
@@ -395,6 +397,53 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
                                _lib.ptr(self._mlp_tc), _stream(dev)), "tvm_pack_mlp_tc")
             self._mlp_tc_key = key
         return self._mlp_tc
+
+    def packed_ref_head(self):
+        """`tvm_ref_head` descriptor + packed parameter buffer of the `Ref` head for tvm_shade_ref_fwd (layout in
+        include/tvm_b200.h); None when the head's configuration has no fused kernel (the torch tail is used)."""
+        rm = self.renderModule
+        if not getattr(rm, "predicted_normals", False) or self.app_dim != 27:
+            return None
+        lins = {"normal": rm.normal_mlp[0], "tint": rm.tint_color_mlp[0], "rough": rm.roughness_mlp[0],
+                "diffuse": rm.diffuse_color_mlp[0], "bott": rm.bottleneck_mlp, "spec": rm.specular_mlp[0]}
+        ps = [p for l in lins.values() for p in (l.weight, l.bias)] + [rm.dir_enc_fn.mat]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_ref_key", None) != key:
+            dev = ps[0].device
+            h = _lib.RefHead()
+            ml = rm.dir_enc_fn.ml_array.detach().cpu().long()
+            h.in_c, h.feature_c = self.app_dim, lins["bott"].out_features
+            h.n_pairs, h.l_max = int(ml.shape[1]), int(rm.dir_enc_fn.mat.shape[0]) - 1
+            if h.n_pairs > 32 or lins["spec"].in_features != h.feature_c + 2 * h.n_pairs + 1:
+                return None
+            h.m[:h.n_pairs] = ml[0].tolist()
+            h.l[:h.n_pairs] = ml[1].tolist()
+            pre, bias = 1.0, 0.0
+            for mod in rm.specular_mlp[1:]:
+                if type(mod).__name__ == "_Scale":
+                    pre = float(mod.value)
+                elif type(mod).__name__ == "_Shift":
+                    bias = float(mod.value)
+            h.rgb_premultiplier, h.rgb_bias, h.rgb_padding = pre, bias, float(rm.rgb_padding)
+            h.diffuse_shift, h.rough_shift = float(rm.diffuse_color_mlp[1].value), float(rm.roughness_mlp[1].value)
+            lib = _lib.load()
+            offs = (C.c_int32 * 8)()
+            _lib.check(lib.tvm_ref_head_layout(C.byref(h), offs), "tvm_ref_head_layout")
+            small_w, bott_w, small_b, bott_b, spec_w, spec_b, ide, in4 = list(offs)
+            buf = torch.zeros(int(lib.tvm_ref_head_floats(C.byref(h))), dtype=torch.float32, device=dev)
+            small = torch.cat([lins[k].weight.detach() for k in ("normal", "tint", "rough", "diffuse")], 0)    # [10, in_c]
+            buf[small_w:small_w + 10 * in4].view(10, in4)[:, :h.in_c] = small
+            buf[bott_w:bott_w + h.feature_c * in4].view(h.feature_c, in4)[:, :h.in_c] = lins["bott"].weight.detach()
+            buf[small_b:small_b + 10] = torch.cat([lins[k].bias.detach() for k in ("normal", "tint", "rough", "diffuse")])
+            buf[bott_b:bott_b + h.feature_c] = lins["bott"].bias.detach()
+            sw = lins["spec"].weight.detach().reshape(-1)
+            buf[spec_w:spec_w + sw.numel()] = sw
+            buf[spec_b:spec_b + 3] = lins["spec"].bias.detach()
+            mat = rm.dir_enc_fn.mat.detach().float().reshape(-1)
+            buf[ide:ide + mat.numel()] = mat
+            h.params = buf.data_ptr()
+            self._ref_key, self._ref_head = key, (h, buf)
+        return self._ref_head
 
     def field_desc(self, need_params=True):
         """Full descriptor with device pointers; keeps the referenced tensors alive via the returned tuple."""
@@ -518,7 +567,14 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
             if keep_workspace:
                 out["workspace"] = views
             if not self.native_shade and n > 0:
-                self._torch_shade_tail(rays, views, bg, out)
+                head = self.packed_ref_head() if self.ref_kernel else None
+                if head is not None:        # fused `Ref` tail (csrc/shade_ref.cu)
+                    _lib.check(lib.tvm_shade_ref_fwd(C.byref(d), C.byref(head[0]), _lib.ptr(rays), n, rays.shape[1],
+                                                     _lib.ptr(bg), _lib.ptr(out["rgb_map"]), _lib.ptr(out["depth_map"]),
+                                                     _lib.ptr(out["acc_map"]), _lib.ptr(ws), ws.numel(), _stream(dev)),
+                               "tvm_shade_ref_fwd")
+                else:
+                    self._torch_shade_tail(rays, views, bg, out)
         return out
 
     def _torch_shade_tail(self, rays, views, bg, out):

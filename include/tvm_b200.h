@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 8
+#define TVM_ABI_VERSION 9
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define TVM_E_NULL        (-1)   /* required pointer is NULL                      */
@@ -50,9 +50,10 @@ extern "C" {
  *
  * Packed factor buffer (`factors`, fp32, channel-last so one texel is one contiguous
  * run of C floats): for k in 0..2
- *     density plane k : [G[m1]][G[m0]][n_sigma[k]]   at float offset dplane_off[k]
+ *     density plane k : [G[m1]][pitch][n_sigma[k]]   at float offset dplane_off[k]; pitch = G[m0] | 1 (rows padded
+ *                       to an odd texel count so vertically adjacent texels use different L1 bank halves)
  *     density line  k : [G[v]][n_sigma[k]]           at dline_off[k]
- *     app plane k     : [G[m1]][G[m0]][n_app[k]]     at aplane_off[k]
+ *     app plane k     : [G[m1]][pitch][n_app[k]]     at aplane_off[k]
  *     app line  k     : [G[v]][n_app[k]]             at aline_off[k]
  * with matMode (m0,m1) = (0,1),(0,2),(1,2) and vecMode v = 2,1,0 (tensorBase.py:311-312).
  * Channel counts must be multiples of 4, n_sigma[k] <= 16, n_app[k] <= 48.
@@ -189,8 +190,59 @@ int tvm_unpack_mlp_grads(const tvm_field_desc* desc, const float* packed_grad, f
 int tvm_point_density(const tvm_field_desc* desc, const float* points /* [n][3] */, int64_t n_points, int mode,
                       float length, float* out /* [n] */, void* stream);
 
-/* Measurement aid: random-granule gather over `bytes` of `buf` (64 B = density texel, 192 B = appearance texel);
- * the caller times the launch with CUDA events; *bytes_moved = bytes requested.  Not used by the render path. */
+/* `Ref` shading head (models/ref.py:48-155; what configs/lego.txt:25 / truck.txt:26 train with), eval forward.
+ * `params` is ONE device float buffer, rows of the in_c-input matrices padded to in4 = round_up(in_c, 4) floats:
+ *   [small_w]  10 x in4 : normal_mlp.0 (3 rows), tint_color_mlp.0 (3), roughness_mlp.0 (1), diffuse_color_mlp.0 (3)
+ *   [bott_w]   feature_c x in4 : bottleneck_mlp
+ *   [small_b]  10 biases in the same order (+2 pad)      [bott_b] feature_c biases
+ *   [spec_w]   3 x (feature_c + 2 n_pairs + 1) : specular_mlp.0 weight, torch layout   [spec_b] 3 (+1 pad)
+ *   [ide_mat]  (l_max + 1) x n_pairs : dir_enc_fn.mat (ref_utils.py:85-98)
+ * tvm_ref_head_layout() returns the seven float offsets (and in4) so the host packs without duplicating the rule. */
+typedef struct tvm_ref_head {
+    const float* params;
+    int32_t in_c;                /* app_dim (27)                                                        */
+    int32_t feature_c;           /* bottleneck width (128)                                              */
+    int32_t n_pairs;             /* (m, l) pairs of the integrated directional encoding (19 at deg 4)   */
+    int32_t l_max;               /* 2^(deg_view-1)                                                      */
+    int32_t m[32], l[32];        /* dir_enc_fn.ml_array rows                                            */
+    float   rgb_premultiplier, rgb_bias, rgb_padding;     /* ref.py:60-62, :84-92                       */
+    float   diffuse_shift;       /* -log(3)  (ref.py:69)                                                */
+    float   rough_shift;         /* -1       (ref.py:75)                                                */
+} tvm_ref_head;
+size_t tvm_ref_head_floats(const tvm_ref_head* head);
+int tvm_ref_head_layout(const tvm_ref_head* head, int32_t offs[8]);
+/* Per-ray tail with this head (tensorBase.py:886-908), reading the march-stage partials from ws like tvm_shade_fwd. */
+int tvm_shade_ref_fwd(const tvm_field_desc* desc, const tvm_ref_head* head, const float* rays, int64_t n_rays,
+                      int ray_stride, const float* bg /* device [3] */, float* rgb, float* depth, float* acc,
+                      const void* ws, size_t ws_bytes, void* stream);
+
+/* TensorVMSplit.compute_appfeature (tensoRF.py:237-256): appearance feature basis_mat(plane (x) line) at NORMALISED
+ * points [n][3] (zero-padded taps) -> out [n][app_dim].  Used by pose_estimation/sampling.py:535-541 (normals of the
+ * Ref head at surface samples). */
+int tvm_point_appfeature(const tvm_field_desc* desc, const float* points /* [n][3] */, int64_t n_points,
+                         float* out /* [n][app_dim] */, void* stream);
+
+/* Fused ray generation for the pixels a step renders, with the pose gradient.  Replaces
+ * get_ray_directions_Ks + get_rays (ray_utils.py:28-100) + the pixel indexing / F.normalize / cat of
+ * inerf/estimate_pose_inerf.py:96-99,149-164 (flags = 3) and of dataLoader/blender.py:69-72,105-114 (flags = 1).
+ *   c2w        device [P][pose_stride] row-major camera-to-world matrices (rows 0..2 of a [3|4][4]); pose_stride 12 or 16
+ *   kinv_host  HOST [9] = inverse intrinsics, row-major (torch.inverse(K), ray_utils.py:50)
+ *   pixels     device [n][2] int32 (x, y), or NULL: ray i is pixel (i % width, i / width) of a full image
+ *   pose_index device [n] int32 pose of each ray, or NULL (pose 0)
+ *   flags      bit 0: normalise the camera-space direction before rotating; bit 1: F.normalize the world direction
+ *   rays       device [n][7] = (origin, direction, radii)  (radii as ray_utils.py:90-98)
+ * tvm_pixel_rays_bwd ACCUMULATES d(rays) [n][g_stride >= 6] (column 6 = d(radii) when g_stride > 6) into
+ * g_c2w [P][3][4] (the autograd edge pose -> rays of estimate_pose_inerf.py:149-178). */
+int tvm_pixel_rays_fwd(const float* c2w, int pose_stride, const float* kinv_host, const int32_t* pixels,
+                       const int32_t* pose_index, int width, int64_t n, int flags, float* rays, void* stream);
+int tvm_pixel_rays_bwd(const float* c2w, int pose_stride, const float* kinv_host, const int32_t* pixels,
+                       const int32_t* pose_index, int width, int64_t n, int flags, const float* g_rays, int g_stride,
+                       float* g_c2w, void* stream);
+
+/* Measurement aid: quads of lanes gather random 64-B pieces (LDG.128 per lane, the march kernel's access shape) from
+ * `granule_bytes`-sized granules (64 = density texel, 192 = appearance texel) inside `bytes` of `buf`: the factor set
+ * size gives the L2 -> SM gather ceiling, a few KB the L1-resident one.  The caller times the launch with CUDA events;
+ * *bytes_moved = bytes requested by the lanes.  Not used by the render path. */
 int tvm_gather_microbench(const void* buf, size_t bytes, int granule_bytes, int iters, float* sink,
                           unsigned long long* bytes_moved, void* stream);
 

@@ -8,6 +8,7 @@ BIT-IDENTICAL, (4) stores the *reference's* outputs as the golden vectors.
 """
 import contextlib
 import io
+import math
 import os
 import sys
 import time
@@ -181,11 +182,13 @@ def point_case(R, name, fld, rays6):
         a_ref = m.compute_alpha(pts, length=m.stepSize.item())
         a_orc = orc.point_alpha(fld, pts, m.stepSize.item())
         f_ref = m.compute_densityfeature(m.normalize_coord(pts))
+        af_ref = m.compute_appfeature(m.normalize_coord(pts))
+        assert torch.equal(af_ref, orc.app_feature(fld, orc.normalize(fld, pts)))
     assert torch.equal(rgb, o["rgb_map"]) and torch.equal(alpha, o["alpha"]) and torch.equal(depth, o["depth_map"])
     assert z.shape == (1, 20) and torch.equal(z, o["z_vals"]) and torch.equal(a_ref, a_orc)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), rgb_map=rgb.numpy(), depth_map=depth.numpy(),
                         acc_map=acc.numpy(), alpha=alpha.numpy(), z_vals=z.numpy(), dists=dists.numpy(),
-                        points=pts.numpy(), point_alpha=a_ref.numpy(), point_feature=f_ref.numpy(),
+                        points=pts.numpy(), point_alpha=a_ref.numpy(), point_feature=f_ref.numpy(), point_appfeature=af_ref.numpy(),
                         param_checksum=fx.param_checksum(fld))
     print(f"[golden] {name}: rays={rays6.shape[0]} lit={(acc > 0).float().mean():.3f} ({time.time()-t:.1f}s) "
           f"oracle==reference bit-exact")
@@ -237,6 +240,41 @@ def ref_head_case(R, name):
           f"({time.time()-t:.1f}s) reference outputs stored")
 
 
+def raygen_case(R, name):
+    """rays of 1024 random pixels through a perturbed orbit pose, exactly as the iNeRF loop builds them
+    (inerf/estimate_pose_inerf.py:96-99,149-164), and the gradient of a fixed linear functional w.r.t. the pose."""
+    import torch.nn.functional as F
+    t = time.time()
+    H = W = 800
+    focal = 400.0 / math.tan(0.5 * 0.6911112)
+    K = torch.tensor([[[focal, 0.0, W / 2], [0.0, focal, H / 2], [0.0, 0.0, 1.0]]])
+    g = torch.Generator().manual_seed(55176280)
+    c2w = torch.cat([fx.orbit_pose(), torch.tensor([[0.0, 0.0, 0.0, 1.0]])], 0)
+    c2w = (c2w + 0.01 * torch.randn(4, 4, generator=g) * torch.tensor([[1.0], [1.0], [1.0], [0.0]])).contiguous()
+    pixels = torch.stack([torch.randint(0, W, (1024,), generator=g), torch.randint(0, H, (1024,), generator=g)], -1)
+    upstream = torch.randn(1024, 7, generator=g)
+    pose = c2w.clone().requires_grad_(True)
+    ori, dx, dy = R.get_ray_directions_Ks(H, W, K, use_pixel_centers=True)
+    directions = ori / torch.linalg.norm(ori, dim=-1, keepdim=True)
+    ro, rd, radii = R.get_rays(directions, pose, directions=ori, dx=dx, dy=dy, keepdim=True)
+    bx, by = pixels[:, 0], pixels[:, 1]
+    rays = torch.cat((ro[0, by, bx], F.normalize(rd[0, by, bx], p=2, dim=-1), radii[0, by, bx]), dim=-1)
+    (rays * upstream).sum().backward()
+    pose2 = c2w.clone().requires_grad_(True)
+    mine = orc.pixel_rays(K, pose2, pixels, H, W)
+    (mine * upstream).sum().backward()
+    assert torch.equal(mine, rays) and torch.equal(pose.grad, pose2.grad), f"{name}: oracle != reference"
+    with torch.no_grad():       # loader semantics (dataLoader/blender.py:105-114): no second normalisation
+        full = torch.cat(R.get_rays(directions, c2w, directions=ori, dx=dx, dy=dy, keepdim=True), -1)[0]
+        loader = full[by, bx]
+        assert torch.equal(loader, orc.pixel_rays(K, c2w, pixels, H, W, renormalize=False))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), K=K.numpy(), c2w=c2w.numpy(), pixels=pixels.numpy(),
+                        upstream=upstream.numpy(), rays=rays.detach().numpy(), loader_rays=loader.numpy(),
+                        d_c2w=pose.grad.numpy(), hw=np.array([H, W]))
+    print(f"[golden] {name}: 1024 pixels, |d_c2w|max={pose.grad.abs().max():.3e} ({time.time()-t:.1f}s) "
+          f"oracle==reference bit-exact fwd+bwd")
+
+
 def point_rays(fld, n, seed=11):
     """Points near the occupied shell with isocell-like random directions (6-col rays)."""
     g = torch.Generator().manual_seed(seed)
@@ -282,6 +320,8 @@ def main():
         point_case(R, "c1_point20", fld, point_rays(fld, 4096))
     if want("c1_ref_head"):
         ref_head_case(R, "c1_ref_head")
+    if want("c5_raygen"):
+        raygen_case(R, "c5_raygen")
     if want("c4_sub"):
         fld, rays = fx.config4()
         sub, idx = fx.subsample(rays, 2048, seed=0)

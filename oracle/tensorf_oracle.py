@@ -321,3 +321,43 @@ def pack_valid_bits(valid: torch.Tensor):
 def train_loss(out, target):
     """train.py:293 + train.py:328-329 (MSE + 0.1*mean(exp(|alpha|)))."""
     return torch.mean((out["rgb_map"] - target) ** 2) + 0.1 * torch.mean(torch.exp(torch.abs(out["alpha"])))
+
+
+# --------------------------------------------------------------------------- #
+# ray generation (SURVEY.md §8f row 4)
+# --------------------------------------------------------------------------- #
+def camera_directions(H: int, W: int, K: torch.Tensor):
+    """Pixel-centre directions K^-1 [x+.5, y+.5, 1] for every pixel and for its +1-x / +1-y neighbours
+    (get_ray_directions_Ks, ray_utils.py:28-60): returns three [1,H,W,3] grids."""
+    xs = torch.arange(W, dtype=torch.float32) + 0.5
+    ys = torch.arange(H, dtype=torch.float32) + 0.5
+    gx, gy = torch.meshgrid(xs, ys, indexing="xy")                     # [H,W] each
+    Kinv = torch.inverse(K.reshape(-1, 3, 3))                          # ray_utils.py:50
+    grids = []
+    for ox, oy in ((0.0, 0.0), (1.0, 0.0), (0.0, 1.0)):
+        pix = torch.stack([gx + ox, gy + oy, torch.ones_like(gx)], 0).reshape(1, 3, -1)
+        grids.append((Kinv @ pix).reshape(-1, 3, H, W).permute(0, 2, 3, 1))
+    return grids
+
+
+def pixel_rays(K: torch.Tensor, c2w: torch.Tensor, pixels: torch.Tensor, H: int, W: int, renormalize: bool = True):
+    """[N,7] rays of `pixels` [N,2] (x,y) through pose `c2w` [3|4,4]: the chain of
+    inerf/estimate_pose_inerf.py:96-99 (unit view directions), ray_utils.py:63-100 (rotate, origin, radii) and
+    :149-164 (pixel indexing, F.normalize, cat).  Differentiable w.r.t. c2w."""
+    ori, dx, dy = camera_directions(H, W, K)
+    view = ori / torch.linalg.norm(ori, dim=-1, keepdim=True)
+    R = c2w[..., :3, :3]
+
+    def rot(v):                                                       # (v[..., None, :] * R).sum(-1), ray_utils.py:76
+        return (v[..., None, :] * R).sum(-1)
+    d = rot(view)                                                     # same creation order as ray_utils.py:76-83
+    wx, wy = rot(dx), rot(dy)
+    wo = rot(ori)
+    o = c2w[..., :3, 3].unsqueeze(-2).expand(d.shape)
+    radii = (0.5 * (torch.linalg.norm(wx - wo, dim=-1) + torch.linalg.norm(wy - wo, dim=-1))[..., None]) \
+        * (2 / math.sqrt(12))                                         # ray_utils.py:90-98
+    px, py = pixels[:, 0].long(), pixels[:, 1].long()
+    d = d[0, py, px]
+    if renormalize:
+        d = F.normalize(d, p=2, dim=-1)                               # estimate_pose_inerf.py:159
+    return torch.cat((o[0, py, px], d, radii[0, py, px]), dim=-1)

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""End-to-end (host rays -> host rgb/depth) timing of OctreeRender_trilinear_fast for different slice counts."""
+"""End-to-end (host rays -> host rgb/depth) timing of OctreeRender_trilinear_fast for different slice counts, next to
+the bare H2D / D2H copy times of the same buffers."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -12,21 +13,28 @@ fld = fx.make_field([300] * 3, density_shift=0.0)
 m = H.module_from_field(fld, dev)
 rays = fx.config2_rays().pin_memory()
 n = rays.shape[0]
-out = torch.empty((n, 4)).pin_memory()
+rgb_h = torch.empty((n, 3)).pin_memory()
+depth_h = torch.empty((n,)).pin_memory()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for prec in ("auto",):
-    m.mlp_precision = prec
-    for slices in (1, 2, 4, 6, 8, 16):
-        m.host_ray_slices = slices
-        def step():
-            rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(rays, m, white_bg=True, device=dev)
-            out[:, :3].copy_(rgb, non_blocking=True); out[:, 3].copy_(depth, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        for _ in range(3): step()
-        tot = 0.0; wall = 0.0
-        for _ in range(10):
-            flush.fill_(1); torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0 = time.perf_counter(); e0.record(); step(); e1.record(); torch.cuda.synchronize(); wall += time.perf_counter() - t0
-            tot += e0.elapsed_time(e1)
-        print(json.dumps({"mlp": prec, "slices": slices, "e2e_ms": round(tot / 10, 3), "wall_ms": round(wall * 100, 3)}))
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm): fn()
+    tot = 0.0
+    for _ in range(reps):
+        flush.fill_(1); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return round(tot / reps, 3)
+
+rd = torch.empty_like(rays, device=dev); rgb_d = torch.empty((n, 3), device=dev); dep_d = torch.empty((n,), device=dev)
+print(json.dumps({"h2d_ms": timeit(lambda: rd.copy_(rays, non_blocking=True)),
+                  "d2h_ms": timeit(lambda: (rgb_h.copy_(rgb_d, non_blocking=True), depth_h.copy_(dep_d, non_blocking=True))),
+                  "device_ms": timeit(lambda: m.render_eval(rd, white_bg=True))}), flush=True)
+for slices in (1, 2, 3, 4, 6, 8):
+    m.host_ray_slices = slices
+    def step():
+        rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(rays, m, white_bg=True, device=dev)
+        rgb_h.copy_(rgb, non_blocking=True); depth_h.copy_(depth, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    print(json.dumps({"slices": slices, "e2e_ms": timeit(step)}), flush=True)

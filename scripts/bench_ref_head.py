@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""800x800 eval render with the `Ref` head (configs/lego.txt:25): fused tail kernel vs the torch-op tail."""
+import contextlib, io, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import iffnerf_b200 as I
+from oracle import fixtures as fx
+from oracle.make_golden import REF_KW
+dev = torch.device("cuda:0")
+aabb = torch.tensor([[-1.5] * 3, [1.5] * 3])
+torch.manual_seed(fx.SEED)
+with contextlib.redirect_stdout(io.StringIO()):
+    m = I.TensorVMSplit(aabb.clone().to(dev), [300] * 3, dev, **REF_KW)
+occ = fx.sphere_occupancy(aabb, 200, radius=1.0)
+m.alphaMask = I.AlphaGridMask(dev, occ.aabb.clone().to(dev), occ.volume.clone().to(dev))
+rays = fx.config2_rays().to(dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+def timeit(fn, reps=5):
+    fn(); fn(); torch.cuda.synchronize(); tot = 0.0
+    for _ in range(reps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); tot += e0.elapsed_time(e1)
+    return round(tot / reps, 3)
+out = {}
+for name, flag in (("fused_tail_ms", True), ("torch_tail_ms", False)):
+    m.ref_kernel = flag
+    out[name] = timeit(lambda: m.render_eval(rays, white_bg=True))
+m.native_shade_backup = None
+print(json.dumps(out))

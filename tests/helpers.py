@@ -58,7 +58,10 @@ def host_pack_factors(m):
         for off, t in ((d.dplane_off[k], m.density_plane[k]), (d.dline_off[k], m.density_line[k]),
                        (d.aplane_off[k], m.app_plane[k]), (d.aline_off[k], m.app_line[k])):
             a = t.detach().cpu().numpy()[0]                   # [C,H,W]
-            a = np.ascontiguousarray(a.transpose(1, 2, 0)).reshape(-1)
+            a = a.transpose(1, 2, 0)                          # [H,W,C]
+            if a.shape[1] > 1:                                # planes: rows padded to an odd pitch (tvm_plane_pitch)
+                a = np.pad(a, ((0, 0), (0, (a.shape[1] | 1) - a.shape[1]), (0, 0)))
+            a = np.ascontiguousarray(a).reshape(-1)
             buf[off:off + a.size] = a
     return d, buf
 

@@ -62,6 +62,12 @@ def test_point_queries_match_reference_golden(c1, dev):
     ref = orc.density_feature(fld, orc.normalize(fld, far.cpu()))
     got = m.compute_densityfeature(m.normalize_coord(far))
     assert (got.cpu() - ref).abs().max() <= 2e-5
+    # compute_appfeature (tensoRF.py:237-256; pose_estimation/sampling.py:535-541): [M, app_dim] incl. basis_mat
+    af = m.compute_appfeature(m.normalize_coord(pts))
+    assert af.shape == (pts.shape[0], 27)
+    assert np.abs(af.cpu().numpy() - g["point_appfeature"]).max() <= 2e-5
+    ref = orc.app_feature(fld, orc.normalize(fld, far.cpu()))
+    assert (m.compute_appfeature(m.normalize_coord(far)).cpu() - ref).abs().max() <= 2e-5
 
 
 def test_update_alpha_mask_and_filtering_match_oracle(dev):

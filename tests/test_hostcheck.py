@@ -158,7 +158,8 @@ def _unpack_host_grads(m, d, gbuf):
                              (f"app_plane.{k}", d.aplane_off[k], m.app_plane[k]),
                              (f"app_line.{k}", d.aline_off[k], m.app_line[k])):
             _, C_, H_, W_ = t.shape
-            out[name] = gbuf[off:off + C_ * H_ * W_].reshape(H_, W_, C_).transpose(2, 0, 1)[None]
+            pitch = (W_ | 1) if W_ > 1 else 1            # plane rows are padded to an odd pitch (tvm_plane_pitch)
+            out[name] = gbuf[off:off + C_ * H_ * pitch].reshape(H_, pitch, C_)[:, :W_].transpose(2, 0, 1)[None]
     return out
 
 

@@ -45,3 +45,18 @@ def test_bit_packing_roundtrip():
     v = torch.rand(5, 70) > 0.5
     w = orc.pack_valid_bits(v).numpy().astype(np.uint32)
     assert np.array_equal(H.unpack_bits(w, 70), v.numpy())
+
+
+def test_oracle_pixel_rays_reproduce_reference_golden():
+    """the ray-generation restatement against the reference's get_rays chain (fwd + pose gradient)."""
+    g = H.golden("c5_raygen")
+    Hh, Ww = (int(v) for v in g["hw"])
+    pose = torch.from_numpy(g["c2w"]).clone().requires_grad_(True)
+    rays = orc.pixel_rays(torch.from_numpy(g["K"]), pose, torch.from_numpy(g["pixels"]), Hh, Ww)
+    (rays * torch.from_numpy(g["upstream"])).sum().backward()
+    assert np.array_equal(rays.detach().numpy(), g["rays"])
+    np.testing.assert_allclose(pose.grad.numpy(), g["d_c2w"], rtol=1e-5, atol=1e-5)   # sum order is thread-count dependent
+    with torch.no_grad():
+        loader = orc.pixel_rays(torch.from_numpy(g["K"]), torch.from_numpy(g["c2w"]), torch.from_numpy(g["pixels"]),
+                                Hh, Ww, renormalize=False)
+    assert np.array_equal(loader.numpy(), g["loader_rays"])
