@@ -30,9 +30,6 @@ namespace {
 #ifndef TVM_MARCH_MIN_BLOCKS
 #define TVM_MARCH_MIN_BLOCKS 4
 #endif
-#ifndef TVM_SPLIT_APP_MIN_BLOCKS
-#define TVM_SPLIT_APP_MIN_BLOCKS 4
-#endif
 constexpr int MARCH_WARPS = TVM_MARCH_WARPS;
 constexpr int MARCH_RAYS_PER_CTA = TVM_MARCH_RAYS_PER_CTA;
 constexpr unsigned FULL = 0xffffffffu;
@@ -64,11 +61,6 @@ struct MarchArgs {
     int rays_per_cta;
     TvmSections sec;
 };
-
-#ifdef TVM_SPLIT_PROBE
-struct SplitProbe { float4* entries; int* grp_ray; unsigned* counter; unsigned cap_groups; };
-__device__ SplitProbe g_probe;
-#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -191,34 +183,8 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                     acc += w;
                     dep = fmaf(w, z, dep);
                     // ---- appearance for samples with weight > rayMarch_weight_thres (:851)
-#ifdef TVM_MARCH_NO_APP      // tuning probe only: density-only march (how does the sampling + sigma part scale with occupancy?)
-                    const bool app = false;
-#else
                     const bool app = keep && (w > f.weight_thres);
-#endif
-#ifdef TVM_MARCH_NO_APP
-                    const unsigned amask = 0u;
-#else
                     const unsigned amask = __ballot_sync(FULL, app);
-#endif
-#ifdef TVM_SPLIT_PROBE
-                    if (amask) {
-                        const int na = __popc(amask), ranka = __popc(amask & lt_mask);
-                        const unsigned ng = (unsigned)(na + 7) >> 3;
-                        unsigned gbase = 0;
-                        if (lane == 0) gbase = atomicAdd(g_probe.counter, ng);
-                        gbase = __shfl_sync(FULL, gbase, 0);
-                        if (gbase + ng <= g_probe.cap_groups) {
-                            if (app) g_probe.entries[(size_t)gbase * 8 + ranka] = make_float4(n[0], n[1], n[2], w);
-                            // pad the last group with zero-weight entries (pad lanes: the first ng*8 - na non-app lanes)
-                            const int pad_rank = __popc(~amask & lt_mask);
-                            if (!app && pad_rank < (int)(ng * 8) - na)
-                                g_probe.entries[(size_t)gbase * 8 + na + pad_rank] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (lane < (int)ng) g_probe.grp_ray[gbase + lane] = (int)r;
-                        }
-                        n_app += na;
-                    }
-#else
                     if (amask) {
                         const int na = __popc(amask), ranka = __popc(amask & lt_mask);
                         if (app) s_slot[warp][ranka] = make_float4(n[0], n[1], n[2], w);
@@ -234,7 +200,6 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                         __syncwarp();
                         n_app += na;
                     }
-#endif
                     if (early && T < f.early_term_eps) dead = true;
                 }
                 if (sample_out && in_range) {
@@ -267,10 +232,8 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                         }
                     }
                     const int j = sub + 4 * g;
-#ifndef TVM_SPLIT_PROBE
                     if (quad == 0 && j < (CA4 > 0 ? CA4 : (f.n_app[k] >> 2)))
                         reinterpret_cast<float4*>(a.ray_feat + r * a.ta + a.app_off[k])[j] = v;
-#endif
                 }
             if (lane == 0) {
                 a.acc[r] = acc;
@@ -285,51 +248,6 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
         local = __shfl_sync(FULL, nxt, 0);
     }
 }
-
-#ifdef TVM_SPLIT_PROBE
-// ---- two-kernel split probe (tuning experiment, not part of the product path): the march kernel writes the
-// appearance samples (fractional texel indices + weight) as groups of 8 into a global list instead of gathering
-// them; app_list_kernel then streams the list.
-
-template <int G, int CA4>
-__global__ void __launch_bounds__(128, TVM_SPLIT_APP_MIN_BLOCKS) app_list_kernel(const __grid_constant__ MarchArgs a) {
-    const tvm_field_desc& f = a.f;
-    const int lane = threadIdx.x & 31, sub = lane & 3, quad = lane >> 2;
-    const unsigned n_groups = min(*g_probe.counter, g_probe.cap_groups);
-    constexpr unsigned CH = 32;                                   // groups per warp chunk
-    const unsigned warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned c0 = warp_id * CH; c0 < n_groups; c0 += n_warps * CH) {
-        const unsigned c1 = min(c0 + CH, n_groups);
-        float4 A[3][G];
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int g = 0; g < G; ++g) A[k][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int cur = __ldg(g_probe.grp_ray + c0);
-        for (unsigned g = c0; g < c1; ++g) {
-            const int ray = __ldg(g_probe.grp_ray + g);
-            if (ray != cur) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-#pragma unroll
-                    for (int gg = 0; gg < G; ++gg) {
-                        atomicAdd(reinterpret_cast<float4*>(a.ray_feat + (long long)cur * a.ta + a.app_off[k]) + sub + 4 * gg, A[k][gg]);
-                        A[k][gg] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                cur = ray;
-            }
-            const float4 e = __ldg(g_probe.entries + (size_t)g * 8 + quad);
-            const float q[3] = {e.x, e.y, e.z};
-            app_accumulate_taps<G, CA4>(f, a.sec, make_sample_taps_idx(f, q), e.w, sub, A);
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int gg = 0; gg < G; ++gg)
-                atomicAdd(reinterpret_cast<float4*>(a.ray_feat + (long long)cur * a.ta + a.app_off[k]) + sub + 4 * gg, A[k][gg]);
-    }
-}
-#endif
 
 int fill_args(MarchArgs& a, const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
               int n_samples, const float* jitter) {
@@ -414,26 +332,3 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
     if (gmax == 2) return launch(march_fwd_kernel<2, false, 0, 0>, a, st);
     return launch(march_fwd_kernel<3, false, 0, 0>, a, st);
 }
-
-#ifdef TVM_SPLIT_PROBE
-#ifndef TVM_SPLIT_APP_MIN_BLOCKS
-#define TVM_SPLIT_APP_MIN_BLOCKS 4
-#endif
-extern "C" int tvm_split_probe_set(void* entries, int* grp_ray, unsigned* counter, unsigned cap_groups) {
-    SplitProbe p{(float4*)entries, grp_ray, counter, cap_groups};
-    return (int)cudaMemcpyToSymbol(g_probe, &p, sizeof(p));
-}
-extern "C" int tvm_split_probe_app(const tvm_field_desc* desc, int64_t n_rays, void* ws, size_t ws_bytes, int ctas, void* stream) {
-    MarchArgs a;
-    const float dummy = 0.f;
-    int rc = fill_args(a, desc, &dummy, n_rays, 6, 32, nullptr);
-    if (rc) return rc;
-    const TvmWorkspace w = tvm_ws_layout(desc, n_rays);
-    if (ws_bytes < w.total) return TVM_E_WORKSPACE;
-    a.ray_feat = (float*)((char*)ws + w.ray_feat);
-    cudaFuncSetAttribute(app_list_kernel<3, 12>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    app_list_kernel<3, 12><<<ctas, 128, 0, (cudaStream_t)stream>>>(a);
-    TVM_LAUNCH_CHECK();
-    return 0;
-}
-#endif
