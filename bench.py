@@ -206,6 +206,43 @@ def dp_train_step(model, dev, fx, world, rank):
             "allreduce_bytes_per_step": sync.bytes // max(sync.calls // 2, 1)}
 
 
+def config4_sharded(dev, fx, Hh, world):
+    """Informational, BASELINE configs[3]: ONE 1920x1080 image of the truck-shaped (non-cubic 300^3-voxel) field,
+    ray-sharded over the ranks in cyclic 4096-ray tiles (iffnerf_b200.sharding.render_sharded), result all-gathered
+    (16 B/ray) so every rank holds the full image.  Strong scaling: total work fixed, time = max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import iffnerf_b200 as I
+    from iffnerf_b200 import sharding
+    fld, rays = fx.config4()
+    m = Hh.module_from_field(fld, dev)
+    m.eval()
+    rays = rays.to(dev)
+
+    def step():
+        if world > 1:
+            return sharding.render_sharded(rays, m, I.OctreeRender_trilinear_fast, white_bg=True, device=dev)
+        return I.OctreeRender_trilinear_fast(rays, m, white_bg=True, device=dev)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    del m
+    return {"rays": int(rays.shape[0]), "grid": list(fld.grid), "ms_per_image": ms,
+            "rays_per_s": rays.shape[0] / (ms / 1e3), "scaling": "strong", "gathered": world > 1}
+
+
 def extra_configs(model, dev, fx):
     """Informational timings of BASELINE configs 3 and 5 on the same field (their parity is in tests/):
     config 3 = train.py-style step (4096 rays, S=1039, fwd+bwd into every parameter gradient);
@@ -252,8 +289,56 @@ def extra_configs(model, dev, fx):
         torch.mean((rgb - ptarget) ** 2).backward()
     ms = timeit(pose_step, steps=5, warm=2)
     out["config5_pose_step_64x1024"] = {"rays": 64 * 1024, "ms_fwd_bwd_to_rays": ms, "rays_per_s": 65536 / (ms / 1e3)}
+    # config 5 as the reference's loop runs it (inerf/estimate_pose_inerf.py:103-186): ONE pose, 1024 pixels per step,
+    # fused ray generation -> render -> MSE -> backward to the pose -> Adam; eager launches vs one CUDA-graph replay
+    import numpy as np
+    import iffnerf_b200 as I
+    Kc = torch.tensor([[[400.0 / math.tan(0.5 * 0.6911112), 0.0, 400.0], [0.0, 400.0 / math.tan(0.5 * 0.6911112), 400.0],
+                        [0.0, 0.0, 1.0]]])
+    base = torch.cat([fx.orbit_pose(), torch.tensor([[0.0, 0.0, 0.0, 1.0]])], 0).to(dev)
+    delta = torch.zeros(3, 4, device=dev, requires_grad=True)
+    opt = torch.optim.Adam([delta], lr=1e-3, capturable=True)
+    pix = torch.stack([torch.randint(200, 600, (1024,), generator=g), torch.randint(200, 600, (1024,), generator=g)],
+                      -1).to(device=dev, dtype=torch.int32)
+    tgt = torch.rand(1024, 3, device=dev)
+
+    def inerf_step():
+        opt.zero_grad(set_to_none=True)
+        pose = base + torch.cat([delta, torch.zeros(1, 4, device=dev)], 0)
+        rays = I.pixel_rays(Kc, pose, pix)
+        rgb = model(rays, bg_color=bg, is_train=False)[0]
+        loss = torch.mean((rgb - tgt) ** 2)
+        loss.backward()
+        opt.step()
+        return loss
+    ms_eager = timeit(inerf_step, steps=20, warm=3)
+    graphed = I.graphs.CapturedStep(inerf_step, models=[model], warmup=1)
+    ms_graph = timeit(graphed, steps=20, warm=3)
+    out["config5_inerf_step_1024"] = {"rays": 1024, "ms_eager": ms_eager, "ms_cuda_graph": ms_graph,
+                                      "rays_per_s_cuda_graph": 1024 / (ms_graph / 1e3)}
     for p in model.parameters():
         p.requires_grad_(True)
+    # config 3 again, whole step (zero_grad, forward, loss, backward, Adam) from a CUDA graph
+    model.train()
+    model.zero_grad(set_to_none=True)
+    topt = torch.optim.Adam(model.get_optparam_groups(0.02, 1e-3), betas=(0.9, 0.99), capturable=True)
+    jit = torch.rand(4096, device=dev)
+
+    def full_train_step():
+        topt.zero_grad(set_to_none=True)
+        rgb, _, _, alpha, _, _ = model(rays, bg_color=ones, is_train=True, N_samples=1039, jitter=jit)
+        loss = torch.mean((rgb - target) ** 2) + 0.1 * torch.mean(torch.exp(torch.abs(alpha)))
+        loss.backward()
+        topt.step()
+        return loss
+    ms_eager = timeit(full_train_step, steps=10, warm=3)
+    graphed_t = I.graphs.CapturedStep(full_train_step, models=[model], warmup=1)
+    ms_graph = timeit(graphed_t, steps=10, warm=3)
+    out["config3_train_step_with_adam"] = {"rays": 4096, "ms_eager": ms_eager, "ms_cuda_graph": ms_graph,
+                                           "rays_per_s_cuda_graph": 4096 / (ms_graph / 1e3)}
+    model.eval()
+    model.zero_grad(set_to_none=True)
+    del graphed, graphed_t
     return out
 
 
@@ -393,6 +478,7 @@ def run_ours(args, rank, world, local_rank):
             gather_peak[name] = best
 
     dp = dp_train_step(model, dev, fx, world, rank) if world > 1 else None
+    c4 = config4_sharded(dev, fx, Hh, world)
 
     t = torch.tensor([ms_dev, ms_march, ms_e2e, ms_dev_tc, ms_e2e_tc, ms_dev_simt], dtype=torch.float64, device=dev)
     if world > 1:
@@ -450,6 +536,7 @@ def run_ours(args, rank, world, local_rank):
             line["other_configs"] = extra_configs(model, dev, fx)
         else:
             line["other_configs"] = {"config3_train_step_data_parallel": dp}
+        line["other_configs"]["config4_truck_1080p_sharded"] = c4
         if not args.no_cpu_baseline and world == 1:
             rate, cores, desc = cpu_oracle_rate(args.cpu_rays)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}

@@ -279,7 +279,18 @@ int launch(K kernel, MarchArgs& a, cudaStream_t st) {
     a.rays_per_cta = pick_rays_per_cta(a.n_rays, MARCH_WARPS, MARCH_RAYS_PER_CTA);
     // small static smem per CTA: ask for a 32 KB carve-out (enough for every resident CTA) and leave the rest
     // of the 228 KB to L1, which is what serves the texel gathers
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 14);
+    // set once per kernel instantiation (all instantiations share the pointer type K, so remember the pointers);
+    // a racing duplicate call is harmless
+    static std::atomic<const void*> seen[8];
+    bool done = false;
+    for (auto& s : seen) done = done || s.load(std::memory_order_relaxed) == (const void*)kernel;
+    if (!done) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 14);
+        for (auto& s : seen) {
+            const void* expect = nullptr;
+            if (s.compare_exchange_strong(expect, (const void*)kernel)) break;
+        }
+    }
     const long long ctas = (a.n_rays + a.rays_per_cta - 1) / a.rays_per_cta;
     kernel<<<(unsigned)ctas, MARCH_WARPS * 32, 0, st>>>(a);
     TVM_LAUNCH_CHECK();

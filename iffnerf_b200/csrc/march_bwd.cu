@@ -18,6 +18,9 @@
 
 namespace {
 
+#ifndef TVM_BWD_MIN_BLOCKS
+#define TVM_BWD_MIN_BLOCKS 3
+#endif
 constexpr int BWD_WARPS = 4;
 constexpr int BWD_RAYS_PER_CTA = 16;
 constexpr unsigned FULL = 0xffffffffu;
@@ -54,7 +57,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 template <int G, bool SCATTER, bool POSE, int CS4, int CA4>
-__global__ void __launch_bounds__(BWD_WARPS * 32) march_bwd_kernel(const __grid_constant__ BwdArgs a) {
+__global__ void __launch_bounds__(BWD_WARPS * 32, TVM_BWD_MIN_BLOCKS) march_bwd_kernel(const __grid_constant__ BwdArgs a) {
     __shared__ int s_next;
     __shared__ float4 s_slot[BWD_WARPS][32];
     __shared__ float s_ret[BWD_WARPS][32];

@@ -273,7 +273,11 @@ extern "C" int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int6
     const size_t nX = (size_t)SH_RAYS * a.k1;
     const size_t smem = (nB + nF + nX) * sizeof(float);
     if (smem > 227 * 1024) return TVM_E_SHAPE;
-    TVM_CUDA_OK(cudaFuncSetAttribute(shade_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        static std::atomic<int> smem_set{0};
+        int rc_attr = tvm_ensure_dyn_smem(shade_fwd_kernel, smem, smem_set);
+        if (rc_attr) return rc_attr;
+    }
     const long long ctas = (n_rays + SH_RAYS - 1) / SH_RAYS;
     shade_fwd_kernel<<<(unsigned)ctas, SH_THREADS, smem, (cudaStream_t)stream>>>(a);
     TVM_LAUNCH_CHECK();

@@ -401,7 +401,11 @@ extern "C" int tvm_shade_bwd(const tvm_field_desc* desc, const float* rays, int6
                           (size_t)SB_RAYS * (a.m.k1 > FC ? a.m.k1 : FC) + (size_t)SB_RAYS * FC * 2 + SB_RAYS * 8;
     const size_t smem = floats * sizeof(float);
     if (smem > 227 * 1024) return TVM_E_SHAPE;
-    TVM_CUDA_OK(cudaFuncSetAttribute(shade_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        static std::atomic<int> smem_set{0};
+        int rc_attr = tvm_ensure_dyn_smem(shade_bwd_kernel, smem, smem_set);
+        if (rc_attr) return rc_attr;
+    }
     const long long ctas = (n_rays + SB_RAYS - 1) / SB_RAYS;
     shade_bwd_kernel<<<(unsigned)ctas, SB_THREADS, smem, (cudaStream_t)stream>>>(a);
     TVM_LAUNCH_CHECK();

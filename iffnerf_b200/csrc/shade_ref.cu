@@ -228,7 +228,9 @@ extern "C" int tvm_shade_ref_fwd(const tvm_field_desc* desc, const tvm_ref_head*
     const unsigned ctas = (unsigned)(tiles < TVM_SM_COUNT * 6 ? tiles : TVM_SM_COUNT * 6);
     cudaStream_t st = (cudaStream_t)stream;
     if (head->in_c == 27) {
-        TVM_CUDA_OK(cudaFuncSetAttribute(shade_ref_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static std::atomic<int> smem_set{0};
+        int rc_attr = tvm_ensure_dyn_smem(shade_ref_kernel<27>, smem, smem_set);
+        if (rc_attr) return rc_attr;
         shade_ref_kernel<27><<<ctas, REF_THREADS, smem, st>>>(a);
     } else {
         return TVM_E_SHAPE;          // app_dim = 27 is what every reference config uses (configs/*.txt)

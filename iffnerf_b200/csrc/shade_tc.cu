@@ -269,7 +269,11 @@ int tvm_shade_tc_launch(const tvm_field_desc* desc, const float* rays, int64_t n
     a.wimg = (const unsigned char*)desc->mlp_tc;
     a.b1 = desc->mlp + m.b1; a.b2 = desc->mlp + m.b2; a.b3 = desc->mlp + m.b3;
     a.d = d;
-    TVM_CUDA_OK(cudaFuncSetAttribute(shade_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        static std::atomic<int> smem_set{0};
+        int rc_attr = tvm_ensure_dyn_smem(shade_tc_kernel, smem, smem_set);
+        if (rc_attr) return rc_attr;
+    }
     const long long tiles = (n_rays + TC_RAYS - 1) / TC_RAYS;
     const unsigned grid = (unsigned)(tiles < TVM_SM_COUNT ? tiles : TVM_SM_COUNT);
     shade_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);

@@ -323,7 +323,11 @@ int tvm_shade_tc3_launch(const tvm_field_desc* desc, const float* rays, int64_t 
     a.wimg = (const unsigned char*)desc->mlp_tc3;
     a.b1 = desc->mlp + m.b1; a.b2 = desc->mlp + m.b2; a.b3 = desc->mlp + m.b3;
     a.d = d;
-    TVM_CUDA_OK(cudaFuncSetAttribute(shade_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        static std::atomic<int> smem_set{0};
+        int rc_attr = tvm_ensure_dyn_smem(shade_tc3_kernel, smem, smem_set);
+        if (rc_attr) return rc_attr;
+    }
     const long long tiles = (n_rays + TC_RAYS - 1) / TC_RAYS;
     const unsigned grid = (unsigned)(tiles < TVM_SM_COUNT ? tiles : TVM_SM_COUNT);
     shade_tc3_kernel<<<grid, TC_THREADS, smem, st>>>(a);

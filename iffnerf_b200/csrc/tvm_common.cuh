@@ -15,6 +15,19 @@
         if (e__ != cudaSuccess) return (int)e__;  \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when the requested size grows past what this process already
+// set for the kernel.  The attribute is per-process CUDA state anyway; skipping the redundant calls keeps a warmed-up
+// launch path free of non-stream API calls, so the entry points can be captured into CUDA graphs.
+#include <atomic>
+template <typename K>
+static inline int tvm_ensure_dyn_smem(K kernel, size_t bytes, std::atomic<int>& high_water) {
+    if ((int)bytes <= high_water.load(std::memory_order_relaxed)) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    high_water.store((int)bytes, std::memory_order_relaxed);
+    return 0;
+}
+
 constexpr int TVM_SM_COUNT = 148;        // B200: 2 dies x 74 SMs
 constexpr int TVM_MAX_SIGMA_C = 16;
 constexpr int TVM_MAX_APP_C = 48;

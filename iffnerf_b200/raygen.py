@@ -22,10 +22,22 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+_kinv_cache = {}
+
+
 def _kinv(K):
-    """Host float[9] of torch.inverse(K) (ray_utils.py:50); K is [3,3] or [1,3,3]."""
-    k = torch.inverse(K.detach().reshape(-1, 3, 3)[0].float().cpu()).contiguous()
-    return (C.c_float * 9)(*k.reshape(-1).tolist())
+    """Host float[9] of torch.inverse(K) (ray_utils.py:50); K is [3,3] or [1,3,3].  Cached per (tensor, version): the
+    intrinsics are constants of a run, and a cached value keeps `pixel_rays` free of host<->device traffic (CUDA-graph
+    capturable) even when K lives on the GPU."""
+    key = (K.data_ptr(), K._version, K.device.type)
+    hit = _kinv_cache.get(key)
+    if hit is None:
+        k = torch.inverse(K.detach().reshape(-1, 3, 3)[0].float().cpu()).contiguous()
+        hit = (C.c_float * 9)(*k.reshape(-1).tolist())
+        if len(_kinv_cache) > 64:
+            _kinv_cache.clear()
+        _kinv_cache[key] = hit
+    return hit
 
 
 class _PixelRays(torch.autograd.Function):

@@ -325,6 +325,12 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         d.n_factor_floats = lay["total"]
         return d
 
+    def invalidate_packed(self):
+        """Forget the cache keys of every packed parameter shadow: the next use re-packs from the parameters.  (Needed
+        after in-place updates that bypass autograd version counters, e.g. an optimiser step replayed by a CUDA graph.)"""
+        self._packed_key = self._mlp_key = self._mlp_tc_key = None
+        self._ref_key = None
+
     def packed_factors(self):
         """Channel-last shadow of the 12 factor tensors, re-packed only when a factor changed."""
         planes, lines = self._factor_params()
