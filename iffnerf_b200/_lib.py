@@ -19,7 +19,6 @@ F_MLP_BF16 = 1 << 1
 F_NO_SHADE = 1 << 2
 F_POINT_SAMPLES = 1 << 3
 F_MLP_TC3 = 1 << 4
-F_REG_ACC = 1 << 5
 
 _f3 = C.c_float * 3
 _f6 = C.c_float * 6

@@ -30,9 +30,6 @@ namespace {
 #ifndef TVM_MARCH_MIN_BLOCKS
 #define TVM_MARCH_MIN_BLOCKS 4
 #endif
-#ifndef TVM_MARCH_TACC_MIN_BLOCKS
-#define TVM_MARCH_TACC_MIN_BLOCKS 6
-#endif
 constexpr int MARCH_WARPS = TVM_MARCH_WARPS;
 constexpr int MARCH_RAYS_PER_CTA = TVM_MARCH_RAYS_PER_CTA;
 constexpr unsigned FULL = 0xffffffffu;
@@ -65,114 +62,22 @@ struct MarchArgs {
     TvmSections sec;
 };
 
-// ---- TMEM-resident appearance accumulator (TACC kernels) --------------------------------------------------------
-// The per-ray accumulator (3 planes x 12 float4 slices / 4 lanes = 36 floats per lane) is what pins the kernel at 128
-// registers = 16 warps per SM.  Blackwell's tensor memory is 128 lanes x 512 columns of 32 bits per SM, reachable
-// with tcgen05.ld / tcgen05.st and outside the L1 data pipe the gathers saturate: each CTA allocates 64 columns, warp
-// w owns TMEM lanes [32w, 32w+32), lane t of the warp keeps its 36 accumulator floats in columns 0..35 of TMEM lane
-// 32w+t.  A slice is read-modify-written around its FMAs, so the accumulator costs 4 live registers instead of 36.
-// (No "memory" clobbers: these instructions touch tensor memory only, and volatile asm keeps their mutual order.)
-constexpr int TACC_COLS = 64;
-__device__ __forceinline__ float4 tmem_ld4(uint32_t taddr) {
-    uint32_t r0, r1, r2, r3;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
-                 "tcgen05.wait::ld.sync.aligned;"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
-    return make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
-}
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, float4 v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                 :: "r"(taddr), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
-                    "r"(__float_as_uint(v.w)));
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;"); }
-
-// issue-only TMEM load of 4 columns and the matching wait, which takes the loaded registers as in/out operands so that
-// every consumer is ordered after it (the values are undefined until tcgen05.wait::ld)
-__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[4]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait12(uint32_t (&a)[4], uint32_t (&b)[4], uint32_t (&c)[4]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]),
-                   "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]));
-}
-
-// one appearance pass with the accumulator in TMEM: every lane of the warp takes part (tcgen05.ld/st are
-// warp-collective); quads without a sample (`active` false) skip the gathers and write their slices back unchanged.
-// Per plane the three slices are requested from TMEM first, the gathers and products run under that latency, one wait
-// orders the adds, three stores write back.
-template <int CA4>
-__device__ __forceinline__ void app_accumulate_tmem(const tvm_field_desc& f, const TvmSections& sec, const float4 e,
-                                                    bool active, int sub, uint32_t tacc) {
-    static_assert(CA4 == 12, "three float4 slices per lane and plane");
-    const float q[3] = {e.x, e.y, e.z};
-    const SampleTaps st = make_sample_taps_idx(f, q);
-    const float4* F4 = reinterpret_cast<const float4*>(f.factors);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const uint32_t col = tacc + (uint32_t)(k * 12);
-        uint32_t acc[3][4];
-#pragma unroll
-        for (int g = 0; g < 3; ++g) tmem_ld4_issue(col + 4 * g, acc[g]);
-        float4 prod[3];
-#pragma unroll
-        for (int g = 0; g < 3; ++g) prod[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) {
-            const PlaneTaps t = make_taps(f, st, k, CA4);
-            const float wl0 = e.w * t.lw0, wl1 = e.w * t.lw1;
-            const unsigned po = sec.aP[k] + (unsigned)sub, lo = sec.aL[k] + (unsigned)sub;
-            const float4* r0 = F4 + (t.pbase + po);
-            const float4* r1 = F4 + (t.pbase + t.prow + po);
-            const float4* lb = F4 + (t.lbase + lo);
-#pragma unroll
-            for (int g = 0; g < 3; ++g) prod[g] = f4_mul(vm_plane(r0, r1, t, CA4, 4 * g), vm_line(lb, wl0, wl1, CA4, 4 * g));
-        }
-        tmem_ld_wait12(acc[0], acc[1], acc[2]);
-#pragma unroll
-        for (int g = 0; g < 3; ++g)
-            tmem_st4(col + 4 * g, make_float4(__uint_as_float(acc[g][0]) + prod[g].x, __uint_as_float(acc[g][1]) + prod[g].y,
-                                              __uint_as_float(acc[g][2]) + prod[g].z, __uint_as_float(acc[g][3]) + prod[g].w));
-    }
-}
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
 
-template <int G, bool MASK_ONLY, int CS4, int CA4, bool TACC = false>
-__global__ void __launch_bounds__(MARCH_WARPS * 32, TACC ? TVM_MARCH_TACC_MIN_BLOCKS : TVM_MARCH_MIN_BLOCKS)
-march_fwd_kernel(const __grid_constant__ MarchArgs a) {
-    static_assert(!TACC || (CA4 > 0 && CA4 % 4 == 0 && 3 * CA4 <= TACC_COLS && MARCH_WARPS == 4),
-                  "TMEM accumulator: specialised channel counts, one warp per TMEM lane quarter");
+template <int G, bool MASK_ONLY, int CS4, int CA4>
+__global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_fwd_kernel(const __grid_constant__ MarchArgs a) {
     __shared__ int s_next;
-    __shared__ uint32_t s_tmem;
     __shared__ float4 s_slot[MARCH_WARPS][32];
     __shared__ float s_ret[MARCH_WARPS][32];
     const tvm_field_desc& f = a.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 3, quad = lane >> 2;
     const unsigned lt_mask = (1u << lane) - 1u;
     if (threadIdx.x == 0) s_next = MARCH_WARPS;
-    uint32_t tacc = 0;
-    if (TACC) {
-        if (warp == 0) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                         :: "r"((uint32_t)__cvta_generic_to_shared(&s_tmem)), "n"(TACC_COLS) : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    }
     __syncthreads();
-    if (TACC) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tacc = s_tmem + ((uint32_t)(warp * 32) << 16);            // this warp's TMEM lane quarter, column 0
-#pragma unroll
-        for (int c = 0; c < 3 * CA4; c += 4) tmem_st4(tacc + c, make_float4(0.f, 0.f, 0.f, 0.f));
-        tmem_wait_st();
-    }
 
     const long long base = (long long)blockIdx.x * a.rays_per_cta;
     const bool sample_out = a.alpha || a.z_vals || a.dists;
@@ -195,13 +100,11 @@ march_fwd_kernel(const __grid_constant__ MarchArgs a) {
         float T = 1.f, acc = 0.f, dep = 0.f;
         int n_valid = 0, n_sigma = 0, n_app = 0, n_occ = 0;
         bool dead = false;
-        float4 A[3][TACC ? 1 : G];         // register accumulator (unused by the TMEM variant)
-        if (!TACC) {
+        float4 A[3][G];
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < 3; ++k)
 #pragma unroll
-                for (int g = 0; g < (TACC ? 1 : G); ++g) A[k][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+            for (int g = 0; g < G; ++g) A[k][g] = make_float4(0.f, 0.f, 0.f, 0.f);
 
         // empty-space skip mask (exact): blocks whose end-sample box misses the aabb / every occupied super-cell
         const TvmBlockMask bm = tvm_block_prepass(f, ray, S, lane);
@@ -286,23 +189,12 @@ march_fwd_kernel(const __grid_constant__ MarchArgs a) {
                         const int na = __popc(amask), ranka = __popc(amask & lt_mask);
                         if (app) s_slot[warp][ranka] = make_float4(n[0], n[1], n[2], w);
                         __syncwarp();
-                        if constexpr (TACC) {
-                            for (int g = 0; g * 8 < na; ++g) {
-                                const int ci = g * 8 + quad;
-                                const bool act = ci < na;
-                                const float4 s = act ? s_slot[warp][ci] : make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (g > 0) tmem_wait_st();              // the previous pass's write-backs
-                                app_accumulate_tmem<CA4>(f, a.sec, s, act, sub, tacc);
-                            }
-                            tmem_wait_st();
-                        } else {
-                            for (int g = 0; g * 8 < na; ++g) {
-                                const int ci = g * 8 + quad;
-                                if (ci < na) {
-                                    const float4 s = s_slot[warp][ci];
-                                    const float q[3] = {s.x, s.y, s.z};
-                                    app_accumulate_taps<G, CA4>(f, a.sec, make_sample_taps_idx(f, q), s.w, sub, A);
-                                }
+                        for (int g = 0; g * 8 < na; ++g) {
+                            const int ci = g * 8 + quad;
+                            if (ci < na) {
+                                const float4 s = s_slot[warp][ci];
+                                const float q[3] = {s.x, s.y, s.z};
+                                app_accumulate_taps<G, CA4>(f, a.sec, make_sample_taps_idx(f, q), s.w, sub, A);
                             }
                         }
                         __syncwarp();
@@ -331,15 +223,7 @@ march_fwd_kernel(const __grid_constant__ MarchArgs a) {
             for (int k = 0; k < 3; ++k)
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if constexpr (TACC) {
-                        if (n_app > 0) {        // warp-uniform: read the slice back and clear it for the next ray
-                            v = tmem_ld4(tacc + (uint32_t)((k * G + g) * 4));
-                            tmem_st4(tacc + (uint32_t)((k * G + g) * 4), make_float4(0.f, 0.f, 0.f, 0.f));
-                        }
-                    } else {
-                        v = A[k][g];
-                    }
+                    float4 v = A[k][g];
                     if (n_app > 0) {            // warp-uniform; rays without appearance samples store their zeros
 #pragma unroll
                         for (int o = 4; o < 32; o <<= 1) {
@@ -359,16 +243,9 @@ march_fwd_kernel(const __grid_constant__ MarchArgs a) {
                 if (a.app_count_out) a.app_count_out[r] = n_app;
             }
         }
-        if (TACC && !MASK_ONLY) tmem_wait_st();
         int nxt = 0;
         if (lane == 0) nxt = atomicAdd(&s_next, 1);
         local = __shfl_sync(FULL, nxt, 0);
-    }
-    if (TACC) {
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (warp == 0)
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem), "n"(TACC_COLS) : "memory");
     }
 }
 
@@ -461,7 +338,6 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
     for (int k = 0; k < 3; ++k) gmax = max(gmax, (desc->n_app[k] + 15) / 16);
     bool lego = true;     // the reference configs: 16 density / 48 appearance components on every plane
     for (int k = 0; k < 3; ++k) lego = lego && desc->n_sigma[k] == 16 && desc->n_app[k] == 48;
-    if (lego && !(flags & TVM_F_REG_ACC)) return launch(march_fwd_kernel<3, false, 4, 12, true>, a, st);
     if (lego) return launch(march_fwd_kernel<3, false, 4, 12>, a, st);
     if (gmax <= 1) return launch(march_fwd_kernel<1, false, 0, 0>, a, st);
     if (gmax == 2) return launch(march_fwd_kernel<2, false, 0, 0>, a, st);

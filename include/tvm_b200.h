@@ -39,8 +39,6 @@ extern "C" {
 #define TVM_F_NO_SHADE     (1u << 2)  /* stop after the march stage: workspace holds ray_feat/acc/depth      */
 #define TVM_F_MLP_TC3      (1u << 4)  /* shade on the tensor cores with bf16x3 SPLIT operands (hi.hi + hi.lo + lo.hi,
                                          fp32 accumulate): fp32-equivalent, rgb within ~1e-6 of the FFMA kernel   */
-#define TVM_F_REG_ACC       (1u << 5)  /* march kernel: keep the appearance accumulator in registers (128 regs, 16 warps/SM)
-                                         instead of tensor memory (default for the 16/48-channel specialisation)  */
 #define TVM_F_POINT_SAMPLES (1u << 3) /* sampler of sample_point_color (tensorBase.py:623-638): n_samples samples
                                          centred on the ray origin, z_i = stepSize*(i - n_samples/2)          */
 

@@ -15,7 +15,6 @@ ap.add_argument("--no-early", action="store_true")
 ap.add_argument("--tag", default=os.environ.get("TVM_B200_LIB", "default"))
 ap.add_argument("--tile", default="", help="WxH: reorder the 800x800 rays so 32 consecutive rays form a WxH pixel tile (locality probe)")
 ap.add_argument("--march-only", action="store_true")
-ap.add_argument("--reg-acc", action="store_true", help="register accumulator instead of the TMEM one")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 fld = fx.make_field([300] * 3, density_shift=0.0)
@@ -37,7 +36,7 @@ ws = torch.empty((need.value,), dtype=torch.uint8, device=dev)
 bg = m._bg(None, True, dev)
 rgb = torch.empty((n, 3), device=dev); depth = torch.empty(n, device=dev); acc = torch.empty(n, device=dev)
 st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-fl = (0 if a.no_early else _lib.F_EARLY_TERM) | (_lib.F_REG_ACC if a.reg_acc else 0)
+fl = 0 if a.no_early else _lib.F_EARLY_TERM
 
 def march():
     _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, None, _lib.ptr(bg), fl | _lib.F_NO_SHADE,
