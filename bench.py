@@ -321,7 +321,12 @@ def extra_configs(model, dev, fx):
     # config 3 again, whole step (zero_grad, forward, loss, backward, Adam) from a CUDA graph
     model.train()
     model.zero_grad(set_to_none=True)
-    topt = torch.optim.Adam(model.get_optparam_groups(0.02, 1e-3), betas=(0.9, 0.99), capturable=True)
+    try:        # torch's fused multi-tensor Adam: one kernel over the 17.4 M parameters instead of ~10 foreach passes
+        topt = torch.optim.Adam(model.get_optparam_groups(0.02, 1e-3), betas=(0.9, 0.99), capturable=True, fused=True)
+        adam_kind = "torch fused"
+    except (RuntimeError, TypeError, ValueError):
+        topt = torch.optim.Adam(model.get_optparam_groups(0.02, 1e-3), betas=(0.9, 0.99), capturable=True)
+        adam_kind = "torch foreach"
     jit = torch.rand(4096, device=dev)
 
     def full_train_step():
@@ -334,7 +339,7 @@ def extra_configs(model, dev, fx):
     ms_eager = timeit(full_train_step, steps=10, warm=3)
     graphed_t = I.graphs.CapturedStep(full_train_step, models=[model], warmup=1)
     ms_graph = timeit(graphed_t, steps=10, warm=3)
-    out["config3_train_step_with_adam"] = {"rays": 4096, "ms_eager": ms_eager, "ms_cuda_graph": ms_graph,
+    out["config3_train_step_with_adam"] = {"rays": 4096, "adam": adam_kind, "ms_eager": ms_eager, "ms_cuda_graph": ms_graph,
                                            "rays_per_s_cuda_graph": 4096 / (ms_graph / 1e3)}
     model.eval()
     model.zero_grad(set_to_none=True)

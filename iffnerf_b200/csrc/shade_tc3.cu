@@ -6,8 +6,9 @@
 //     A_hi.B_hi + A_hi.B_lo + A_lo.B_hi          (the dropped lo.lo term is <= 2^-18 relative)
 // which reproduces the fp32 FFMA result to ~1e-6 on rgb while running on the 5th-gen tensor cores.  Operand
 // footprint doubles, so only basis_mat and W3 stay resident in shared memory; W1 / W2 (hi+lo images, 80 / 64 KB)
-// are streamed from L2 into one weight buffer per tile, W1 while the ray_feat tile is being staged and W2 under the
-// first hidden layer's epilogue.  One persistent CTA (16 warps) per SM, 128 rays per tile, TMEM lane == ray.
+// are streamed from L2 into one weight buffer per tile by TMA bulk copies (cp.async.bulk + mbarrier complete_tx) that
+// one thread fires as soon as the MMA reading the buffer has completed: W2 under the first hidden layer's epilogue, the
+// next tile's W1 under the last epilogues and the next staging; only the MMA-issuing thread ever waits for them.  One persistent CTA (16 warps) per SM, 128 rays per tile, TMEM lane == ray.
 #include "tvm_tc.cuh"
 
 namespace {
@@ -77,6 +78,16 @@ __device__ __forceinline__ void split_store1(unsigned char* hi_base, unsigned ch
     *reinterpret_cast<__nv_bfloat16*>(hi_base + off) = h;
     *reinterpret_cast<__nv_bfloat16*>(lo_base + off) = __float2bfloat16_rn(v - __bfloat162float(h));
 }
+// Asynchronous weight streaming: one thread arms the mbarrier with the byte count and fires two TMA bulk copies
+// (hi and lo image) L2 -> shared memory; nobody waits until the MMA that consumes the image is about to be issued.
+__device__ __forceinline__ void bulk_load_pair(uint32_t dst_hi, uint32_t dst_lo, const unsigned char* src, int bytes_each,
+                                               uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(2 * bytes_each) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_hi), "l"(src), "r"(bytes_each), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_lo), "l"(src + bytes_each), "r"(bytes_each), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void coop_copy(unsigned char* dst, const unsigned char* __restrict__ src, int bytes, int tid) {
     for (int i = tid * 16; i < bytes; i += TC_THREADS * 16)
         *reinterpret_cast<uint4*>(dst + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
@@ -97,7 +108,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
     unsigned char* s_a = s_w + 2 * w_half;                     // A operand: hi | lo
     float* s_bias = reinterpret_cast<float*>(s_a + 2 * a_half);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 2 * FC + 4);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);        // s_bar[0]: MMA completion, s_bar[1]: weight arrival
     unsigned char* s_ah = s_a;
     unsigned char* s_al = s_a + a_half;
 
@@ -108,6 +119,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
     }
     if (tid == 0) {
         mbar_init(smem_u32(s_bar), 1);
+        mbar_init(smem_u32(s_bar + 1), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     coop_copy(s_b0, a.wimg + L.b0, 2 * L.sz_b0, tid);
@@ -125,8 +137,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
     const uint32_t swh = smem_u32(s_w), swl = smem_u32(s_w + w_half);
     const uint32_t sb0h = smem_u32(s_b0), sb0l = smem_u32(s_b0 + L.sz_b0);
     const uint32_t sw3h = smem_u32(s_w3), sw3l = smem_u32(s_w3 + L.sz_w3);
-    uint32_t phase = 0;
+    const uint32_t wbar = smem_u32(s_bar + 1);
+    uint32_t phase = 0, wphase = 0;
     const long long n_tiles = (a.n_rays + TC_RAYS - 1) / TC_RAYS;
+    // W1 of the first tile; afterwards the weight buffer is refilled as soon as the MMA reading it has completed
+    if (tid == 0 && (long long)blockIdx.x < n_tiles) bulk_load_pair(swh, swl, a.wimg + L.w1, L.sz_w1, wbar);
     const int nbase = d.app_dim + 3;
     const int sin_f = nbase, cos_f = sin_f + d.app_dim * d.fea_pe;
     const int sin_v = cos_f + d.app_dim * d.fea_pe, cos_v = sin_v + 3 * d.view_pe;
@@ -134,9 +149,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long r = tile * TC_RAYS + row;
         const bool live = r < a.n_rays;
-        // ---- stream W1 (hi|lo) into the weight buffer; stage the ray_feat tile as split A operand (K0)
-        coop_copy(s_w, a.wimg + L.w1, L.sz_w1, tid);
-        coop_copy(s_w + w_half, a.wimg + L.w1 + L.sz_w1, L.sz_w1, tid);
+        // ---- stage the ray_feat tile as split A operand (K0); W1 (hi|lo) is already in flight into the weight buffer
         for (int kc = cg; kc < d.k0 / 8; kc += 4) {
             float v[8];
 #pragma unroll
@@ -187,12 +200,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
         tc_fence_before();
         __syncthreads();
         // ---- MMA 2: h1 = X . W1^T
-        if (tid == 0) { tc_fence_after(); issue_gemm3(tmem + COL1, sah, sal, swh, swl, d.k1, FC, bar); }
+        if (tid == 0) {
+            mbar_wait(wbar, wphase);                       // W1 has landed
+            tc_fence_after();
+            issue_gemm3(tmem + COL1, sah, sal, swh, swl, d.k1, FC, bar);
+        }
+        wphase ^= 1;
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
-        // W1 and X are consumed: stream W2 into the weight buffer under the epilogue
-        coop_copy(s_w, a.wimg + L.w2, L.sz_w2, tid);
-        coop_copy(s_w + w_half, a.wimg + L.w2 + L.sz_w2, L.sz_w2, tid);
+        // W1 and X are consumed: W2 streams into the weight buffer under the epilogue
+        if (tid == 0) bulk_load_pair(swh, swl, a.wimg + L.w2, L.sz_w2, wbar);
         {
             const int cb = cg * 32;
             float v[32];
@@ -209,9 +226,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
         tc_fence_before();
         __syncthreads();
         // ---- MMA 3: h2 = h1 . W2^T
-        if (tid == 0) { tc_fence_after(); issue_gemm3(tmem + COL2, sah, sal, swh, swl, FC, FC, bar); }
+        if (tid == 0) {
+            mbar_wait(wbar, wphase);                       // W2 has landed
+            tc_fence_after();
+            issue_gemm3(tmem + COL2, sah, sal, swh, swl, FC, FC, bar);
+        }
+        wphase ^= 1;
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
+        // W2 is consumed: W1 of this CTA's next tile streams in under the remaining epilogues and the next staging
+        if (tid == 0 && tile + gridDim.x < n_tiles) bulk_load_pair(swh, swl, a.wimg + L.w1, L.sz_w1, wbar);
         {
             const int cb = cg * 32;
             float v[32];
@@ -262,7 +286,7 @@ size_t tc3_smem_bytes(const TcDims& d) {
     const int kmax = d.k0 > d.k1 ? (d.k0 > FC ? d.k0 : FC) : (d.k1 > FC ? d.k1 : FC);
     const size_t a_half = (size_t)TC_RAYS * kmax * 2;
     const size_t w_half = (size_t)FC * (d.k1 > FC ? d.k1 : FC) * 2;
-    return 2 * (size_t)L.sz_b0 + 2 * (size_t)L.sz_w3 + 2 * w_half + 2 * a_half + (2 * FC + 4) * 4 + 16;
+    return 2 * (size_t)L.sz_b0 + 2 * (size_t)L.sz_w3 + 2 * w_half + 2 * a_half + (2 * FC + 4) * 4 + 32;
 }
 
 }  // namespace
