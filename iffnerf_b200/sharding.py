@@ -28,10 +28,27 @@ def shard_tiles(n_rays: int, world: int, rank: int, tile: int = DEFAULT_TILE) ->
     return [(t * tile, min((t + 1) * tile, n_rays)) for t in range(rank, n_tiles, world)]
 
 
+_index_cache = {}
+
+
 def shard_index(n_rays: int, world: int, rank: int, tile: int = DEFAULT_TILE, device=None) -> torch.Tensor:
-    """Flat ray indices owned by `rank` (concatenation of its tiles, ascending)."""
-    parts = [torch.arange(a, b, device=device) for a, b in shard_tiles(n_rays, world, rank, tile)]
-    return torch.cat(parts) if parts else torch.empty(0, dtype=torch.long, device=device)
+    """Flat ray indices owned by `rank` (concatenation of its tiles, ascending).  Built with a handful of vectorised ops
+    (local position j -> ((j // tile) * world + rank) * tile + j % tile) and cached per (n, world, rank, tile, device):
+    a 1080p image has 507 tiles, and one `arange` launch per tile made the sharded render host-bound."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    key = (n_rays, world, rank, tile, str(device))
+    hit = _index_cache.get(key)
+    if hit is None:
+        n_tiles = (n_rays + tile - 1) // tile
+        mine = len(range(rank, n_tiles, world))
+        j = torch.arange(mine * tile, device=device)
+        g = (torch.div(j, tile, rounding_mode="floor") * world + rank) * tile + j % tile
+        hit = g[g < n_rays]
+        if len(_index_cache) > 64:
+            _index_cache.clear()
+        _index_cache[key] = hit
+    return hit
 
 
 def local_rays(rays: torch.Tensor, world: int, rank: int, tile: int = DEFAULT_TILE) -> Tuple[torch.Tensor, torch.Tensor]:
