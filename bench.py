@@ -288,7 +288,11 @@ def extra_configs(model, dev, fx):
         rgb = model(r, bg_color=bg, is_train=False)[0]
         torch.mean((rgb - ptarget) ** 2).backward()
     ms = timeit(pose_step, steps=5, warm=2)
-    out["config5_pose_step_64x1024"] = {"rays": 64 * 1024, "ms_fwd_bwd_to_rays": ms, "rays_per_s": 65536 / (ms / 1e3)}
+    model.eval_sample_outputs = False      # the pose loop reads rgb / opacity only: early termination in both directions
+    ms_et = timeit(pose_step, steps=5, warm=2)
+    out["config5_pose_step_64x1024"] = {"rays": 64 * 1024, "ms_fwd_bwd_to_rays": ms, "rays_per_s": 65536 / (ms / 1e3),
+                                        "ms_without_sample_outputs": ms_et,
+                                        "rays_per_s_without_sample_outputs": 65536 / (ms_et / 1e3)}
     # config 5 as the reference's loop runs it (inerf/estimate_pose_inerf.py:103-186): ONE pose, 1024 pixels per step,
     # fused ray generation -> render -> MSE -> backward to the pose -> Adam; eager launches vs one CUDA-graph replay
     import numpy as np
@@ -314,8 +318,9 @@ def extra_configs(model, dev, fx):
     ms_eager = timeit(inerf_step, steps=20, warm=3)
     graphed = I.graphs.CapturedStep(inerf_step, models=[model], warmup=1)
     ms_graph = timeit(graphed, steps=20, warm=3)
-    out["config5_inerf_step_1024"] = {"rays": 1024, "ms_eager": ms_eager, "ms_cuda_graph": ms_graph,
+    out["config5_inerf_step_1024"] = {"rays": 1024, "sample_outputs": False, "ms_eager": ms_eager, "ms_cuda_graph": ms_graph,
                                       "rays_per_s_cuda_graph": 1024 / (ms_graph / 1e3)}
+    model.eval_sample_outputs = True
     for p in model.parameters():
         p.requires_grad_(True)
     # config 3 again, whole step (zero_grad, forward, loss, backward, Adam) from a CUDA graph

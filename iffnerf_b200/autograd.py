@@ -29,7 +29,9 @@ def _mlp_params(model):
 
 
 class _Render(torch.autograd.Function):
-    """inputs: model, rays, S, jitter, bg, flags, 12 factors, basis, w1, b1, w2, b2, w3, b3"""
+    """inputs: model, rays, S, jitter, bg, flags, 12 factors, basis, w1, b1, w2, b2, w3, b3.
+    flags & F_EARLY_TERM: the caller does not want the per-sample outputs (alpha / z_vals / dists come back as None),
+    so forward and backward both stop a ray at T < early_term_eps."""
 
     @staticmethod
     def forward(ctx, model, rays, S, jitter, bg, flags, *params):
@@ -45,7 +47,8 @@ class _Render(torch.autograd.Function):
         rgb = torch.empty((n, 3), device=dev)
         depth = torch.empty((n,), device=dev)
         acc = torch.empty((n,), device=dev)
-        alpha, z, dists = (torch.empty((n, S), device=dev) for _ in range(3))
+        want_samples = not (flags & _lib.F_EARLY_TERM)
+        alpha, z, dists = (torch.empty((n, S), device=dev) for _ in range(3)) if want_samples else (None, None, None)
         jit = None if jitter is None else jitter.detach().to(dev).float().reshape(-1).contiguous()
         bg_c = _c(bg)
         _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], S, _lib.ptr(jit),
@@ -56,7 +59,10 @@ class _Render(torch.autograd.Function):
         ctx.ray_cols = rays.shape[1]
         ctx.flags = flags
         ctx.keys = (model._packed_key, model._mlp_key)
-        ctx.mark_non_differentiable(depth, z, dists)
+        if want_samples:
+            ctx.mark_non_differentiable(depth, z, dists)
+        else:
+            ctx.mark_non_differentiable(depth)
         return rgb, depth, acc, alpha, z, dists
 
     @staticmethod
@@ -117,13 +123,16 @@ class _Render(torch.autograd.Function):
         return (None, d_rays, None, None, None, None, *factor_grads, g_basis, *mlp_grads)
 
 
-def render_with_grad(model, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples=False):
-    """Differentiable TensorBase.forward (models/tensorBase.py:775-917): 6-tuple, `depth_map` without grad."""
+def render_with_grad(model, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples=False, want_samples=True):
+    """Differentiable TensorBase.forward (models/tensorBase.py:775-917): 6-tuple, `depth_map` without grad.
+    want_samples=False (eval only): alpha / z_vals / dists are None and rays terminate early in both directions."""
     S = N_samples if N_samples > 0 else model.nSamples
     planes, lines = model._factor_params()
     rays = rays_chunk if rays_chunk.dtype == torch.float32 else rays_chunk.float()
     bg = model._bg(bg_color, white_bg, rays.device)
     flags = _lib.F_POINT_SAMPLES if point_samples else 0
+    if not want_samples and model.early_term_eps > 0:
+        flags |= _lib.F_EARLY_TERM
     return _Render.apply(model, rays, S, jitter, bg, flags, *planes, *lines, model.basis_mat.weight,
                          *_mlp_params(model))
 

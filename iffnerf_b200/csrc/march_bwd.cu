@@ -105,7 +105,11 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, TVM_BWD_MIN_BLOCKS) march_bwd_
         float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};   // sum dL/dp and sum z*dL/dp (sub==0 lanes)
         const TvmBlockMask bm = tvm_block_prepass(f, ray, S, lane);
 
+        // TVM_F_EARLY_TERM (only valid without a loss on alpha, and with a forward that used it too): samples behind
+        // T < eps carry weights <= eps, their share of every gradient is below eps relative — stop like the forward
+        const bool early = (a.flags & TVM_F_EARLY_TERM) && !a.d_alpha;
         for (int i0 = 0; i0 < S; i0 += 32) {
+            if (early && T < f.early_term_eps) break;
             if (!bm.test(i0 >> 5)) continue;
             const int i = i0 + lane;
             const bool in_range = i < S;

@@ -116,6 +116,10 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
 
     # launch-size cap for the chunk-free eval path (rays per kernel launch)
     max_launch_rays = 1 << 20
+    # eval-mode forward(): also return the per-sample tensors alpha / z_vals / dists [N,S] like the reference (True).
+    # False returns None for them; rays then terminate at T < early_term_eps in forward AND backward, which is what the
+    # pose-refinement loop wants (inerf/estimate_pose_inerf.py:166 reads rgb and opacity only).
+    eval_sample_outputs = True
     ref_kernel = True            # `Ref` head, eval: fused tail kernel (False: the torch-op tail, kept for cross-checks)
     # transmittance below which an eval ray stops marching (error on rgb/acc <= this value)
     early_term_eps = 1e-5
@@ -632,14 +636,18 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
             jitter = None
         needs_grad = torch.is_grad_enabled() and (
             rays_chunk.requires_grad or any(p.requires_grad for p in self.parameters()))
+        want_samples = is_train or point_samples or bool(self.eval_sample_outputs)
         if needs_grad:
             from .autograd import render_with_grad, render_with_grad_torch_tail
-            fn = render_with_grad if self.native_shade else render_with_grad_torch_tail
-            out = fn(self, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples)
+            if self.native_shade:
+                out = render_with_grad(self, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples,
+                                       want_samples=want_samples)
+            else:
+                out = render_with_grad_torch_tail(self, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples)
         else:
             o = self.render_eval(rays_chunk, N_samples=N_samples, white_bg=white_bg, bg_color=bg_color, jitter=jitter,
-                                 sample_outputs=True, point_samples=point_samples)
-            out = (o["rgb_map"], o["depth_map"], o["acc_map"], o["alpha"], o["z_vals"], o["dists"])
+                                 sample_outputs=want_samples, point_samples=point_samples)
+            out = (o["rgb_map"], o["depth_map"], o["acc_map"], o.get("alpha"), o.get("z_vals"), o.get("dists"))
         if point_samples:
             # the reference's sampler returns ONE broadcast row of z values ([1,S], tensorBase.py:628-638)
             out = out[:4] + (out[4][:1], out[5][:1])

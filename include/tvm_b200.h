@@ -155,7 +155,8 @@ int tvm_render_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays
 
 /* Backward of the march stage: given d(ray_feat) [n][sum(n_app)], d(acc) [n] and d(alpha) [n][n_samples]
  * (any NULL = zero) it re-marches the rays and scatters into g_factors (packed layout, pre-zeroed or
- * accumulating) and, when g_rays != NULL, writes d(rays) [n][6] (pose mode). ws is the forward workspace
+ * accumulating) and, when g_rays != NULL, writes d(rays) [n][6] (pose mode).  With TVM_F_EARLY_TERM (and
+ * d_alpha == NULL) the re-march stops at T < early_term_eps like the forward it pairs with.  ws is the forward workspace
  * (tvm_render_fwd with the same rays / n_samples / jitter; replaces autograd through grid_sampler_2d_backward,
  * cumprod, softplus ... driven by train.py:338 and inerf/estimate_pose_inerf.py:178). */
 int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,

@@ -91,6 +91,35 @@ def test_pose_gradients_match_reference_golden(lego, dev):
     assert np.abs(got - ref).max() <= 5e-3 * scale, (np.abs(got - ref).max(), scale)
 
 
+def test_pose_gradients_with_early_termination(lego, dev):
+    """eval_sample_outputs=False: alpha / z_vals / dists come back as None and both directions stop a ray at
+    T < early_term_eps; rgb and d(rays) stay inside the same tolerances against the reference golden."""
+    fld, rays, m = lego
+    g = H.golden("c5_pose")
+    sub, _ = fx.subsample(rays, 512, seed=2)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    m.eval_sample_outputs = False
+    try:
+        r = sub.to(dev).requires_grad_(True)
+        rgb, depth, acc, alpha, z, dists = m(r, bg_color=torch.from_numpy(g["bg"]).to(dev), is_train=False)
+        assert alpha is None and z is None and dists is None
+        loss = torch.mean((rgb - torch.from_numpy(g["target"]).to(dev)) ** 2)
+        loss.backward()
+        with torch.no_grad():
+            o = m(sub.to(dev), bg_color=torch.from_numpy(g["bg"]).to(dev), is_train=False)
+        assert o[3] is None and (o[0] - rgb).abs().max().item() <= 1e-6
+    finally:
+        m.eval_sample_outputs = True
+        for p in m.parameters():
+            p.requires_grad_(True)
+    assert np.abs(rgb.detach().cpu().numpy() - g["rgb_map"]).max() <= 1e-4
+    assert np.abs(acc.detach().cpu().numpy() - g["acc_map"]).max() <= 1e-4
+    ref = g["d_rays"]
+    scale = np.abs(ref).max()
+    assert np.abs(r.grad.cpu().numpy() - ref).max() <= 5e-3 * scale
+
+
 def _pose_rays(base_c2w, w, t, dirs, radii):
     """Minimal SE(3) perturbation (stand-in for inerf.CameraTransfer): c2w = [exp(skew(w)) R | p + t]."""
     zero = torch.zeros((), dtype=w.dtype, device=w.device)
