@@ -293,6 +293,19 @@ def extra_configs(model, dev, fx):
     out["config5_pose_step_64x1024"] = {"rays": 64 * 1024, "ms_fwd_bwd_to_rays": ms, "rays_per_s": 65536 / (ms / 1e3),
                                         "ms_without_sample_outputs": ms_et,
                                         "rays_per_s_without_sample_outputs": 65536 / (ms_et / 1e3)}
+    # the IFFNeRF ray-bank query (pose_estimation/sampling.py:237-251): 540 k 6-column rays from
+    # surface points, 20 samples centred on each origin (sample_point_color), regenerated 150x per object
+    gq = torch.Generator().manual_seed(11)
+    pq = torch.randn(540000, 3, generator=gq)
+    pq = pq / pq.norm(dim=-1, keepdim=True) * (0.55 + 0.5 * torch.rand(540000, 1, generator=gq))
+    dq = torch.randn(540000, 3, generator=gq)
+    rays6 = torch.cat([pq, dq / dq.norm(dim=-1, keepdim=True)], -1).to(dev)
+
+    def raybank():
+        with torch.no_grad():
+            return model(rays6, N_samples=20, sample_func=model.sample_point_color, white_bg=True)
+    ms = timeit(raybank, steps=10, warm=3)
+    out["iffnerf_raybank_540k_x20"] = {"rays": 540000, "n_samples": 20, "ms": ms, "rays_per_s": 540000 / (ms / 1e3)}
     # config 5 as the reference's loop runs it (inerf/estimate_pose_inerf.py:103-186): ONE pose, 1024 pixels per step,
     # fused ray generation -> render -> MSE -> backward to the pose -> Adam; eager launches vs one CUDA-graph replay
     import numpy as np

@@ -203,12 +203,15 @@ static inline void tvm_host_add4(float4* p, float4 v) { p->x += v.x; p->y += v.y
 // One float4 channel slice j of plane/line pair k: given the upstream gradient `up` on (plane (x) line)[channels],
 // scatter into gP/gL and accumulate d/dn.  Returns (plane (x) line) for this slice.
 template <bool SCATTER, bool POSE>
-TVM_HD float4 vm_slice_bwd(const tvm_field_desc& f, const float4* __restrict__ P, const float4* __restrict__ Ln,
-                           float4* __restrict__ gP, float4* __restrict__ gL, const SampleTaps& s, const PlaneTaps& t,
+TVM_HD float4 vm_slice_bwd(const tvm_field_desc& f, const float4* __restrict__ F4, float4* __restrict__ G4,
+                           unsigned poff, unsigned loff, const SampleTaps& s, const PlaneTaps& t,
                            int C4, int j, float4 up, int k, float dn[3]) {
-    const float4* pb = P + (t.pbase + (unsigned)j);
-    const float4* pb1 = P + (t.pbase + t.prow + (unsigned)j);
-    const float4* lb = Ln + (t.lbase + (unsigned)j);
+    // one base pointer for the factors and one for the gradient buffer (same packed layout): every address is a
+    // 32-bit float4 index off it, like the forward
+    const unsigned ip = t.pbase + poff + (unsigned)j, ip1 = ip + t.prow, il = t.lbase + loff + (unsigned)j;
+    const float4* pb = F4 + ip;
+    const float4* pb1 = F4 + ip1;
+    const float4* lb = F4 + il;
     const float4 a = TVM_LDG4(pb);
     const float4 b = TVM_LDG4(pb + C4);
     const float4 c = TVM_LDG4(pb1);
@@ -222,9 +225,9 @@ TVM_HD float4 vm_slice_bwd(const tvm_field_desc& f, const float4* __restrict__ P
     const float4 up_ln = f4_mul(up, ln);        // d/d(plane value)
     const float4 up_pl = f4_mul(up, pl);        // d/d(line value)
     if (SCATTER) {
-        float4* gpb = gP + (t.pbase + (unsigned)j);
-        float4* gpb1 = gP + (t.pbase + t.prow + (unsigned)j);
-        float4* glb = gL + (t.lbase + (unsigned)j);
+        float4* gpb = G4 + ip;
+        float4* gpb1 = G4 + ip1;
+        float4* glb = G4 + il;
         TVM_RED4(gpb, f4_scale(t.w00, up_ln));
         TVM_RED4(gpb + C4, f4_scale(t.w01, up_ln));
         TVM_RED4(gpb1, f4_scale(t.w10, up_ln));
@@ -258,10 +261,8 @@ TVM_HD float density_bwd(const tvm_field_desc& f, const float n[3], float dfeat,
         if (sub < C4) {
             const PlaneTaps t = make_taps(f, st, k, C4);
             const float4 v = vm_slice_bwd<SCATTER, POSE>(
-                f, reinterpret_cast<const float4*>(f.factors + f.dplane_off[k]),
-                reinterpret_cast<const float4*>(f.factors + f.dline_off[k]),
-                SCATTER ? reinterpret_cast<float4*>(gbuf + f.dplane_off[k]) : nullptr,
-                SCATTER ? reinterpret_cast<float4*>(gbuf + f.dline_off[k]) : nullptr, st, t, C4, sub, up, k, dn);
+                f, reinterpret_cast<const float4*>(f.factors), reinterpret_cast<float4*>(gbuf),
+                (unsigned)(f.dplane_off[k] >> 2), (unsigned)(f.dline_off[k] >> 2), st, t, C4, sub, up, k, dn);
             tot += (v.x + v.y) + (v.z + v.w);
         }
     }
@@ -283,10 +284,8 @@ TVM_HD float app_bwd(const tvm_field_desc& f, const float n[3], float w, int sub
             const int j = sub + 4 * gi;
             if (j < C4) {
                 const float4 phi = vm_slice_bwd<SCATTER, POSE>(
-                    f, reinterpret_cast<const float4*>(f.factors + f.aplane_off[k]),
-                    reinterpret_cast<const float4*>(f.factors + f.aline_off[k]),
-                    SCATTER ? reinterpret_cast<float4*>(gbuf + f.aplane_off[k]) : nullptr,
-                    SCATTER ? reinterpret_cast<float4*>(gbuf + f.aline_off[k]) : nullptr, st, t, C4, j,
+                    f, reinterpret_cast<const float4*>(f.factors), reinterpret_cast<float4*>(gbuf),
+                    (unsigned)(f.aplane_off[k] >> 2), (unsigned)(f.aline_off[k] >> 2), st, t, C4, j,
                     f4_scale(w, gF[k][gi]), k, dn);
                 dot += f4_dot(gF[k][gi], phi);
             }
