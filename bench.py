@@ -450,10 +450,24 @@ def run_ours(args, rank, world, local_rank):
         depth_host.copy_(depth, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
 
+    # informational: the same image rendered from the POSE (fused on-device ray generation, no ray upload), result to host
+    Kc = torch.tensor([[[400.0 / math.tan(0.5 * 0.6911112), 0.0, 400.0], [0.0, 400.0 / math.tan(0.5 * 0.6911112), 400.0],
+                        [0.0, 0.0, 1.0]]])
+    pose_dev = torch.cat([fx.orbit_pose(35.0 + 45.0 * rank), torch.tensor([[0.0, 0.0, 0.0, 1.0]])], 0).to(dev)
+
+    def step_from_pose():
+        with torch.no_grad():
+            r = I.pixel_rays(Kc, pose_dev, None, image_wh=(W, H), renormalize=False)
+            rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(r, model, white_bg=True, device=dev)
+        rgb_host.copy_(rgb, non_blocking=True)
+        depth_host.copy_(depth, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
     with ClockSampler(local_rank) as clk:
         ms_dev = timed(step_device, args.steps, args.warmup)
     ms_march = timed(step_march_only, args.steps, 1)
     ms_e2e = timed(step_e2e, args.steps, 1)
+    ms_pose = timed(step_from_pose, args.steps, 1)
     shade_default = model._shade_mode()          # "tc3": tensor cores, bf16x3 split operands, fp32 accumulate
     # the same step with the other shading kernels: fp32 SIMT FFMA, and plain-bf16 tensor cores (1e-2 mode)
     model.mlp_precision = "fp32"
@@ -529,6 +543,8 @@ def run_ours(args, rank, world, local_rank):
                 "e2e": {"value": world * n * K / (ms_e2e / 1e3), "unit": UNIT,
                         "h2d_bytes_per_step": int(rays_host.numel() * 4), "d2h_bytes_per_step": int(n * 16),
                         "ms_per_step": ms_e2e / K},
+                "render_from_pose": {"ms_per_image": ms_pose / K, "rays_per_s": n * K / (ms_pose / 1e3),
+                                     "note": "rank 0: pixel_rays(K, c2w) on the device + render + D2H of rgb/depth; no ray upload"},
                 "gpu_launches": 2 * K,
                 "roofline": {"bound": "hbm", "kernel": "march_fwd_kernel", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
