@@ -133,6 +133,28 @@ def test_no_cpu_fallback_and_unsupported_modes_raise():
         I.OctreeRender_trilinear_fast(rays, m, device="cpu")
     with pytest.raises(NotImplementedError):
         _module(shadingMode="SH")
+    # the ray generator and the point queries have no CPU path either
+    K = torch.tensor([[[100.0, 0.0, 50.0], [0.0, 100.0, 50.0], [0.0, 0.0, 1.0]]])
+    with pytest.raises(_lib.TvmError):
+        I.pixel_rays(K, torch.eye(4), torch.zeros(4, 2, dtype=torch.int32))
+    with pytest.raises(_lib.TvmError):
+        m.compute_appfeature(torch.zeros(4, 3))
+    with pytest.raises(_lib.TvmError):
+        m.compute_alpha(torch.zeros(4, 3))
+
+
+def test_ray_generator_argument_checks():
+    import iffnerf_b200 as I
+    K = torch.tensor([[[100.0, 0.0, 50.0], [0.0, 100.0, 50.0], [0.0, 0.0, 1.0]]])
+    with pytest.raises(ValueError):
+        I.pixel_rays(K, torch.eye(4), None)                    # neither pixels nor image_wh
+    with pytest.raises(ValueError):
+        I.pixel_rays(K, torch.eye(4)[None].repeat(2, 1, 1), None, image_wh=(8, 8))   # full image takes one pose
+    from iffnerf_b200 import raygen
+    k1 = raygen._kinv(K)
+    assert raygen._kinv(K) is k1                                # cached per (tensor, version)
+    ref = torch.inverse(K[0])
+    assert max(abs(k1[i] - ref.reshape(-1)[i].item()) for i in range(9)) < 1e-9
 
 
 def test_product_package_never_imports_oracle():

@@ -20,7 +20,10 @@ def test_shard_tiles_partition_every_ray_exactly_once():
             idx = sharding.shard_index(n, world, r, tile)
             seen[idx] += 1
             sizes.append(idx.numel())
-            assert idx.numel() == sum(b - a for a, b in sharding.shard_tiles(n, world, r, tile))
+            tiles = sharding.shard_tiles(n, world, r, tile)
+            assert idx.numel() == sum(b - a for a, b in tiles)
+            ref = torch.cat([torch.arange(a, b) for a, b in tiles]) if tiles else torch.empty(0, dtype=torch.long)
+            assert torch.equal(idx, ref)                    # the vectorised index == the concatenated tile ranges
         assert bool((seen == 1).all())
         assert max(sizes) - min(sizes) <= tile              # balanced to within one tile
 
