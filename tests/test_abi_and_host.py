@@ -143,6 +143,19 @@ def test_no_cpu_fallback_and_unsupported_modes_raise():
         m.compute_alpha(torch.zeros(4, 3))
 
 
+def test_missing_library_fails_loudly(tmp_path):
+    """No CUDA library -> TvmError naming the build command; nothing falls back to another implementation."""
+    import subprocess, sys
+    code = ("import os, sys; os.environ['TVM_B200_LIB'] = sys.argv[1]\n"
+            "from iffnerf_b200 import _lib\n"
+            "try:\n    _lib.load()\nexcept _lib.TvmError as e:\n"
+            "    assert 'no CPU fallback' in str(e) and 'iffnerf_b200.build' in str(e); print('loud')\n"
+            "else:\n    raise SystemExit('load() succeeded without a library')\n")
+    out = subprocess.run([sys.executable, "-c", code, str(tmp_path / "absent.so")], check=True, cwd=ROOT,
+                         capture_output=True, text=True).stdout
+    assert "loud" in out
+
+
 def test_ray_generator_argument_checks():
     import iffnerf_b200 as I
     K = torch.tensor([[[100.0, 0.0, 50.0], [0.0, 100.0, 50.0], [0.0, 0.0, 1.0]]])
