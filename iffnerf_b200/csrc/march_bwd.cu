@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, TVM_BWD_MIN_BLOCKS) march_bwd_
     __shared__ float4 s_slot[BWD_WARPS][32];
     __shared__ float s_ret[BWD_WARPS][32];
     __shared__ float s_z[BWD_WARPS][32];
+    __shared__ float4 s_dn[BWD_WARPS][32];      // pose-only mode: d(sigma_feature)/d(normalised coords) per sample
     const tvm_field_desc& f = a.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 3, quad = lane >> 2;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -132,12 +133,22 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, TVM_BWD_MIN_BLOCKS) march_bwd_
                 for (int g = 0; g * 8 < nv; ++g) {
                     const int ci = g * 8 + quad;
                     float part = 0.f;
+                    float dq[3] = {0.f, 0.f, 0.f};
                     if (ci < nv) {
                         const float4 s = s_slot[warp][ci];
                         const float q[3] = {s.x, s.y, s.z};
-                        part = density_partial<CS4>(f, q, sub);
+                        // pose-only mode (frozen factors): the coordinate derivative of the feature does not depend on
+                        // the upstream scalar, so it is taken here, on the texels this pass loads anyway, and the
+                        // second density pass below disappears
+                        if (POSE && !SCATTER) part = density_bwd<false, true, CS4>(f, q, 1.0f, sub, nullptr, dq);
+                        else part = density_partial<CS4>(f, q, sub);
                     }
                     part = quad_sum(part);
+                    if (POSE && !SCATTER) {
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) dq[cc] = quad_sum(dq[cc]);
+                        if (sub == 0 && ci < nv) s_dn[warp][ci] = make_float4(dq[0], dq[1], dq[2], 0.f);
+                    }
                     if (sub == 0 && ci < nv) s_ret[warp][ci] = part;
                 }
                 __syncwarp();
@@ -207,8 +218,21 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, TVM_BWD_MIN_BLOCKS) march_bwd_
                 if (a.d_alpha && in_range) dalpha += __ldg(a.d_alpha + r * S + i);
                 const float dsigma = dalpha * delta * (1.f - alpha);
                 const float dfeat = keep ? dsigma * tvm_density_grad(f, feat) : 0.f;
+                // ---- density: pose-only mode finishes in the owning lane (dL/dn = dfeat * d feat/dn from the recompute pass)
+                if (POSE && !SCATTER) {
+                    if (keep) {
+                        const float4 dnv = s_dn[warp][rank];
+                        const float dnc[3] = {dnv.x, dnv.y, dnv.z};
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) {
+                            const float dp = dfeat * dnc[cc] * f.inv_aabb[cc];
+                            go[cc] += dp;
+                            gd[cc] = fmaf(dp, z, gd[cc]);
+                        }
+                    }
+                }
                 // ---- density scatter (quads again)
-                const bool live = keep && dfeat != 0.f;
+                const bool live = !(POSE && !SCATTER) && keep && dfeat != 0.f;
                 const unsigned dmask = __ballot_sync(FULL, live);
                 if (dmask) {
                     const int nd = __popc(dmask), rankd = __popc(dmask & lt_mask);

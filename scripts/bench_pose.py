@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Pose-mode step (BASELINE config 5: 64 x 1024 rays, frozen field, gradient w.r.t. the rays) — run it under
+`ncu --metrics gpu__time_duration.sum` for the per-kernel split, or plainly for the step time."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from oracle import fixtures as fx
+from tests import helpers as H
+dev = torch.device("cuda:0")
+fld = fx.make_field([300] * 3, density_shift=0.0)
+m = H.module_from_field(fld, dev)
+m.eval()
+for p in m.parameters():
+    p.requires_grad_(False)
+m.eval_sample_outputs = "--samples" in sys.argv
+g = torch.Generator().manual_seed(0)
+allrays = fx.config2_rays()
+prays = allrays[torch.randint(0, allrays.shape[0], (64 * 1024,), generator=g)].to(dev)
+target = torch.rand(64 * 1024, 3, device=dev)
+bg = torch.rand(3, device=dev)
+def step():
+    r = prays.clone().requires_grad_(True)
+    rgb = m(r, bg_color=bg, is_train=False)[0]
+    torch.mean((rgb - target) ** 2).backward()
+for _ in range(3): step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5): step()
+e1.record(); torch.cuda.synchronize()
+print(json.dumps({"sample_outputs": m.eval_sample_outputs, "pose_step_ms": round(e0.elapsed_time(e1) / 5, 3)}))
