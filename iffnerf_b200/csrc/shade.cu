@@ -86,6 +86,24 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const __grid_cons
     float* sH = sF;
     const long long r0 = (long long)blockIdx.x * SH_RAYS;
 
+    // tiles without a single appearance sample (background) skip the MLP, as the reference does for such rays
+    // (tensorBase.py:876-896): rgb = bg * (1 - acc)
+    {
+        const long long r = r0 + tid;
+        const bool live = tid < SH_RAYS && r < a.n_rays;
+        if (!__syncthreads_or(live && __ldg(a.app_count + r) > 0)) {
+            if (live) {
+                const float ac = __ldg(a.acc + r);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) a.rgb[r * 3 + c] = fminf(fmaxf(__ldg(a.bg + c) * (1.f - ac), 0.f), 1.f);
+                const float last = __ldg(a.rays + r * a.ray_stride + a.ray_stride - 1);
+                if (a.depth_out) a.depth_out[r] = __ldg(a.depth + r) + (1.f - ac) * last;
+                if (a.acc_out) a.acc_out[r] = ac;
+            }
+            return;
+        }
+    }
+
     for (int i = tid; i < a.app_dim * ta; i += SH_THREADS) {
         const int j = i / ta, c = i - j * ta;
         sB[c * 32 + j] = __ldg(a.basis + i);

@@ -90,6 +90,15 @@ __global__ void __launch_bounds__(REF_THREADS) shade_ref_kernel(const __grid_con
     // persistent CTAs: the 34 KB of weights are staged once, then the CTA walks 128-ray tiles
     for (long long r = (long long)blockIdx.x * REF_THREADS + threadIdx.x; r < a.n; r += (long long)gridDim.x * REF_THREADS) {
 
+    const float* rp = a.rays + r * a.ray_stride;
+    if (a.app_count[r] <= 0) {       // no appearance sample: the head is not evaluated (tensorBase.py:876-896), rgb = bg (1 - acc)
+        const float acc0 = a.acc[r];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) a.rgb[r * 3 + o] = fminf(fmaxf(__ldg(a.bg + o) * (1.0f - acc0), 0.f), 1.f);
+        a.depth[r] = a.depth_part[r] + (1.0f - acc0) * __ldg(rp + a.ray_stride - 1);
+        if (a.acc_out) a.acc_out[r] = acc0;
+        continue;
+    }
     // ---- feat = basis_mat . ray_feat
     float F[IN4];
 #pragma unroll
@@ -103,7 +112,6 @@ __global__ void __launch_bounds__(REF_THREADS) shade_ref_kernel(const __grid_con
             F[i] = fmaf(b.x, x.x, fmaf(b.y, x.y, fmaf(b.z, x.z, fmaf(b.w, x.w, F[i]))));
         }
     }
-    const float* rp = a.rays + r * a.ray_stride;
     const float v[3] = {__ldg(rp + 3), __ldg(rp + 4), __ldg(rp + 5)};
 
     // ---- the ten scalar heads

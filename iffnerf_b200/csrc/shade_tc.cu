@@ -90,6 +90,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long r = tile * TC_RAYS + row;          // this thread's ray == its TMEM lane
         const bool live = r < a.n_rays;
+        // tiles without a single appearance sample need no GEMM (the reference skips the MLP for such rays too,
+        // tensorBase.py:876-896): rgb = bg * (1 - acc)
+        if (!__syncthreads_or(live && __ldg(a.app_count + r) > 0)) {
+            if (cg == 0 && live) {
+                const float ac = __ldg(a.acc + r);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) a.rgb[r * 3 + c] = fminf(fmaxf(__ldg(a.bg + c) * (1.f - ac), 0.f), 1.f);
+                const float last = __ldg(a.rays + r * a.ray_stride + a.ray_stride - 1);
+                if (a.depth_out) a.depth_out[r] = __ldg(a.depth + r) + (1.f - ac) * last;
+                if (a.acc_out) a.acc_out[r] = ac;
+            }
+            continue;
+        }
         // ---- stage 0: ray_feat row -> bf16 A operand (K0 columns); the 4 column groups interleave the 16-B chunks
         for (int kc = cg; kc < d.k0 / 8; kc += 4) {
             float v[8];

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
     const long long n_tiles = (a.n_rays + TC_RAYS - 1) / TC_RAYS;
     // W1 of the first tile; afterwards the weight buffer is refilled as soon as the MMA reading it has completed
     if (tid == 0 && (long long)blockIdx.x < n_tiles) bulk_load_pair(swh, swl, a.wimg + L.w1, L.sz_w1, wbar);
+    bool w1_in_flight = (long long)blockIdx.x < n_tiles;       // uniform: a W1 copy is armed and not yet consumed
     const int nbase = d.app_dim + 3;
     const int sin_f = nbase, cos_f = sin_f + d.app_dim * d.fea_pe;
     const int sin_v = cos_f + d.app_dim * d.fea_pe, cos_v = sin_v + 3 * d.view_pe;
@@ -149,6 +150,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long r = tile * TC_RAYS + row;
         const bool live = r < a.n_rays;
+        // ---- tiles without a single appearance sample (background: the reference skips the MLP for such rays too,
+        // tensorBase.py:876-896) need no GEMM: rgb = bg * (1 - acc).  The W1 copy already in flight simply stays in the
+        // weight buffer for the next tile that is shaded.
+        if (!__syncthreads_or(live && __ldg(a.app_count + r) > 0)) {
+            if (cg == 0 && live) {
+                const float ac = __ldg(a.acc + r);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) a.rgb[r * 3 + c] = fminf(fmaxf(__ldg(a.bg + c) * (1.f - ac), 0.f), 1.f);
+                const float last = __ldg(a.rays + r * a.ray_stride + a.ray_stride - 1);
+                if (a.depth_out) a.depth_out[r] = __ldg(a.depth + r) + (1.f - ac) * last;
+                if (a.acc_out) a.acc_out[r] = ac;
+            }
+            continue;
+        }
+        if (!w1_in_flight) {          // the previous shaded tile was this CTA's last by its own count, but this one follows
+            if (tid == 0) bulk_load_pair(swh, swl, a.wimg + L.w1, L.sz_w1, wbar);
+            w1_in_flight = true;
+        }
         // ---- stage the ray_feat tile as split A operand (K0); W1 (hi|lo) is already in flight into the weight buffer
         for (int kc = cg; kc < d.k0 / 8; kc += 4) {
             float v[8];
@@ -206,6 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
             issue_gemm3(tmem + COL1, sah, sal, swh, swl, d.k1, FC, bar);
         }
         wphase ^= 1;
+        w1_in_flight = false;
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
         // W1 and X are consumed: W2 streams into the weight buffer under the epilogue
@@ -235,7 +255,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
         // W2 is consumed: W1 of this CTA's next tile streams in under the remaining epilogues and the next staging
-        if (tid == 0 && tile + gridDim.x < n_tiles) bulk_load_pair(swh, swl, a.wimg + L.w1, L.sz_w1, wbar);
+        if (tile + gridDim.x < n_tiles) {
+            if (tid == 0) bulk_load_pair(swh, swl, a.wimg + L.w1, L.sz_w1, wbar);
+            w1_in_flight = true;
+        }
         {
             const int cb = cg * 32;
             float v[32];
@@ -276,6 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
         __syncthreads();
         tc_fence_after();
     }
+    if (w1_in_flight && tid == 0) mbar_wait(wbar, wphase);     // never leave with a bulk copy still writing into our smem
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(TMEM_COLS) : "memory");
     }
