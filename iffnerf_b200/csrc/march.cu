@@ -249,242 +249,6 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
     }
 }
 
-// ---- warp-specialised variant (experiment, built with -DTVM_MARCH_WS) -------------------------------------------
-// CTA = 2 warpgroups: warps 0-3 march rays (sampling, occupancy, density, compositing: 64 registers after
-// setmaxnreg.dec) and push the appearance samples (fractional texel indices + weight) into a per-pair shared-memory
-// ring; warps 4-7 (setmaxnreg.inc 96) pop groups of 8 samples, gather the appearance factors and own the per-ray
-// accumulator.  Producer p feeds consumer p+4.  A ray's samples are padded to a multiple of 8 and followed by a
-// sentinel group (w = -1: flush to ray id; w = -2: no more rays).
-#ifndef TVM_WS_RING
-#define TVM_WS_RING 64
-#endif
-#ifndef TVM_WS_PREG
-#define TVM_WS_PREG 64
-#endif
-#ifndef TVM_WS_CREG
-#define TVM_WS_CREG 96
-#endif
-#ifndef TVM_WS_MINB
-#define TVM_WS_MINB 3
-#endif
-#ifndef TVM_WS_SLEEP
-#define TVM_WS_SLEEP 64
-#endif
-constexpr int WS_RING = TVM_WS_RING;
-struct WsPair {
-    float4 ring[WS_RING];
-    volatile unsigned head;        // entries produced
-    volatile unsigned tail;        // entries consumed
-};
-
-template <int CS4, int CA4>
-__global__ void __launch_bounds__(256, TVM_WS_MINB) march_ws_kernel(const __grid_constant__ MarchArgs a) {
-    constexpr int G = CA4 / 4;
-    __shared__ int s_next;
-    __shared__ WsPair s_pair[4];
-    __shared__ float4 s_slot[4][32];
-    __shared__ float s_ret[4][32];
-    const tvm_field_desc& f = a.f;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 3, quad = lane >> 2;
-    const int pair = warp & 3;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    if (threadIdx.x == 0) s_next = 4;
-    if (threadIdx.x < 4) { s_pair[threadIdx.x].head = 0u; s_pair[threadIdx.x].tail = 0u; }
-    __syncthreads();
-    WsPair& P = s_pair[pair];
-
-    if (warp >= 4) {
-        // =============================== consumer: appearance gathers + accumulator ===============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(TVM_WS_CREG));
-        float4 A[3][G];
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int g = 0; g < G; ++g) A[k][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        unsigned tail = 0, h = 0;
-        for (;;) {
-            // poll the producer's counter only when the groups seen so far are used up
-            while (h - tail < 8u) {
-                unsigned hh = 0;
-                if (lane == 0) hh = P.head;
-                h = __shfl_sync(FULL, hh, 0);
-                if (h - tail >= 8u) break;
-                __nanosleep(TVM_WS_SLEEP);
-            }
-            __threadfence_block();
-            const float4 e = P.ring[(tail + quad) & (WS_RING - 1)];
-            const float w0 = __shfl_sync(FULL, e.w, 0);
-            if (w0 < 0.f) {
-                if (w0 < -1.5f) break;                                   // no more rays for this pair
-                const unsigned rlo = __float_as_uint(__shfl_sync(FULL, e.x, 0));
-                const unsigned rhi = __float_as_uint(__shfl_sync(FULL, e.y, 0));
-                const long long r = (long long)(((unsigned long long)rhi << 32) | rlo);
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        float4 v = A[k][g];
-#pragma unroll
-                        for (int o = 4; o < 32; o <<= 1) {
-                            v.x += __shfl_xor_sync(FULL, v.x, o); v.y += __shfl_xor_sync(FULL, v.y, o);
-                            v.z += __shfl_xor_sync(FULL, v.z, o); v.w += __shfl_xor_sync(FULL, v.w, o);
-                        }
-                        if (quad == 0) reinterpret_cast<float4*>(a.ray_feat + r * a.ta + a.app_off[k])[sub + 4 * g] = v;
-                        A[k][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-            } else if (e.w > 0.f) {
-                const float q[3] = {e.x, e.y, e.z};
-                app_accumulate_taps<G, CA4>(f, a.sec, make_sample_taps_idx(f, q), e.w, sub, A);
-            }
-            __syncwarp();
-            tail += 8u;
-            if (lane == 0 && ((tail & (WS_RING / 2 - 1)) == 0u || w0 < 0.f)) P.tail = tail;
-        }
-        return;
-    }
-
-    // ===================================== producer: march rays =====================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(TVM_WS_PREG));
-    const long long base = (long long)blockIdx.x * a.rays_per_cta;
-    const bool early = (a.flags & TVM_F_EARLY_TERM) != 0;
-    const int S = a.S, nblk = (S + 31) >> 5;
-    unsigned head = 0, tail_seen = 0;
-    // reserve `need` ring entries (waits for the consumer), writes are published by publish()
-    auto reserve = [&](unsigned need) {
-        for (;;) {
-            if (head + need - tail_seen <= (unsigned)WS_RING) break;
-            unsigned t = 0;
-            if (lane == 0) t = P.tail;
-            tail_seen = __shfl_sync(FULL, t, 0);
-            if (head + need - tail_seen <= (unsigned)WS_RING) break;
-            __nanosleep(TVM_WS_SLEEP);
-        }
-    };
-    auto publish = [&](unsigned n) {
-        __threadfence_block();
-        __syncwarp();
-        head += n;
-        if (lane == 0) P.head = head;
-    };
-    int local = warp;
-    while (local < a.rays_per_cta) {
-        const long long r = base + local;
-        if (r >= a.n_rays) break;
-        TvmRay ray;
-        {
-            const float* rp = a.rays + r * a.ray_stride;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { ray.o[c] = __ldg(rp + c); ray.d[c] = __ldg(rp + 3 + c); }
-        }
-        tvm_init_ray(f, ray, 0.f, a.S, (a.flags & TVM_F_POINT_SAMPLES) != 0);
-        float T = 1.f, acc = 0.f, dep = 0.f;
-        int n_sigma = 0, n_app = 0, n_occ = 0;
-        const TvmBlockMask bm = tvm_block_prepass(f, ray, S, lane);
-        int wi = 0;
-        unsigned todo = bm.word(0);
-        for (;;) {
-            while (todo == 0u && ++wi < ((nblk + 31) >> 5)) todo = bm.word(wi);
-            if (todo == 0u) break;
-            const int blk = (wi << 5) + (__ffs(todo) - 1);
-            todo &= todo - 1u;
-            const int i = (blk << 5) + lane;
-            const float z = tvm_sample_z(f, ray, i);
-            float p[3];
-            const bool inside = tvm_sample_point(f, ray, z, p) && i < S;
-            bool keep = inside;
-            if (f.occ_cells != nullptr && inside) keep = tvm_occupancy_keep(f, p);
-            const unsigned vmask = __ballot_sync(FULL, keep);
-            n_occ += __popc(__ballot_sync(FULL, inside));
-            if (!vmask) continue;
-            const float zn = tvm_sample_z(f, ray, i + 1);
-            const float dist = (i < S - 1) ? rn_sub(zn, z) : 0.f;
-            float n[3];
-            tvm_normalize(f, p, n);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) n[c] = tvm_unnormalize(n[c], f.grid[c]);
-            const int nv = __popc(vmask), rank = __popc(vmask & lt_mask);
-            if (keep) s_slot[pair][rank] = make_float4(n[0], n[1], n[2], 0.f);
-            __syncwarp();
-            for (int g = 0; g * 8 < nv; ++g) {
-                const int ci = g * 8 + quad;
-                float part = 0.f;
-                if (ci < nv) {
-                    const float4 sl = s_slot[pair][ci];
-                    const float q[3] = {sl.x, sl.y, sl.z};
-                    part = density_partial_taps<CS4>(f, a.sec, make_sample_taps_idx(f, q), sub);
-                }
-                part += __shfl_xor_sync(FULL, part, 1);
-                part += __shfl_xor_sync(FULL, part, 2);
-                if (sub == 0 && ci < nv) s_ret[pair][ci] = part;
-            }
-            __syncwarp();
-            float sigma = 0.f;
-            if (keep) sigma = tvm_density(f, s_ret[pair][rank]);
-            n_sigma += nv;
-            const float alpha = 1.f - expf(-sigma * rn_mul(dist, f.distance_scale));
-            float incl = 1.f - alpha + 1e-10f;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl *= v;
-            }
-            float excl = __shfl_up_sync(FULL, incl, 1);
-            if (lane == 0) excl = 1.f;
-            const float w = alpha * (T * excl);
-            T *= __shfl_sync(FULL, incl, 31);
-            acc += w;
-            dep = fmaf(w, z, dep);
-            const bool app = keep && (w > f.weight_thres);
-            const unsigned amask = __ballot_sync(FULL, app);
-            if (amask) {
-                const unsigned na = (unsigned)__popc(amask), ranka = (unsigned)__popc(amask & lt_mask);
-                reserve(na);
-                if (app) P.ring[(head + ranka) & (WS_RING - 1)] = make_float4(n[0], n[1], n[2], w);
-                publish(na);
-                n_app += (int)na;
-            }
-            if (early && T < f.early_term_eps) break;
-        }
-        // ---- end of ray
-        if (n_app > 0) {
-            const unsigned pad = (8u - (head & 7u)) & 7u;
-            reserve(pad + 8u);
-            if (lane < (int)(pad + 8u)) {
-                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane == (int)pad)
-                    e = make_float4(__uint_as_float((unsigned)(r & 0xffffffffll)), __uint_as_float((unsigned)(r >> 32)), 0.f, -1.f);
-                P.ring[(head + (unsigned)lane) & (WS_RING - 1)] = e;
-            }
-            publish(pad + 8u);
-        } else if (quad == 0) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-#pragma unroll
-                for (int g = 0; g < G; ++g)
-                    reinterpret_cast<float4*>(a.ray_feat + r * a.ta + a.app_off[k])[sub + 4 * g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        acc = warp_sum(acc);
-        dep = warp_sum(dep);
-        if (lane == 0) {
-            a.acc[r] = acc;
-            a.depth[r] = dep;
-            a.sigma_count[r] = n_sigma;
-            a.app_count[r] = n_app;
-            if (a.occ_count) a.occ_count[r] = n_occ;
-            if (a.app_count_out) a.app_count_out[r] = n_app;
-        }
-        int nxt = 0;
-        if (lane == 0) nxt = atomicAdd(&s_next, 1);
-        local = __shfl_sync(FULL, nxt, 0);
-    }
-    // ---- no more rays: tell the consumer
-    {
-        reserve(8u);
-        if (lane < 8) P.ring[(head + (unsigned)lane) & (WS_RING - 1)] = make_float4(0.f, 0.f, 0.f, lane == 0 ? -2.f : 0.f);
-        publish(8u);
-    }
-}
-
 int fill_args(MarchArgs& a, const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
               int n_samples, const float* jitter) {
     int rc = tvm_check_desc(desc);
@@ -574,16 +338,6 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
     for (int k = 0; k < 3; ++k) gmax = max(gmax, (desc->n_app[k] + 15) / 16);
     bool lego = true;     // the reference configs: 16 density / 48 appearance components on every plane
     for (int k = 0; k < 3; ++k) lego = lego && desc->n_sigma[k] == 16 && desc->n_app[k] == 48;
-#ifdef TVM_MARCH_WS
-    if (lego && !alpha && !z_vals && !dists && !valid_bits && !valid_count && !jitter) {
-        a.rays_per_cta = pick_rays_per_cta(a.n_rays, 4, MARCH_RAYS_PER_CTA);
-        cudaFuncSetAttribute(march_ws_kernel<4, 12>, cudaFuncAttributePreferredSharedMemoryCarveout, 20);
-        const long long ctas = (a.n_rays + a.rays_per_cta - 1) / a.rays_per_cta;
-        march_ws_kernel<4, 12><<<(unsigned)ctas, 256, 0, st>>>(a);
-        TVM_LAUNCH_CHECK();
-        return 0;
-    }
-#endif
     if (lego) return launch(march_fwd_kernel<3, false, 4, 12>, a, st);
     if (gmax <= 1) return launch(march_fwd_kernel<1, false, 0, 0>, a, st);
     if (gmax == 2) return launch(march_fwd_kernel<2, false, 0, 0>, a, st);
