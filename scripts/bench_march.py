@@ -59,7 +59,12 @@ def shade_tc():
     _lib.check(lib.tvm_shade_fwd(C.byref(d2), _lib.ptr(rays), n, rays.shape[1], _lib.ptr(bg), _lib.F_MLP_BF16, _lib.ptr(rgb),
                                  _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(ws), ws.numel(), st), "shade_tc")
 if a.march_only:
-    print(json.dumps({"tag": a.tag, "tile": a.tile, "march_ms": round(timeit(march), 4)}))
+    out = {"tag": a.tag, "tile": a.tile, "march_ms": round(timeit(march), 4)}
+    v = m.workspace_views(d, ws, n)      # checksums of the march outputs (compare builds)
+    out.update(feat_sum=float(v["ray_feat"].double().sum()), feat_abs=float(v["ray_feat"].double().abs().sum()),
+               acc_sum=float(v["acc"].double().sum()), depth_sum=float(v["depth"].double().sum()),
+               app=int(v["app_count"].sum()), sigma=int(v["sigma_count"].sum()))
+    print(json.dumps(out))
     sys.exit(0)
 march()
 ref_rgb = torch.empty_like(rgb); shade(); ref_rgb.copy_(rgb)
