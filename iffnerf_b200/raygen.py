@@ -26,18 +26,23 @@ _kinv_cache = {}
 
 
 def _kinv(K):
-    """Host float[9] of torch.inverse(K) (ray_utils.py:50); K is [3,3] or [1,3,3].  Cached per (tensor, version): the
-    intrinsics are constants of a run, and a cached value keeps `pixel_rays` free of host<->device traffic (CUDA-graph
-    capturable) even when K lives on the GPU."""
-    key = (K.data_ptr(), K._version, K.device.type)
+    """Host float[9] of torch.inverse(K) (ray_utils.py:50); K is [3,3] or [1,3,3].  Cached (CPU intrinsics by value,
+    device intrinsics by tensor identity + version): the intrinsics are constants of a run, and a cached value keeps
+    `pixel_rays` free of host<->device traffic (CUDA-graph capturable) even when K lives on the GPU."""
+    if K.device.type == "cpu":
+        key = ("cpu",) + tuple(K.detach().reshape(-1)[:9].tolist())     # by value: no aliasing of recycled addresses
+        keep = None
+    else:
+        key = ("dev", K.data_ptr(), K._version)                          # by identity; the entry keeps K alive, so the
+        keep = K                                                         # address cannot be recycled while it is cached
     hit = _kinv_cache.get(key)
     if hit is None:
         k = torch.inverse(K.detach().reshape(-1, 3, 3)[0].float().cpu()).contiguous()
-        hit = (C.c_float * 9)(*k.reshape(-1).tolist())
+        hit = ((C.c_float * 9)(*k.reshape(-1).tolist()), keep)
         if len(_kinv_cache) > 64:
             _kinv_cache.clear()
         _kinv_cache[key] = hit
-    return hit
+    return hit[0]
 
 
 class _PixelRays(torch.autograd.Function):

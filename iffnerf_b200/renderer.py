@@ -54,6 +54,8 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
     copy_stream, compute = _side_streams(dev)
     tensorf.field_desc()                       # (re)pack parameter shadows on the caller's stream before forking
     tensorf._bg(bg_color, bool(white_bg), dev)  # ... and create the cached background constant there too
+    if not tensorf.native_shade and tensorf.ref_kernel:
+        tensorf.packed_ref_head()               # ... and the `Ref` head's packed parameters
     fork = torch.cuda.Event()
     fork.record(main)
     copy_stream.wait_event(fork)
