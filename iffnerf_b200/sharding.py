@@ -73,17 +73,18 @@ def render_sharded(rays, tensorf, renderer, group=None, tile: int = DEFAULT_TILE
         if world == 1:
             return rgb, depth
         return rgb, depth, idx
-    # equal-sized payloads for all_gather_into_tensor: pad every shard to the largest one
-    per = max(len(shard_index(n, world, r, tile)) for r in range(world))
+    # equal-sized payloads for all_gather_into_tensor: every rank pads its shard to max_tiles full tiles, so the
+    # gathered buffer is [world][max_tiles][tile] and ONE permuted copy puts tile t = j * world + r back at offset
+    # t * tile (the only partial tile is the last one of the image, so truncating to n is enough)
+    n_tiles = (n + tile - 1) // tile
+    max_tiles = (n_tiles + world - 1) // world
+    per = max_tiles * tile
     payload = torch.zeros((per, 4), dtype=rgb.dtype, device=rgb.device)
     payload[: rgb.shape[0], :3] = rgb
     payload[: rgb.shape[0], 3] = depth
     full = torch.empty((world * per, 4), dtype=rgb.dtype, device=rgb.device)
     dist.all_gather_into_tensor(full, payload, group=group)
-    out = torch.empty((n, 4), dtype=rgb.dtype, device=rgb.device)
-    for r in range(world):
-        ridx = shard_index(n, world, r, tile, device=rgb.device)
-        out[ridx] = full[r * per: r * per + ridx.numel()]
+    out = full.view(world, max_tiles, tile, 4).permute(1, 0, 2, 3).reshape(-1, 4)[:n]
     return out[:, :3].contiguous(), out[:, 3].contiguous()
 
 
