@@ -41,6 +41,14 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
         # end of one slice's march overlap the start of the next instead of leaving SMs idle
         n_slices = int(getattr(tensorf, "host_ray_slices", 0)) or (2 if n >= (1 << 18) else 1)     # measured: 2 is best at 800x800
         step = min(step, max(1 << 14, -(-n // n_slices)))
+    # slice boundaries; the FIRST slice is short (its upload is the only one nothing can hide behind), the rest of the
+    # rays is cut into n_slices - 1 equal parts (each within max_launch_rays)
+    bounds = list(range(0, n, step)) + [n]
+    first_frac = float(getattr(tensorf, "host_first_slice_frac", 0.5))
+    if on_host and len(bounds) > 2 and 0.0 < first_frac < 1.0:
+        first = min(n, max(1 << 14, int(step * first_frac) // 4096 * 4096))
+        rest_step = min(int(tensorf.max_launch_rays), max(1 << 14, -(-(n - first) // max(len(bounds) - 2, 1))))
+        bounds = [0] + list(range(first, n, rest_step)) + [n]
     main = torch.cuda.current_stream(dev)
     if not on_host or n <= step:
         for a in range(0, n, step):
@@ -60,9 +68,9 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
     fork.record(main)
     copy_stream.wait_event(fork)
     done = []
-    for k, a in enumerate(range(0, n, step)):
+    for k, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
         with torch.cuda.stream(copy_stream):
-            cur = rays[a:a + step].to(dev, non_blocking=True)
+            cur = rays[a:b].to(dev, non_blocking=True)
             arrived = torch.cuda.Event()
             arrived.record(copy_stream)
         cs = compute[k % len(compute)]
@@ -72,7 +80,7 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
         with torch.cuda.stream(cs):
             cur.record_stream(cs)
             tensorf.render_eval(cur, N_samples=N_samples, white_bg=bool(white_bg), bg_color=bg_color,
-                                out_rgb=rgb[a:a + step], out_depth=depth[a:a + step])
+                                out_rgb=rgb[a:b], out_depth=depth[a:b])
             ev = torch.cuda.Event()
             ev.record(cs)
         done.append(ev)
