@@ -30,6 +30,9 @@ namespace {
 #ifndef TVM_MARCH_MIN_BLOCKS
 #define TVM_MARCH_MIN_BLOCKS 4
 #endif
+#ifndef TVM_MARCH_CARVEOUT
+#define TVM_MARCH_CARVEOUT 14          // % of the 228 KB given to shared memory; the rest is the L1 the gathers live in
+#endif
 constexpr int MARCH_WARPS = TVM_MARCH_WARPS;
 constexpr int MARCH_RAYS_PER_CTA = TVM_MARCH_RAYS_PER_CTA;
 constexpr unsigned FULL = 0xffffffffu;
@@ -285,7 +288,7 @@ int launch(K kernel, MarchArgs& a, cudaStream_t st) {
     bool done = false;
     for (auto& s : seen) done = done || s.load(std::memory_order_relaxed) == (const void*)kernel;
     if (!done) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 14);
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, TVM_MARCH_CARVEOUT);
         for (auto& s : seen) {
             const void* expect = nullptr;
             if (s.compare_exchange_strong(expect, (const void*)kernel)) break;
