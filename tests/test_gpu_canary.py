@@ -18,7 +18,7 @@ PAD = 1024
 class Guarded:
     def __init__(self, shape, dev, dtype=torch.float32):
         n = int(np.prod(shape))
-        self.buf = torch.full((n + 2 * PAD,), SENT, dtype=dtype, device=dev)
+        self.buf = torch.full((n + 2 * PAD,), SENT if dtype.is_floating_point else 7, dtype=dtype, device=dev)
         self.view = self.buf[PAD:PAD + n].view(*shape)
 
     def intact(self):
@@ -93,3 +93,50 @@ def test_ref_head_tail_kernel_stays_inside_its_slices(dev):
         torch.cuda.synchronize()
         assert rgb.intact() and depth.intact(), n
         assert torch.isfinite(rgb.view).all() and not (rgb.view == SENT).any()
+
+
+def test_backward_kernels_stay_inside_their_buffers(dev, built_lib):
+    """tvm_shade_bwd + tvm_march_bwd (factor-gradient scatter and d(rays)) with every output guarded."""
+    from iffnerf_b200 import _lib
+    fld, rays = fx.config1(0.0, "sphere", 6)
+    m = H.module_from_field(fld, dev)
+    m.mlp_precision = "fp32"
+    d, keep = m.field_desc()
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    S = m.nSamples
+    ta = sum(m.app_n_comp)
+    bg = torch.ones(3, device=dev)
+    g = torch.Generator().manual_seed(1)
+    for n in (1, 33, 65, 129, 1025):
+        r = rays[4545:4545 + n].to(dev).contiguous()                 # starts at the image centre: hits the object
+        need = C.c_size_t(0)
+        built_lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need))
+        ws = Guarded((need.value,), dev, dtype=torch.uint8)
+        rgb, depth, acc = torch.empty(n, 3, device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev)
+        alpha = Guarded((n, S), dev)
+        _lib.check(built_lib.tvm_render_fwd(C.byref(d), _lib.ptr(r), n, 6, S, None, _lib.ptr(bg), 0, _lib.ptr(rgb), _lib.ptr(depth),
+                                            _lib.ptr(acc), _lib.ptr(alpha.view), None, None, None, None, None,
+                                            _lib.ptr(ws.view), need.value, st), "fwd")
+        d_rgb = torch.randn(n, 3, generator=g).to(dev)
+        d_feat, d_acc, d_view = Guarded((n, ta), dev), Guarded((n,), dev), Guarded((n, 3), dev)
+        g_basis = Guarded((27, ta), dev)
+        g_mlp = Guarded((int(built_lib.tvm_mlp_grad_floats(C.byref(d))),), dev)
+        g_basis.view.zero_(); g_mlp.view.zero_()
+        _lib.check(built_lib.tvm_shade_bwd(C.byref(d), _lib.ptr(r), n, 6, _lib.ptr(bg), _lib.ptr(d_rgb), None, _lib.ptr(d_feat.view),
+                                           _lib.ptr(d_acc.view), _lib.ptr(g_basis.view), _lib.ptr(g_mlp.view), _lib.ptr(d_view.view),
+                                           _lib.ptr(ws.view), need.value, st), "shade_bwd")
+        g_fac = Guarded((int(d.n_factor_floats),), dev)
+        g_fac.view.zero_()
+        g_rays = Guarded((n, 6), dev)
+        g_rays.view.zero_()
+        d_alpha = (torch.randn(n, S, generator=g) * 1e-3).to(dev)
+        _lib.check(built_lib.tvm_march_bwd(C.byref(d), _lib.ptr(r), n, 6, S, None, 0, _lib.ptr(d_feat.view), _lib.ptr(d_acc.view),
+                                           _lib.ptr(d_alpha), _lib.ptr(g_fac.view), _lib.ptr(g_rays.view), _lib.ptr(ws.view),
+                                           need.value, st), "march_bwd")
+        torch.cuda.synchronize()
+        assert (ws.buf[:PAD] == 7).all() and (ws.buf[-PAD:] == 7).all(), n
+        for name, t in (("alpha", alpha), ("d_feat", d_feat), ("d_acc", d_acc), ("d_view", d_view), ("g_basis", g_basis),
+                        ("g_mlp", g_mlp), ("g_fac", g_fac), ("g_rays", g_rays)):
+            assert t.intact(), (name, n)
+            assert torch.isfinite(t.view).all(), (name, n)
+        assert float(g_fac.view.abs().sum()) > 0 and float(g_rays.view.abs().sum()) > 0
