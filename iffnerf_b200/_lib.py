@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_B200_LIB lets the tuning scripts load a differently-compiled build of the SAME sources
 LIB_PATH = os.environ.get("TVM_B200_LIB") or os.path.join(_HERE, "libtvm_b200.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 F_EARLY_TERM = 1 << 0
 F_MLP_BF16 = 1 << 1
@@ -92,6 +92,8 @@ _SIGNATURES = {
     "tvm_ref_head_layout": (C.c_int, [C.POINTER(RefHead), C.POINTER(C.c_int32)]),
     "tvm_shade_ref_fwd": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(RefHead), _P, C.c_int64, C.c_int, _P, _P, _P, _P, _P,
                                     C.c_size_t, _P]),
+    "tvm_shade_ref_bwd": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(RefHead), _P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P,
+                                    _P, _P, _P, _P, _P, _P]),
     "tvm_point_appfeature": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, _P, _P]),
     "tvm_pixel_rays_fwd": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _P, _P, C.c_int, C.c_int64, C.c_int, _P, _P]),
     "tvm_pixel_rays_bwd": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _P, _P, C.c_int, C.c_int64, C.c_int, _P, C.c_int,

@@ -200,12 +200,119 @@ class _March(torch.autograd.Function):
         return (None, d_rays, None, None, None, *grads)
 
 
+class _RefTail(torch.autograd.Function):
+    """Fused `Ref` tail under autograd: forward = tvm_shade_ref_fwd on the march outputs, backward = tvm_shade_ref_bwd.
+    inputs: model, rays, bg, ray_feat, acc, depth_partial, app_count, basis, then the 12 head tensors
+    (normal / tint / rough / diffuse / bottleneck / specular: weight, bias each)."""
+
+    NAMES = ("normal", "tint", "rough", "diffuse", "bott", "spec")
+
+    @staticmethod
+    def _lins(model):
+        rm = model.renderModule
+        return [rm.normal_mlp[0], rm.tint_color_mlp[0], rm.roughness_mlp[0], rm.diffuse_color_mlp[0], rm.bottleneck_mlp,
+                rm.specular_mlp[0]]
+
+    @staticmethod
+    def forward(ctx, model, rays, bg, ray_feat, acc, depth_p, app_count, basis, *head):
+        from .tensorf import _stream
+        dev = ray_feat.device
+        rays_c = model._prep_rays(rays)
+        n = rays_c.shape[0]
+        d, keep = model.field_desc()
+        h, buf = model.packed_ref_head()
+        lib = _lib.load()
+        # the march outputs in the workspace layout tvm_shade_ref_fwd reads
+        need = C.c_size_t(0)
+        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need)), "tvm_workspace_bytes")
+        ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
+        v = model.workspace_views(d, ws, n)
+        v["ray_feat"].copy_(ray_feat); v["acc"].copy_(acc); v["depth"].copy_(depth_p); v["app_count"].copy_(app_count)
+        rgb = torch.empty((n, 3), device=dev)
+        depth = torch.empty((n,), device=dev)
+        bg_c = _c(bg)
+        _lib.check(lib.tvm_shade_ref_fwd(C.byref(d), C.byref(h), _lib.ptr(rays_c), n, rays_c.shape[1], _lib.ptr(bg_c),
+                                         _lib.ptr(rgb), _lib.ptr(depth), None, _lib.ptr(ws), ws.numel(), _stream(dev)),
+                   "tvm_shade_ref_fwd")
+        ctx.model, ctx.rays_c, ctx.bg, ctx.ray_cols = model, rays_c, bg_c, rays.shape[1]
+        ctx.save_for_backward(ray_feat, acc, app_count)
+        ctx.key = model._ref_key
+        ctx.mark_non_differentiable(depth)
+        return rgb, depth
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth):
+        from .tensorf import _stream
+        model, rays_c = ctx.model, ctx.rays_c
+        ray_feat, acc, app_count = ctx.saved_tensors
+        dev = ray_feat.device
+        n, ta = ray_feat.shape
+        need = ctx.needs_input_grad
+        if model._ref_key != ctx.key:
+            raise _lib.TvmError("Ref head parameters were modified between forward and backward")
+        d, keep = model.field_desc()
+        h, buf = model.packed_ref_head()
+        lib = _lib.load()
+        want_rays, want_basis, want_head = need[1], need[7], any(need[8:])
+        d_feat = torch.empty((n, ta), device=dev)
+        d_acc = torch.empty((n,), device=dev)
+        d_view = torch.empty((n, 3), device=dev) if want_rays else None
+        g_basis = torch.zeros_like(model.basis_mat.weight) if want_basis else None
+        g_par = torch.zeros_like(buf) if want_head else None
+        g_rgb_c = _c(g_rgb) if g_rgb is not None else torch.zeros((n, 3), device=dev)
+        _lib.check(lib.tvm_shade_ref_bwd(C.byref(d), C.byref(h), _lib.ptr(rays_c), n, rays_c.shape[1], _lib.ptr(ctx.bg),
+                                         _lib.ptr(_c(ray_feat)), _lib.ptr(_c(acc)), _lib.ptr(app_count.contiguous()),
+                                         _lib.ptr(g_rgb_c), None, _lib.ptr(d_feat), _lib.ptr(d_acc), _lib.ptr(d_view),
+                                         _lib.ptr(g_basis), _lib.ptr(g_par), _stream(dev)), "tvm_shade_ref_bwd")
+        head_grads = [None] * 12
+        if want_head:
+            offs = (C.c_int32 * 8)()
+            _lib.check(lib.tvm_ref_head_layout(C.byref(h), offs), "tvm_ref_head_layout")
+            small_w, bott_w, small_b, bott_b, spec_w, spec_b, ide, in4 = list(offs)
+            in_c, fc = h.in_c, h.feature_c
+            sw = g_par[small_w:small_w + 10 * in4].view(10, in4)[:, :in_c]
+            sb = g_par[small_b:small_b + 10]
+            rows = {"normal": (0, 3), "tint": (3, 6), "rough": (6, 7), "diffuse": (7, 10)}
+            lins = _RefTail._lins(model)
+            out = []
+            for name, lin in zip(_RefTail.NAMES, lins):
+                if name in rows:
+                    a_, b_ = rows[name]
+                    out += [sw[a_:b_].contiguous(), sb[a_:b_].contiguous()]
+                elif name == "bott":
+                    out += [g_par[bott_w:bott_w + fc * in4].view(fc, in4)[:, :in_c].contiguous(), g_par[bott_b:bott_b + fc].contiguous()]
+                else:
+                    nin = lin.in_features
+                    out += [g_par[spec_w:spec_w + 3 * nin].view(3, nin).contiguous(), g_par[spec_b:spec_b + 3].contiguous()]
+            head_grads = out
+        d_rays = None
+        if want_rays:
+            d_rays = torch.zeros((n, ctx.ray_cols), device=dev)
+            d_rays[:, 3:6] = d_view
+        return (None, d_rays, None, d_feat, d_acc, None, None, g_basis, *head_grads)
+
+
+def _ref_tail_params(model):
+    ps = []
+    for lin in _RefTail._lins(model):
+        ps += [lin.weight, lin.bias]
+    return ps
+
+
 def render_with_grad_torch_tail(model, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples=False):
     S = N_samples if N_samples > 0 else model.nSamples
     planes, lines = model._factor_params()
     rays = rays_chunk if rays_chunk.dtype == torch.float32 else rays_chunk.float()
     flags = _lib.F_POINT_SAMPLES if point_samples else 0
     ray_feat, acc, depth_p, alpha, z, dists, app_count = _March.apply(model, rays, S, jitter, flags, *planes, *lines)
+    if bg_color is None:
+        bg_color = model._bg(None, white_bg, rays.device)
+    if getattr(model, "ref_kernel_train", False) and model.ref_kernel and not model.native_shade \
+            and model.packed_ref_head() is not None:
+        # fused Ref tail in both directions (csrc/shade_ref.cu); d(rgb_map)/d(acc) reaches the march backward through acc
+        rgb_map, depth_map = _RefTail.apply(model, rays, bg_color, ray_feat, acc, depth_p, app_count,
+                                            model.basis_mat.weight, *_ref_tail_params(model))
+        return rgb_map, depth_map, acc, alpha, z, dists
     view = rays[:, 3:6]
     feat = F.linear(ray_feat, model.basis_mat.weight)
     rgb, _ = model.renderModule(None, view, feat, None)

@@ -120,6 +120,7 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
     # False returns None for them; rays then terminate at T < early_term_eps in forward AND backward, which is what the
     # pose-refinement loop wants (inerf/estimate_pose_inerf.py:166 reads rgb and opacity only).
     eval_sample_outputs = True
+    ref_kernel_train = True      # `Ref` head, training: fused tail backward kernel (False: torch autograd through the head)
     ref_kernel = True            # `Ref` head, eval: fused tail kernel (False: the torch-op tail, kept for cross-checks)
     # transmittance below which an eval ray stops marching (error on rgb/acc <= this value)
     early_term_eps = 1e-5

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 9
+#define TVM_ABI_VERSION 10
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define TVM_E_NULL        (-1)   /* required pointer is NULL                      */
@@ -216,6 +216,15 @@ int tvm_ref_head_layout(const tvm_ref_head* head, int32_t offs[8]);
 int tvm_shade_ref_fwd(const tvm_field_desc* desc, const tvm_ref_head* head, const float* rays, int64_t n_rays,
                       int ray_stride, const float* bg /* device [3] */, float* rgb, float* depth, float* acc,
                       const void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of that tail (training with the Ref head): d_rgb [n][3] (+ optional upstream d_acc_in [n]) -> d_ray_feat
+ * [n][sum(n_app)], d_acc [n], optional d_view [n][3]; parameter gradients are ACCUMULATED into g_basis [in_c][sum(n_app)]
+ * and g_params (packed layout of tvm_ref_head.params; the ide_mat section is not touched).  ray_feat / acc / app_count
+ * are the march-stage outputs (tvm_render_fwd with TVM_F_NO_SHADE). */
+int tvm_shade_ref_bwd(const tvm_field_desc* desc, const tvm_ref_head* head, const float* rays, int64_t n_rays,
+                      int ray_stride, const float* bg /* device [3] */, const float* ray_feat, const float* acc,
+                      const int32_t* app_count, const float* d_rgb, const float* d_acc_in, float* d_ray_feat,
+                      float* d_acc, float* d_view, float* g_basis, float* g_params, void* stream);
 
 /* TensorVMSplit.compute_appfeature (tensoRF.py:237-256): appearance feature basis_mat(plane (x) line) at NORMALISED
  * points [n][3] (zero-padded taps) -> out [n][app_dim].  Used by pose_estimation/sampling.py:535-541 (normals of the
