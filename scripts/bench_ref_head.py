@@ -36,6 +36,7 @@ tr = allrays[torch.randint(0, allrays.shape[0], (4096,), generator=g)].to(dev)
 target = torch.rand(4096, 3, device=dev)
 ones = torch.ones(3, device=dev)
 m.train()
+m.ref_kernel = True
 def train_step():
     m.zero_grad(set_to_none=True)
     rgb, _, _, alpha, _, _ = m(tr, bg_color=ones, is_train=True, N_samples=1039)
