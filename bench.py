@@ -362,6 +362,23 @@ def extra_configs(model, dev, fx):
     model.eval()
     model.zero_grad(set_to_none=True)
     del graphed, graphed_t
+    # the same train step with the `Ref` shading head (what configs/lego.txt trains with): fused tail kernels both ways
+    import contextlib, io
+    torch.manual_seed(20211202)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rm = I.TensorVMSplit(model.aabb.clone(), GRID, dev, density_n_comp=[16] * 3, appearance_n_comp=[48] * 3, app_dim=27,
+                             near_far=[2.0, 6.0], shadingMode="Ref", alphaMask_thres=1e-4, density_shift=0.0,
+                             distance_scale=25, pos_pe=6, view_pe=2, fea_pe=2, featureC=128, step_ratio=0.5,
+                             fea2denseAct="softplus")
+    rm.alphaMask = model.alphaMask
+    rm.train()
+
+    def ref_train_step():
+        rm.zero_grad(set_to_none=True)
+        rgb, _, _, alpha, _, _ = rm(rays, bg_color=ones, is_train=True, N_samples=1039)
+        (torch.mean((rgb - target) ** 2) + 0.1 * torch.mean(torch.exp(torch.abs(alpha)))).backward()
+    out["ref_head_train_step"] = {"rays": 4096, "n_samples": 1039, "ms_fwd_bwd": timeit(ref_train_step)}
+    del rm
     return out
 
 

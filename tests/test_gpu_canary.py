@@ -140,3 +140,35 @@ def test_backward_kernels_stay_inside_their_buffers(dev, built_lib):
             assert t.intact(), (name, n)
             assert torch.isfinite(t.view).all(), (name, n)
         assert float(g_fac.view.abs().sum()) > 0 and float(g_rays.view.abs().sum()) > 0
+
+
+def test_ref_head_backward_kernel_stays_inside_its_buffers(dev, built_lib):
+    """tvm_shade_ref_bwd with every output guarded, ragged ray counts around its 64-ray tile."""
+    from iffnerf_b200 import _lib
+    from tests.test_gpu_ref_head import _ref_model
+    m = _ref_model(dev)
+    d, keep = m.field_desc()
+    h, buf = m.packed_ref_head()
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _, rays = fx.config1(0.0, None, 7)
+    ta = sum(m.app_n_comp)
+    bg = torch.ones(3, device=dev)
+    g = torch.Generator().manual_seed(2)
+    for n in (1, 63, 65, 129, 1000):
+        r = rays[4545:4545 + n].to(dev).contiguous()
+        o = m.render_eval(r, white_bg=True, keep_workspace=True, want_counts=True)
+        v = o["workspace"]
+        d_rgb = torch.randn(n, 3, generator=g).to(dev)
+        d_feat, d_acc, d_view = Guarded((n, ta), dev), Guarded((n,), dev), Guarded((n, 3), dev)
+        g_basis, g_par = Guarded((27, ta), dev), Guarded((buf.numel(),), dev)
+        g_basis.view.zero_(); g_par.view.zero_()
+        _lib.check(built_lib.tvm_shade_ref_bwd(C.byref(d), C.byref(h), _lib.ptr(r), n, 7, _lib.ptr(bg), _lib.ptr(v["ray_feat"]),
+                                               _lib.ptr(v["acc"]), _lib.ptr(v["app_count"]), _lib.ptr(d_rgb), None,
+                                               _lib.ptr(d_feat.view), _lib.ptr(d_acc.view), _lib.ptr(d_view.view),
+                                               _lib.ptr(g_basis.view), _lib.ptr(g_par.view), st), "shade_ref_bwd")
+        torch.cuda.synchronize()
+        for name, t in (("d_feat", d_feat), ("d_acc", d_acc), ("d_view", d_view), ("g_basis", g_basis), ("g_par", g_par)):
+            assert t.intact(), (name, n)
+            assert torch.isfinite(t.view).all(), (name, n)
+        assert not (d_feat.view == SENT).any() and not (d_acc.view == SENT).any()
+        assert float(g_par.view.abs().sum()) > 0
