@@ -153,7 +153,8 @@ class _March(torch.autograd.Function):
         need = C.c_size_t(0)
         _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need)), "tvm_workspace_bytes")
         ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
-        alpha, z, dists = (torch.empty((n, S), device=dev) for _ in range(3))
+        want_samples = not (flags & _lib.F_EARLY_TERM)     # without per-sample outputs both directions terminate early
+        alpha, z, dists = (torch.empty((n, S), device=dev) for _ in range(3)) if want_samples else (None, None, None)
         jit = None if jitter is None else jitter.detach().to(dev).float().reshape(-1).contiguous()
         bg = model._bg(None, False, dev)
         _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], S, _lib.ptr(jit),
@@ -163,7 +164,10 @@ class _March(torch.autograd.Function):
         v = model.workspace_views(d, ws, n)
         ctx.model, ctx.S, ctx.jit, ctx.rays_c, ctx.ws, ctx.flags = model, S, jit, rays_c, ws, flags
         ctx.ray_cols = rays.shape[1]
-        ctx.mark_non_differentiable(v["depth"], z, dists, v["app_count"])
+        if want_samples:
+            ctx.mark_non_differentiable(v["depth"], z, dists, v["app_count"])
+        else:
+            ctx.mark_non_differentiable(v["depth"], v["app_count"])
         return v["ray_feat"], v["acc"], v["depth"], alpha, z, dists, v["app_count"]
 
     @staticmethod
@@ -299,11 +303,14 @@ def _ref_tail_params(model):
     return ps
 
 
-def render_with_grad_torch_tail(model, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples=False):
+def render_with_grad_torch_tail(model, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples=False,
+                                want_samples=True):
     S = N_samples if N_samples > 0 else model.nSamples
     planes, lines = model._factor_params()
     rays = rays_chunk if rays_chunk.dtype == torch.float32 else rays_chunk.float()
     flags = _lib.F_POINT_SAMPLES if point_samples else 0
+    if not want_samples and model.early_term_eps > 0:
+        flags |= _lib.F_EARLY_TERM
     ray_feat, acc, depth_p, alpha, z, dists, app_count = _March.apply(model, rays, S, jitter, flags, *planes, *lines)
     if bg_color is None:
         bg_color = model._bg(None, white_bg, rays.device)

@@ -644,7 +644,8 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
                 out = render_with_grad(self, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples,
                                        want_samples=want_samples)
             else:
-                out = render_with_grad_torch_tail(self, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples)
+                out = render_with_grad_torch_tail(self, rays_chunk, white_bg, bg_color, N_samples, jitter, point_samples,
+                                                  want_samples=want_samples)
         else:
             o = self.render_eval(rays_chunk, N_samples=N_samples, white_bg=white_bg, bg_color=bg_color, jitter=jitter,
                                  sample_outputs=want_samples, point_samples=point_samples)
