@@ -9,12 +9,12 @@
 //        tvm_pack_mlp, unpacked by tvm_unpack_mlp_grads).
 // One CTA re-runs the forward for a tile of 64 rays keeping every activation in shared memory (X, h1, h2, F:
 // ~200 KB), then walks the chain backwards; each weight gradient is a [out x 64] . [64 x in] product formed in
-// registers and flushed with 16-byte vector reductions.
+// registers and flushed with 16-byte vector reductions. Batches that would leave SMs idle with 64-ray tiles
+// (n <= 148 * 32 rays: the 4096-ray train step, the 1024-ray iNeRF step) run the 32-ray instantiation instead.
 #include "tvm_common.cuh"
 
 namespace {
 
-constexpr int SB_RAYS = 64;
 constexpr int SB_THREADS = 256;
 constexpr int FC = TVM_FEATURE_C;
 constexpr unsigned FULL = 0xffffffffu;
@@ -40,8 +40,9 @@ struct ShadeBwdArgs {
     int ta, app_dim, fea_pe, view_pe;
 };
 
-// acc[8][4] += A[8 rows][K] (smem, row stride lda) * W[K][ldw] (global), columns 4*tx .. 4*tx+3
-__device__ __forceinline__ void rows8_gemm(float (&acc)[8][4], const float* __restrict__ sA, int lda, int row0, int K,
+// acc[R][4] += A[R rows][K] (smem, row stride lda) * W[K][ldw] (global), columns 4*tx .. 4*tx+3
+template <int R>
+__device__ __forceinline__ void rows_gemm(float (&acc)[R][4], const float* __restrict__ sA, int lda, int row0, int K,
                                            const float* __restrict__ W, int ldw, int col0) {
     for (int k = 0; k < K; k += 4) {
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (k + 0) * ldw + col0));
@@ -49,7 +50,7 @@ __device__ __forceinline__ void rows8_gemm(float (&acc)[8][4], const float* __re
         const float4 w2 = __ldg(reinterpret_cast<const float4*>(W + (k + 2) * ldw + col0));
         const float4 w3 = __ldg(reinterpret_cast<const float4*>(W + (k + 3) * ldw + col0));
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < R; ++r) {
             const float4 x = *reinterpret_cast<const float4*>(sA + (row0 + r) * lda + k);
             acc[r][0] = fmaf(x.x, w0.x, fmaf(x.y, w1.x, fmaf(x.z, w2.x, fmaf(x.w, w3.x, acc[r][0]))));
             acc[r][1] = fmaf(x.x, w0.y, fmaf(x.y, w1.y, fmaf(x.z, w2.y, fmaf(x.w, w3.y, acc[r][1]))));
@@ -60,6 +61,7 @@ __device__ __forceinline__ void rows8_gemm(float (&acc)[8][4], const float* __re
 }
 
 // G[v0+j][u0+i] += sum_ray U[ray][u0+i] * V[ray][v0+j]  (8x8 register block; G is global, row stride ldg, i contiguous)
+template <int RAYS>
 __device__ __forceinline__ void outer8x8_flush(const float* __restrict__ sU, int ldu, int u0, const float* __restrict__ sV,
                                                int ldv, int v0, int vmax, float* __restrict__ G, int ldg) {
     float p[8][8];
@@ -67,7 +69,7 @@ __device__ __forceinline__ void outer8x8_flush(const float* __restrict__ sU, int
     for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int i = 0; i < 8; ++i) p[j][i] = 0.f;
-    for (int ray = 0; ray < SB_RAYS; ++ray) {
+    for (int ray = 0; ray < RAYS; ++ray) {
         const float4 ua = *reinterpret_cast<const float4*>(sU + ray * ldu + u0);
         const float4 ub = *reinterpret_cast<const float4*>(sU + ray * ldu + u0 + 4);
         const float4 va = *reinterpret_cast<const float4*>(sV + ray * ldv + v0);
@@ -88,7 +90,9 @@ __device__ __forceinline__ void outer8x8_flush(const float* __restrict__ sU, int
     }
 }
 
+template <int RAYS>      // rays per CTA: 64, or 32 for batches that would not fill the SMs
 __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_constant__ ShadeBwdArgs a) {
+    constexpr int SB_RAYS = RAYS, R = RAYS / 8, RSHIFT = RAYS == 64 ? 6 : 5;   // R rays per warp in the GEMM phases
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ta = a.ta, k1 = a.m.k1, fs = ta + 4;
@@ -122,17 +126,20 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
         *reinterpret_cast<float4*>(sF + ray * fs + c4 * 4) = v;
     }
     __syncthreads();
-    {   // feat = B . F  (2 rays x 4 cols per thread)
+    {   // feat = B . F  (RAYS/32 rays x 4 cols per thread)
+        constexpr int RB = RAYS / 32;
         const int tx = tid & 7, ty = tid >> 3;
-        float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        float o[RB][4];
+#pragma unroll
+        for (int rr = 0; rr < RB; ++rr) o[rr][0] = o[rr][1] = o[rr][2] = o[rr][3] = 0.f;
         for (int c = 0; c < ta; c += 4) {
             const float4 q0 = *reinterpret_cast<const float4*>(sB + (c + 0) * 32 + tx * 4);
             const float4 q1 = *reinterpret_cast<const float4*>(sB + (c + 1) * 32 + tx * 4);
             const float4 q2 = *reinterpret_cast<const float4*>(sB + (c + 2) * 32 + tx * 4);
             const float4 q3 = *reinterpret_cast<const float4*>(sB + (c + 3) * 32 + tx * 4);
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const float4 x = *reinterpret_cast<const float4*>(sF + (ty * 2 + rr) * fs + c);
+            for (int rr = 0; rr < RB; ++rr) {
+                const float4 x = *reinterpret_cast<const float4*>(sF + (ty * RB + rr) * fs + c);
                 o[rr][0] = fmaf(x.x, q0.x, fmaf(x.y, q1.x, fmaf(x.z, q2.x, fmaf(x.w, q3.x, o[rr][0]))));
                 o[rr][1] = fmaf(x.x, q0.y, fmaf(x.y, q1.y, fmaf(x.z, q2.y, fmaf(x.w, q3.y, o[rr][1]))));
                 o[rr][2] = fmaf(x.x, q0.z, fmaf(x.y, q1.z, fmaf(x.z, q2.z, fmaf(x.w, q3.z, o[rr][2]))));
@@ -140,10 +147,10 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
             }
         }
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
+        for (int rr = 0; rr < RB; ++rr)
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                if (tx * 4 + e < a.app_dim) sX[(ty * 2 + rr) * k1 + tx * 4 + e] = o[rr][e];
+                if (tx * 4 + e < a.app_dim) sX[(ty * RB + rr) * k1 + tx * 4 + e] = o[rr][e];
         if (tid < SB_RAYS * 3) {
             const int vr = tid / 3, c = tid - vr * 3;
             const long long r = r0 + vr;
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
     const int sin_f = nbase, cos_f = sin_f + a.app_dim * a.fea_pe;
     const int sin_v = cos_f + a.app_dim * a.fea_pe, cos_v = sin_v + 3 * a.view_pe;
     for (int it = tid; it < SB_RAYS * nbase; it += SB_THREADS) {
-        const int ray = it & (SB_RAYS - 1), ch = it >> 6;
+        const int ray = it & (SB_RAYS - 1), ch = it >> RSHIFT;
         const float v = sX[ray * k1 + ch];
         const bool is_feat = ch < a.app_dim;
         const int nf = is_feat ? a.fea_pe : a.view_pe;
@@ -176,35 +183,35 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
     }
     __syncthreads();
     const int tx = lane, ty = warp;
-    float acc[8][4];
+    float acc[R][4];
     {
         const float4 b = __ldg(reinterpret_cast<const float4*>(b1) + tx);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { acc[r][0] = b.x; acc[r][1] = b.y; acc[r][2] = b.z; acc[r][3] = b.w; }
+        for (int r = 0; r < R; ++r) { acc[r][0] = b.x; acc[r][1] = b.y; acc[r][2] = b.z; acc[r][3] = b.w; }
     }
-    rows8_gemm(acc, sX, k1, ty * 8, k1, w1t, FC, tx * 4);
+    rows_gemm<R>(acc, sX, k1, ty * R, k1, w1t, FC, tx * 4);
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-        *reinterpret_cast<float4*>(sH1 + (ty * 8 + r) * FC + tx * 4) =
+    for (int r = 0; r < R; ++r)
+        *reinterpret_cast<float4*>(sH1 + (ty * R + r) * FC + tx * 4) =
             make_float4(fmaxf(acc[r][0], 0.f), fmaxf(acc[r][1], 0.f), fmaxf(acc[r][2], 0.f), fmaxf(acc[r][3], 0.f));
     __syncthreads();
     {
         const float4 b = __ldg(reinterpret_cast<const float4*>(b2) + tx);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { acc[r][0] = b.x; acc[r][1] = b.y; acc[r][2] = b.z; acc[r][3] = b.w; }
+        for (int r = 0; r < R; ++r) { acc[r][0] = b.x; acc[r][1] = b.y; acc[r][2] = b.z; acc[r][3] = b.w; }
     }
-    rows8_gemm(acc, sH1, FC, ty * 8, FC, w2t, FC, tx * 4);
+    rows_gemm<R>(acc, sH1, FC, ty * R, FC, w2t, FC, tx * 4);
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-        *reinterpret_cast<float4*>(sH2 + (ty * 8 + r) * FC + tx * 4) =
+    for (int r = 0; r < R; ++r)
+        *reinterpret_cast<float4*>(sH2 + (ty * R + r) * FC + tx * 4) =
             make_float4(fmaxf(acc[r][0], 0.f), fmaxf(acc[r][1], 0.f), fmaxf(acc[r][2], 0.f), fmaxf(acc[r][3], 0.f));
     __syncthreads();
     {   // layer 3 + sigmoid + blend, and the head of the backward: g_z3, d_acc
         const float4 wr = __ldg(reinterpret_cast<const float4*>(w3) + lane);
         const float4 wg = __ldg(reinterpret_cast<const float4*>(w3 + FC) + lane);
         const float4 wb = __ldg(reinterpret_cast<const float4*>(w3 + 2 * FC) + lane);
-        for (int rr = 0; rr < 8; ++rr) {
-            const int ray = warp * 8 + rr;
+        for (int rr = 0; rr < R; ++rr) {
+            const int ray = warp * R + rr;
             const long long r = r0 + ray;
             const float4 h = *reinterpret_cast<const float4*>(sH2 + ray * FC + lane * 4);
             float vr = h.x * wr.x + h.y * wr.y + h.z * wr.z + h.w * wr.w;
@@ -243,8 +250,8 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
         const float4 wg = __ldg(reinterpret_cast<const float4*>(w3 + FC) + tx);
         const float4 wb = __ldg(reinterpret_cast<const float4*>(w3 + 2 * FC) + tx);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int ray = ty * 8 + r;
+        for (int r = 0; r < R; ++r) {
+            const int ray = ty * R + r;
             const float g0 = sS[ray * 8 + 3], g1 = sS[ray * 8 + 4], g2 = sS[ray * 8 + 5];
             const float4 h = *reinterpret_cast<const float4*>(sH2 + ray * FC + tx * 4);
             float4 g;
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
     __syncthreads();
     if (a.g_mlp) {   // gW2^T[k][n] += sum_ray h1[ray][k] * g_h2[ray][n]   (packed layout is transposed: [k][n]);  gb2
         const int n0 = (tid & 15) * 8, kq = (tid >> 4) * 8;
-        outer8x8_flush(sG, FC, n0, sH1, FC, kq, FC, a.g_mlp + a.m.w2t, FC);
+        outer8x8_flush<RAYS>(sG, FC, n0, sH1, FC, kq, FC, a.g_mlp + a.m.w2t, FC);
         if (tid < FC) {
             float s = 0.f;
             for (int ray = 0; ray < SB_RAYS; ++ray) s += sG[ray * FC + tid];
@@ -281,13 +288,13 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
     }
     // g_h1 = (g_h2 . W2) * [h1 > 0]   (W2 in torch orientation [n][k]: reduction over n)
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
-    rows8_gemm(acc, sG, FC, ty * 8, FC, w2n, FC, tx * 4);
+    for (int r = 0; r < R; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+    rows_gemm<R>(acc, sG, FC, ty * R, FC, w2n, FC, tx * 4);
     __syncthreads();                             // every read of g_h2 (outer product + gemm) is done
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const float4 h = *reinterpret_cast<const float4*>(sH1 + (ty * 8 + r) * FC + tx * 4);
-        *reinterpret_cast<float4*>(sG + (ty * 8 + r) * FC + tx * 4) =
+    for (int r = 0; r < R; ++r) {
+        const float4 h = *reinterpret_cast<const float4*>(sH1 + (ty * R + r) * FC + tx * 4);
+        *reinterpret_cast<float4*>(sG + (ty * R + r) * FC + tx * 4) =
             make_float4(h.x > 0.f ? acc[r][0] : 0.f, h.y > 0.f ? acc[r][1] : 0.f, h.z > 0.f ? acc[r][2] : 0.f,
                         h.w > 0.f ? acc[r][3] : 0.f);
     }
@@ -295,7 +302,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
     if (a.g_mlp) {   // gW1^T[k][n] += sum_ray x[ray][k] * g_h1[ray][n];  gb1
         const int n0 = (tid & 15) * 8;
         for (int kq = (tid >> 4) * 8; kq < k1; kq += 16 * 8)
-            outer8x8_flush(sG, FC, n0, sX, k1, kq, k1, a.g_mlp + a.m.w1t, FC);
+            outer8x8_flush<RAYS>(sG, FC, n0, sX, k1, kq, k1, a.g_mlp + a.m.w1t, FC);
         if (tid < FC) {
             float s = 0.f;
             for (int ray = 0; ray < SB_RAYS; ++ray) s += sG[ray * FC + tid];
@@ -307,22 +314,22 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
     sGX = sH1;                                   // h1 and h2 are both dead after this point (h1 read below first)
     {
         // columns 0..127 then the remainder, 8 rays x 4 cols per thread
-        float gx[8][4];
-        float gx2[8][4];
+        float gx[R][4];
+        float gx2[R][4];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { gx[r][0] = gx[r][1] = gx[r][2] = gx[r][3] = 0.f; gx2[r][0] = gx2[r][1] = gx2[r][2] = gx2[r][3] = 0.f; }
+        for (int r = 0; r < R; ++r) { gx[r][0] = gx[r][1] = gx[r][2] = gx[r][3] = 0.f; gx2[r][0] = gx2[r][1] = gx2[r][2] = gx2[r][3] = 0.f; }
         const bool head = tx * 4 < k1;           // k1 may be smaller than FC (fea_pe = view_pe = 0 -> k1 = 32)
-        if (head) rows8_gemm(gx, sG, FC, ty * 8, FC, w1n, k1, tx * 4);
+        if (head) rows_gemm<R>(gx, sG, FC, ty * R, FC, w1n, k1, tx * 4);
         const bool tail = FC + tx * 4 < k1;
-        if (tail) rows8_gemm(gx2, sG, FC, ty * 8, FC, w1n, k1, FC + tx * 4);
+        if (tail) rows_gemm<R>(gx2, sG, FC, ty * R, FC, w1n, k1, FC + tx * 4);
         __syncthreads();                         // all reads of h1 (outer product) and g_h1 are done
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < R; ++r) {
             if (head)
-                *reinterpret_cast<float4*>(sGX + (ty * 8 + r) * k1 + tx * 4) =
+                *reinterpret_cast<float4*>(sGX + (ty * R + r) * k1 + tx * 4) =
                     make_float4(gx[r][0], gx[r][1], gx[r][2], gx[r][3]);
             if (tail)
-                *reinterpret_cast<float4*>(sGX + (ty * 8 + r) * k1 + FC + tx * 4) =
+                *reinterpret_cast<float4*>(sGX + (ty * R + r) * k1 + FC + tx * 4) =
                     make_float4(gx2[r][0], gx2[r][1], gx2[r][2], gx2[r][3]);
         }
     }
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
     // g_feat / g_view through the encodings: d sin(v 2^j) = 2^j cos, d cos(v 2^j) = -2^j sin (values are still in sX)
     float* sGF = sG;                             // g_feat [64][32] (cols >= app_dim zero), g_h1 is dead
     for (int it = tid; it < SB_RAYS * 32; it += SB_THREADS) {
-        const int ray = it & (SB_RAYS - 1), ch = it >> 6;
+        const int ray = it & (SB_RAYS - 1), ch = it >> RSHIFT;
         float g = 0.f;
         if (ch < nbase) {
             const bool is_feat = ch < a.app_dim;
@@ -397,17 +404,24 @@ extern "C" int tvm_shade_bwd(const tvm_field_desc* desc, const float* rays, int6
     a.m = tvm_mlp_layout(desc);
     a.ta = tvm_total_app(desc); a.app_dim = desc->app_dim; a.fea_pe = desc->fea_pe; a.view_pe = desc->view_pe;
     if (a.m.k1 > 2 * FC || a.m.k1 % 8) return TVM_E_SHAPE;       // g_x reuses the h1|h2 span; 8-wide outer blocks
-    const size_t floats = (size_t)a.ta * 32 + (size_t)SB_RAYS * (a.ta + 4) + (size_t)SB_RAYS * a.m.k1 +
-                          (size_t)SB_RAYS * (a.m.k1 > FC ? a.m.k1 : FC) + (size_t)SB_RAYS * FC * 2 + SB_RAYS * 8;
+    const bool small = (n_rays + 31) / 32 <= (long long)TVM_SM_COUNT;     // one wave of 32-ray tiles beats idle SMs
+    const size_t tile = small ? 32 : 64;
+    const size_t floats = (size_t)a.ta * 32 + tile * (a.ta + 4) + tile * a.m.k1 +
+                          tile * (a.m.k1 > FC ? a.m.k1 : FC) + tile * FC * 2 + tile * 8;
     const size_t smem = floats * sizeof(float);
     if (smem > 227 * 1024) return TVM_E_SHAPE;
-    {
+    const long long ctas = (n_rays + (long long)tile - 1) / (long long)tile;
+    if (small) {
         static std::atomic<int> smem_set{0};
-        int rc_attr = tvm_ensure_dyn_smem(shade_bwd_kernel, smem, smem_set);
+        int rc_attr = tvm_ensure_dyn_smem(shade_bwd_kernel<32>, smem, smem_set);
         if (rc_attr) return rc_attr;
+        shade_bwd_kernel<32><<<(unsigned)ctas, SB_THREADS, smem, (cudaStream_t)stream>>>(a);
+    } else {
+        static std::atomic<int> smem_set{0};
+        int rc_attr = tvm_ensure_dyn_smem(shade_bwd_kernel<64>, smem, smem_set);
+        if (rc_attr) return rc_attr;
+        shade_bwd_kernel<64><<<(unsigned)ctas, SB_THREADS, smem, (cudaStream_t)stream>>>(a);
     }
-    const long long ctas = (n_rays + SB_RAYS - 1) / SB_RAYS;
-    shade_bwd_kernel<<<(unsigned)ctas, SB_THREADS, smem, (cudaStream_t)stream>>>(a);
     TVM_LAUNCH_CHECK();
     return 0;
 }

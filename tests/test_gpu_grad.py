@@ -167,23 +167,25 @@ def test_batched_candidate_poses_chain_to_pose_parameters(dev):
         assert scale > 0 and (a - b).abs().max().item() <= 1e-2 * scale, ((a - b).abs().max().item(), scale)
 
 
-def test_shade_backward_kernel_matches_torch_autograd_tail(dev):
+@pytest.mark.parametrize("n", [777, 5001])     # 32-ray tiles (n <= 148*32) and 64-ray tiles
+def test_shade_backward_kernel_matches_torch_autograd_tail(dev, n):
     """tvm_shade_bwd (hand-written) against the variant whose shading tail is torch autograd on the same march
     outputs: every parameter gradient and d(rays), incl. a 7-column batch whose size is not a tile multiple."""
     from iffnerf_b200 import autograd as ag
     fld, rays = fx.config1(0.0, "sphere", 7)
     m = H.module_from_field(fld, dev)
-    sub = rays[2000:2000 + 777].to(dev)
+    assert rays.shape[0] >= 2000 + n
+    sub = rays[2000:2000 + n].to(dev)
     torch.manual_seed(2)
-    jit = torch.rand(777, device=dev)
-    target = torch.rand(777, 3, device=dev)
+    jit = torch.rand(n, device=dev)
+    target = torch.rand(n, 3, device=dev)
     bg = torch.tensor([0.1, 0.9, 0.4], device=dev)
     res = []
     for fn in (ag.render_with_grad, ag.render_with_grad_torch_tail):
         m.zero_grad()
         r = sub.clone().requires_grad_(True)
         rgb, depth, acc, alpha, z, dists = fn(m, r, False, bg, 300, jit)
-        loss = torch.mean((rgb - target) ** 2) + 0.05 * acc.sum() / 777 + 0.1 * torch.mean(torch.exp(torch.abs(alpha)))
+        loss = torch.mean((rgb - target) ** 2) + 0.05 * acc.sum() / n + 0.1 * torch.mean(torch.exp(torch.abs(alpha)))
         loss.backward()
         res.append((rgb.detach().clone(), [p.grad.clone() for p in _module_params(m)], r.grad.clone()))
     (rgb_a, ga, ra), (rgb_b, gb, rb) = res
