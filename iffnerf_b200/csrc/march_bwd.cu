@@ -21,7 +21,10 @@ namespace {
 #ifndef TVM_BWD_MIN_BLOCKS
 #define TVM_BWD_MIN_BLOCKS 3
 #endif
-constexpr int BWD_WARPS = 4;
+#ifndef TVM_BWD_WARPS
+#define TVM_BWD_WARPS 4
+#endif
+constexpr int BWD_WARPS = TVM_BWD_WARPS;
 constexpr int BWD_RAYS_PER_CTA = 16;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -338,6 +341,9 @@ extern "C" int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int6
     {
         long long rpc = n_rays / (TVM_SM_COUNT * 8);
         a.rays_per_cta = (int)(rpc < BWD_WARPS ? BWD_WARPS : (rpc > BWD_RAYS_PER_CTA ? BWD_RAYS_PER_CTA : rpc));
+#ifdef TVM_BWD_RPC_FIXED
+        a.rays_per_cta = TVM_BWD_RPC_FIXED;
+#endif
     }
     int gmax = 0;
     for (int k = 0; k < 3; ++k) gmax = max(gmax, (desc->n_app[k] + 15) / 16);

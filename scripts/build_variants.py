@@ -7,9 +7,10 @@ from iffnerf_b200 import build
 
 out_dir = os.path.join(ROOT, "iffnerf_b200", "variants")
 os.makedirs(out_dir, exist_ok=True)
-combos = [(4, 32, 3), (4, 32, 4), (8, 32, 2), (8, 64, 2)]
-for warps, rpc, mb in combos:
-    tag = f"w{warps}_r{rpc}_b{mb}"
+combos = [(1, 12, 1), (1, 12, 0), (2, 6, 2), (4, 3, 0)]
+for warps, mb, rpc in combos:
+    tag = f"bwd_w{warps}_b{mb}_r{rpc}"
     out = os.path.join(out_dir, f"libtvm_{tag}.so")
-    build.build(defines=[f"TVM_MARCH_WARPS={warps}", f"TVM_MARCH_RAYS_PER_CTA={rpc}", f"TVM_MARCH_MIN_BLOCKS={mb}"], out=out)
+    defs = [f"TVM_BWD_WARPS={warps}", f"TVM_BWD_MIN_BLOCKS={mb}"] + ([f"TVM_BWD_RPC_FIXED={rpc}"] if rpc else [])
+    build.build(defines=defs, out=out)
     print(out)
