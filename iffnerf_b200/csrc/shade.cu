@@ -168,8 +168,10 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const __grid_cons
         const int nbase = a.app_dim + 3;
         const int sin_f = nbase, cos_f = sin_f + a.app_dim * a.fea_pe;
         const int sin_v = cos_f + a.app_dim * a.fea_pe, cos_v = sin_v + 3 * a.view_pe;
-        for (int it = tid; it < SH_RAYS * nbase; it += SH_THREADS) {
-            const int ray = it & (SH_RAYS - 1), ch = it >> 6;
+        const int chs = nbase > 32 ? 6 : 5;                           // lanes run over the channels of one ray
+        for (int it = tid; it < (SH_RAYS << chs); it += SH_THREADS) { // (bank-conflict-free; nbase <= 35)
+            const int ch = it & ((1 << chs) - 1), ray = it >> chs;
+            if (ch >= nbase) continue;
             const float v = sX[ray * k1 + ch];
             const bool is_feat = ch < a.app_dim;
             const int nf = is_feat ? a.fea_pe : a.view_pe;

@@ -16,8 +16,16 @@
 namespace {
 
 constexpr int SB_THREADS = 256;
+#ifndef TVM_SHADE_BWD_SMALL_BLOCKS
+#define TVM_SHADE_BWD_SMALL_BLOCKS 1      // resident CTAs/SM the 32-ray instantiation is compiled for
+#endif
+#ifndef TVM_SHADE_BWD_SMALL_ALWAYS
+#define TVM_SHADE_BWD_SMALL_ALWAYS 0      // 1: 32-ray tiles at every batch size
+#endif
 constexpr int FC = TVM_FEATURE_C;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int BS = 36;          // row stride of the transposed basis in smem: 16-B aligned rows, float4 reads by
+                                // consecutive rows land on distinct bank groups (36 mod 32 = 4)
 
 struct ShadeBwdArgs {
     const float* rays;
@@ -40,22 +48,46 @@ struct ShadeBwdArgs {
     int ta, app_dim, fea_pe, view_pe;
 };
 
-// acc[R][4] += A[R rows][K] (smem, row stride lda) * W[K][ldw] (global), columns 4*tx .. 4*tx+3
+// acc[R][4] += A[R rows][K] (smem, row stride lda) * W[K][ldw] (global), columns 4*tx .. 4*tx+3.
+// The weight rows of GEMM_DEPTH k-steps (4 rows each) are kept in flight in registers: with 8 warps per CTA a k-step
+// that waited for its own loads paid the full L2 latency (~0.4 us) 166 times per tile.
+#ifndef TVM_SHADE_BWD_DEPTH
+#define TVM_SHADE_BWD_DEPTH 2
+#endif
+constexpr int GEMM_DEPTH = TVM_SHADE_BWD_DEPTH;
 template <int R>
 __device__ __forceinline__ void rows_gemm(float (&acc)[R][4], const float* __restrict__ sA, int lda, int row0, int K,
-                                           const float* __restrict__ W, int ldw, int col0) {
-    for (int k = 0; k < K; k += 4) {
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (k + 0) * ldw + col0));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (k + 1) * ldw + col0));
-        const float4 w2 = __ldg(reinterpret_cast<const float4*>(W + (k + 2) * ldw + col0));
-        const float4 w3 = __ldg(reinterpret_cast<const float4*>(W + (k + 3) * ldw + col0));
+                                          const float* __restrict__ W, int ldw, int col0) {
+    float4 w[GEMM_DEPTH][4];
+    const int n = K >> 2;
+    const float* wp = W + col0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float4 x = *reinterpret_cast<const float4*>(sA + (row0 + r) * lda + k);
-            acc[r][0] = fmaf(x.x, w0.x, fmaf(x.y, w1.x, fmaf(x.z, w2.x, fmaf(x.w, w3.x, acc[r][0]))));
-            acc[r][1] = fmaf(x.x, w0.y, fmaf(x.y, w1.y, fmaf(x.z, w2.y, fmaf(x.w, w3.y, acc[r][1]))));
-            acc[r][2] = fmaf(x.x, w0.z, fmaf(x.y, w1.z, fmaf(x.z, w2.z, fmaf(x.w, w3.z, acc[r][2]))));
-            acc[r][3] = fmaf(x.x, w0.w, fmaf(x.y, w1.w, fmaf(x.z, w2.w, fmaf(x.w, w3.w, acc[r][3]))));
+    for (int d = 0; d < GEMM_DEPTH; ++d)
+        if (d < n) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[d][e] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(d * 4 + e) * ldw));
+        }
+    for (int s0 = 0; s0 < n; s0 += GEMM_DEPTH) {
+#pragma unroll
+        for (int d = 0; d < GEMM_DEPTH; ++d) {
+            const int s = s0 + d;
+            if (s < n) {
+                const float4 w0 = w[d][0], w1 = w[d][1], w2 = w[d][2], w3 = w[d][3];
+                if (s + GEMM_DEPTH < n) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        w[d][e] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)((s + GEMM_DEPTH) * 4 + e) * ldw));
+                }
+                const int k = s * 4;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float4 x = *reinterpret_cast<const float4*>(sA + (row0 + r) * lda + k);
+                    acc[r][0] = fmaf(x.x, w0.x, fmaf(x.y, w1.x, fmaf(x.z, w2.x, fmaf(x.w, w3.x, acc[r][0]))));
+                    acc[r][1] = fmaf(x.x, w0.y, fmaf(x.y, w1.y, fmaf(x.z, w2.y, fmaf(x.w, w3.y, acc[r][1]))));
+                    acc[r][2] = fmaf(x.x, w0.z, fmaf(x.y, w1.z, fmaf(x.z, w2.z, fmaf(x.w, w3.z, acc[r][2]))));
+                    acc[r][3] = fmaf(x.x, w0.w, fmaf(x.y, w1.w, fmaf(x.z, w2.w, fmaf(x.w, w3.w, acc[r][3]))));
+                }
+            }
         }
     }
 }
@@ -91,13 +123,13 @@ __device__ __forceinline__ void outer8x8_flush(const float* __restrict__ sU, int
 }
 
 template <int RAYS>      // rays per CTA: 64, or 32 for batches that would not fill the SMs
-__global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_constant__ ShadeBwdArgs a) {
-    constexpr int SB_RAYS = RAYS, R = RAYS / 8, RSHIFT = RAYS == 64 ? 6 : 5;   // R rays per warp in the GEMM phases
+__global__ void __launch_bounds__(SB_THREADS, RAYS == 32 ? TVM_SHADE_BWD_SMALL_BLOCKS : 1) shade_bwd_kernel(const __grid_constant__ ShadeBwdArgs a) {
+    constexpr int SB_RAYS = RAYS, R = RAYS / 8;   // R rays per warp in the GEMM phases
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ta = a.ta, k1 = a.m.k1, fs = ta + 4;
-    float* sB = smem;                          // basis^T padded [ta][32]
-    float* sF = sB + ta * 32;                  // ray_feat tile [64][ta+4]
+    float* sB = smem;                          // basis^T padded [ta][BS] (columns >= app_dim zero)
+    float* sF = sB + ta * BS;                  // ray_feat tile [64][ta+4]
     float* sX = sF + SB_RAYS * fs;             // MLP input [64][k1]
     float* sH1 = sX + SB_RAYS * k1;            // [64][FC]
     float* sH2 = sH1 + SB_RAYS * FC;           // [64][FC]
@@ -112,11 +144,11 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
     // ================= forward recompute (same as shade_fwd_kernel) =================
     for (int i = tid; i < a.app_dim * ta; i += SB_THREADS) {
         const int j = i / ta, c = i - j * ta;
-        sB[c * 32 + j] = __ldg(a.basis + i);
+        sB[c * BS + j] = __ldg(a.basis + i);
     }
     for (int i = tid; i < (32 - a.app_dim) * ta; i += SB_THREADS) {
         const int c = i / (32 - a.app_dim), j = a.app_dim + i - c * (32 - a.app_dim);
-        sB[c * 32 + j] = 0.f;
+        sB[c * BS + j] = 0.f;
     }
     for (int i = tid; i < SB_RAYS * (ta >> 2); i += SB_THREADS) {
         const int ray = i / (ta >> 2), c4 = i - ray * (ta >> 2);
@@ -133,10 +165,10 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
 #pragma unroll
         for (int rr = 0; rr < RB; ++rr) o[rr][0] = o[rr][1] = o[rr][2] = o[rr][3] = 0.f;
         for (int c = 0; c < ta; c += 4) {
-            const float4 q0 = *reinterpret_cast<const float4*>(sB + (c + 0) * 32 + tx * 4);
-            const float4 q1 = *reinterpret_cast<const float4*>(sB + (c + 1) * 32 + tx * 4);
-            const float4 q2 = *reinterpret_cast<const float4*>(sB + (c + 2) * 32 + tx * 4);
-            const float4 q3 = *reinterpret_cast<const float4*>(sB + (c + 3) * 32 + tx * 4);
+            const float4 q0 = *reinterpret_cast<const float4*>(sB + (c + 0) * BS + tx * 4);
+            const float4 q1 = *reinterpret_cast<const float4*>(sB + (c + 1) * BS + tx * 4);
+            const float4 q2 = *reinterpret_cast<const float4*>(sB + (c + 2) * BS + tx * 4);
+            const float4 q3 = *reinterpret_cast<const float4*>(sB + (c + 3) * BS + tx * 4);
 #pragma unroll
             for (int rr = 0; rr < RB; ++rr) {
                 const float4 x = *reinterpret_cast<const float4*>(sF + (ty * RB + rr) * fs + c);
@@ -165,8 +197,10 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
     const int nbase = a.app_dim + 3;
     const int sin_f = nbase, cos_f = sin_f + a.app_dim * a.fea_pe;
     const int sin_v = cos_f + a.app_dim * a.fea_pe, cos_v = sin_v + 3 * a.view_pe;
-    for (int it = tid; it < SB_RAYS * nbase; it += SB_THREADS) {
-        const int ray = it & (SB_RAYS - 1), ch = it >> RSHIFT;
+    const int chs = nbase > 32 ? 6 : 5;                           // lanes run over the channels of one ray
+    for (int it = tid; it < (SB_RAYS << chs); it += SB_THREADS) {
+        const int ch = it & ((1 << chs) - 1), ray = it >> chs;
+        if (ch >= nbase) continue;
         const float v = sX[ray * k1 + ch];
         const bool is_feat = ch < a.app_dim;
         const int nf = is_feat ? a.fea_pe : a.view_pe;
@@ -337,7 +371,7 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
     // g_feat / g_view through the encodings: d sin(v 2^j) = 2^j cos, d cos(v 2^j) = -2^j sin (values are still in sX)
     float* sGF = sG;                             // g_feat [64][32] (cols >= app_dim zero), g_h1 is dead
     for (int it = tid; it < SB_RAYS * 32; it += SB_THREADS) {
-        const int ray = it & (SB_RAYS - 1), ch = it >> RSHIFT;
+        const int ch = it & 31, ray = it >> 5;
         float g = 0.f;
         if (ch < nbase) {
             const bool is_feat = ch < a.app_dim;
@@ -366,7 +400,11 @@ __global__ void __launch_bounds__(SB_THREADS, 1) shade_bwd_kernel(const __grid_c
         const int ray = i / ta, c = i - ray * ta;
         const long long r = r0 + ray;
         float s = 0.f;
-        for (int j = 0; j < a.app_dim; ++j) s = fmaf(sGF[ray * 32 + j], sB[c * 32 + j], s);
+        for (int j = 0; j < a.app_dim; j += 4) {          // both rows are zero-padded to 32 columns
+            const float4 gq = *reinterpret_cast<const float4*>(sGF + ray * 32 + j);
+            const float4 bq = *reinterpret_cast<const float4*>(sB + c * BS + j);
+            s = fmaf(gq.x, bq.x, fmaf(gq.y, bq.y, fmaf(gq.z, bq.z, fmaf(gq.w, bq.w, s))));
+        }
         if (r < a.n_rays) a.d_ray_feat[r * ta + c] = s;
     }
     if (a.g_basis) {
@@ -390,6 +428,7 @@ extern "C" int tvm_shade_bwd(const tvm_field_desc* desc, const float* rays, int6
     if (n_rays == 0) return 0;
     if (!rays || !bg || !d_rgb || !d_ray_feat || !d_acc || !ws || !desc->basis || !desc->mlp) return TVM_E_NULL;
     if (desc->feature_c != FC || desc->app_dim > 32 || desc->app_dim <= 0) return TVM_E_SHAPE;
+    if (d_view && desc->app_dim + 3 > 32) return TVM_E_SHAPE;    // the encoding backward walks 32 channels per ray
     const TvmWorkspace w = tvm_ws_layout(desc, n_rays);
     if (ws_bytes < w.total) return TVM_E_WORKSPACE;
     const char* base = (const char*)ws;
@@ -404,9 +443,9 @@ extern "C" int tvm_shade_bwd(const tvm_field_desc* desc, const float* rays, int6
     a.m = tvm_mlp_layout(desc);
     a.ta = tvm_total_app(desc); a.app_dim = desc->app_dim; a.fea_pe = desc->fea_pe; a.view_pe = desc->view_pe;
     if (a.m.k1 > 2 * FC || a.m.k1 % 8) return TVM_E_SHAPE;       // g_x reuses the h1|h2 span; 8-wide outer blocks
-    const bool small = (n_rays + 31) / 32 <= (long long)TVM_SM_COUNT;     // one wave of 32-ray tiles beats idle SMs
+    const bool small = TVM_SHADE_BWD_SMALL_ALWAYS || (n_rays + 31) / 32 <= (long long)TVM_SM_COUNT;     // one wave of 32-ray tiles beats idle SMs
     const size_t tile = small ? 32 : 64;
-    const size_t floats = (size_t)a.ta * 32 + tile * (a.ta + 4) + tile * a.m.k1 +
+    const size_t floats = (size_t)a.ta * BS + tile * (a.ta + 4) + tile * a.m.k1 +
                           tile * (a.m.k1 > FC ? a.m.k1 : FC) + tile * FC * 2 + tile * 8;
     const size_t smem = floats * sizeof(float);
     if (smem > 227 * 1024) return TVM_E_SHAPE;

@@ -294,12 +294,16 @@ __global__ void __launch_bounds__(RB_THREADS) shade_ref_bwd_kernel(const __grid_
     float* s_par = smem;
     float* s_basis = s_par + L.total;                 // [IN_C][ta]
     float* sF = s_basis + IN_C * ta;                  // [64][IN4]
-    float* sGF = sF + RB_RAYS * IN4;                  // [64][IN4]
-    float* sGsm = sGF + RB_RAYS * IN4;                // [64][12]   g_small (10)
-    float* sGsp = sGsm + RB_RAYS * 12;                // [64][4]    g_sp (3)
-    float* sXt = sGsp + RB_RAYS * 4;                  // [64][RB_XT] encoding tail: enc (2 NP), n.v
-    float* sGb = sXt + RB_RAYS * RB_XT;               // [64][FC]   g_bottleneck
-    float* sRf = sGb + RB_RAYS * FC;                  // [64][ta]   ray_feat rows
+    // per-ray rows are written by one thread per ray: odd row strides keep those scalar accesses on distinct banks,
+    // and ta + 4 does the same for the float4 reads of the ray_feat rows
+    constexpr int SFS = IN4 + 1, SMS = 13, SPS = 5, XTS = RB_XT + 1;
+    const int GBS = FC + 1, RFS = ta + 4;
+    float* sGF = sF + RB_RAYS * SFS;                  // [64][IN4]
+    float* sGsm = sGF + RB_RAYS * SFS;                // [64][10]   g_small
+    float* sGsp = sGsm + RB_RAYS * SMS;               // [64][3]    g_sp
+    float* sXt = sGsp + RB_RAYS * SPS;                // [64][RB_XT] encoding tail: enc (2 NP), n.v
+    float* sGb = sXt + RB_RAYS * XTS;                 // [64][FC]   g_bottleneck
+    float* sRf = sGb + RB_RAYS * GBS;                 // [64][ta]   ray_feat rows (16-byte aligned: 64 x anything)
     const int tid = threadIdx.x;
     for (int i = tid; i < L.total; i += RB_THREADS) s_par[i] = __ldg(h.params + i);
     for (int i = tid; i < IN_C * ta; i += RB_THREADS) s_basis[i] = __ldg(a.f.basis + i);
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(RB_THREADS) shade_ref_bwd_kernel(const __grid_
     for (int i = tid; i < RB_RAYS * (ta >> 2); i += RB_THREADS) {
         const int ray = i / (ta >> 2), c4 = i - ray * (ta >> 2);
         const long long r = r0 + ray;
-        reinterpret_cast<float4*>(sRf + ray * ta)[c4] =
+        reinterpret_cast<float4*>(sRf + ray * RFS)[c4] =
             r < a.n ? __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * ta) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
@@ -322,8 +326,8 @@ __global__ void __launch_bounds__(RB_THREADS) shade_ref_bwd_kernel(const __grid_
         float gsm[10], gsp[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int o = 0; o < 10; ++o) gsm[o] = 0.f;
-        for (int j = 0; j < RB_XT; ++j) sXt[ray * RB_XT + j] = 0.f;
-        for (int j = 0; j < FC; ++j) sGb[ray * FC + j] = 0.f;
+        for (int j = 0; j < RB_XT; ++j) sXt[ray * XTS + j] = 0.f;
+        for (int j = 0; j < FC; ++j) sGb[ray * GBS + j] = 0.f;
         float d_acc = 0.f, gv[3] = {0.f, 0.f, 0.f};
         if (live) {
             const float* rp = a.rays + r * a.ray_stride;
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(RB_THREADS) shade_ref_bwd_kernel(const __grid_
             d_acc = a.d_acc_in ? __ldg(a.d_acc_in + r) : 0.f;
             // ---------------- forward (same arithmetic as shade_ref_kernel) ----------------
             for (int c4 = 0; c4 < (ta >> 2); ++c4) {
-                const float4 x = *reinterpret_cast<const float4*>(sRf + ray * ta + 4 * c4);
+                const float4 x = *reinterpret_cast<const float4*>(sRf + ray * RFS + 4 * c4);
 #pragma unroll
                 for (int i = 0; i < IN_C; ++i) {
                     const float4 b = *reinterpret_cast<const float4*>(s_basis + i * ta + 4 * c4);
@@ -383,13 +387,13 @@ __global__ void __launch_bounds__(RB_THREADS) shade_ref_bwd_kernel(const __grid_
                 for (int k = 0; k <= h.l_max; ++k) poly = fmaf(zp[k], s_par[L.ide_mat + k * NP + p], poly);
                 const float att = expf(-(0.5f * (float)l * (float)(l + 1)) * rough);
                 const float re = cre[m] * poly * att, im = cim[m] * poly * att;
-                sXt[ray * RB_XT + 2 * p] = re;
-                sXt[ray * RB_XT + 2 * p + 1] = im;
+                sXt[ray * XTS + 2 * p] = re;
+                sXt[ray * XTS + 2 * p + 1] = im;
 #pragma unroll
                 for (int o = 0; o < 3; ++o)
                     sp[o] = fmaf(s_par[L.spec_w + o * SW + FC + 2 * p], re, fmaf(s_par[L.spec_w + o * SW + FC + 2 * p + 1], im, sp[o]));
             }
-            sXt[ray * RB_XT + 2 * NP] = ndv;
+            sXt[ray * XTS + 2 * NP] = ndv;
             float S[3], lin[3], srgb[3], rgb[3];
             const float eps = 1.1920928955078125e-07f;
 #pragma unroll
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(RB_THREADS) shade_ref_bwd_kernel(const __grid_
                 // bottleneck columns: g_b[j] = sum_o g_sp[o] Ws[o][j];  g_F += Wb^T g_b
                 for (int j = 0; j < FC; ++j) {
                     const float gb = gsp[0] * s_par[L.spec_w + j] + gsp[1] * s_par[L.spec_w + SW + j] + gsp[2] * s_par[L.spec_w + 2 * SW + j];
-                    sGb[ray * FC + j] = gb;
+                    sGb[ray * GBS + j] = gb;
                     const float* wrow = s_par + L.bott_w + j * IN4;
 #pragma unroll
                     for (int i = 0; i < IN_C; ++i) gF[i] = fmaf(wrow[i], gb, gF[i]);
@@ -507,11 +511,11 @@ __global__ void __launch_bounds__(RB_THREADS) shade_ref_bwd_kernel(const __grid_
             if (a.d_view) { a.d_view[r * 3] = gv[0]; a.d_view[r * 3 + 1] = gv[1]; a.d_view[r * 3 + 2] = gv[2]; }
         }
 #pragma unroll
-        for (int i = 0; i < IN4; ++i) { sF[ray * IN4 + i] = F[i]; sGF[ray * IN4 + i] = gF[i]; }
+        for (int i = 0; i < IN4; ++i) { sF[ray * SFS + i] = F[i]; sGF[ray * SFS + i] = gF[i]; }
 #pragma unroll
-        for (int o = 0; o < 10; ++o) sGsm[ray * 12 + o] = gsm[o];
+        for (int o = 0; o < 10; ++o) sGsm[ray * SMS + o] = gsm[o];
 #pragma unroll
-        for (int o = 0; o < 3; ++o) sGsp[ray * 4 + o] = gsp[o];
+        for (int o = 0; o < 3; ++o) sGsp[ray * SPS + o] = gsp[o];
     }
     __syncthreads();
 
@@ -524,10 +528,10 @@ __global__ void __launch_bounds__(RB_THREADS) shade_ref_bwd_kernel(const __grid_
 #pragma unroll
             for (int i = 0; i < IN4; ++i) accw[i] = 0.f;
             for (int ray = 0; ray < RB_RAYS; ++ray) {
-                const float g = row < 10 ? sGsm[ray * 12 + row] : sGb[ray * FC + (row - 10)];
+                const float g = row < 10 ? sGsm[ray * SMS + row] : sGb[ray * GBS + (row - 10)];
                 accb += g;
 #pragma unroll
-                for (int i = 0; i < IN_C; ++i) accw[i] = fmaf(g, sF[ray * IN4 + i], accw[i]);
+                for (int i = 0; i < IN_C; ++i) accw[i] = fmaf(g, sF[ray * SFS + i], accw[i]);
             }
             const int woff = row < 10 ? L.small_w + row * IN4 : L.bott_w + (row - 10) * IN4;
             const int boff = row < 10 ? L.small_b + row : L.bott_b + (row - 10);
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(RB_THREADS) shade_ref_bwd_kernel(const __grid_
         if (tid < 3 * (IN_C + 1)) {
             const int o = tid / (IN_C + 1), i = tid - o * (IN_C + 1);
             float s = 0.f;
-            for (int ray = 0; ray < RB_RAYS; ++ray) s = fmaf(sGsp[ray * 4 + o], i < IN_C ? sF[ray * IN4 + i] : 1.f, s);
+            for (int ray = 0; ray < RB_RAYS; ++ray) s = fmaf(sGsp[ray * SPS + o], i < IN_C ? sF[ray * SFS + i] : 1.f, s);
             sM[o][i] = s;                       // column IN_C holds s[o]
         }
         __syncthreads();
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(RB_THREADS) shade_ref_bwd_kernel(const __grid_
                 g = s_par[L.bott_b + j] * sM[o][IN_C];
                 for (int i = 0; i < IN_C; ++i) g = fmaf(s_par[L.bott_w + j * IN4 + i], sM[o][i], g);
             } else {
-                for (int ray = 0; ray < RB_RAYS; ++ray) g = fmaf(sGsp[ray * 4 + o], sXt[ray * RB_XT + (j - FC)], g);
+                for (int ray = 0; ray < RB_RAYS; ++ray) g = fmaf(sGsp[ray * SPS + o], sXt[ray * XTS + (j - FC)], g);
             }
             atomicAdd(G + L.spec_w + e, g);
         }
@@ -562,8 +566,8 @@ __global__ void __launch_bounds__(RB_THREADS) shade_ref_bwd_kernel(const __grid_
             const int i = e / (ta >> 2), c4 = e - i * (ta >> 2);
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int ray = 0; ray < RB_RAYS; ++ray) {
-                const float g = sGF[ray * IN4 + i];
-                const float4 x = *reinterpret_cast<const float4*>(sRf + ray * ta + 4 * c4);
+                const float g = sGF[ray * SFS + i];
+                const float4 x = *reinterpret_cast<const float4*>(sRf + ray * RFS + 4 * c4);
                 s.x = fmaf(g, x.x, s.x); s.y = fmaf(g, x.y, s.y); s.z = fmaf(g, x.z, s.z); s.w = fmaf(g, x.w, s.w);
             }
             atomicAdd(reinterpret_cast<float4*>(a.g_basis + (size_t)i * ta) + c4, s);
@@ -595,7 +599,7 @@ extern "C" int tvm_shade_ref_bwd(const tvm_field_desc* desc, const tvm_ref_head*
     a.ta = tvm_total_app(desc);
     const RefLayout L = ref_layout(*head);
     const int in4 = L.in4;
-    const size_t floats = (size_t)L.total + (size_t)head->in_c * a.ta + (size_t)RB_RAYS * (2 * in4 + 12 + 4 + RB_XT + head->feature_c + a.ta);
+    const size_t floats = (size_t)L.total + (size_t)head->in_c * a.ta + (size_t)RB_RAYS * (2 * (in4 + 1) + 13 + 5 + (RB_XT + 1) + (head->feature_c + 1) + (a.ta + 4));
     const size_t smem = floats * sizeof(float);
     if (smem > 220 * 1024) return TVM_E_SHAPE;
     static std::atomic<int> smem_set{0};

@@ -7,10 +7,9 @@ from iffnerf_b200 import build
 
 out_dir = os.path.join(ROOT, "iffnerf_b200", "variants")
 os.makedirs(out_dir, exist_ok=True)
-combos = [(1, 12, 1), (1, 12, 0), (2, 6, 2), (4, 3, 0)]
-for warps, mb, rpc in combos:
-    tag = f"bwd_w{warps}_b{mb}_r{rpc}"
+combos = [(2, 1), (2, 0)]
+for blocks, always in combos:
+    tag = f"sbwd_b{blocks}_a{always}"
     out = os.path.join(out_dir, f"libtvm_{tag}.so")
-    defs = [f"TVM_BWD_WARPS={warps}", f"TVM_BWD_MIN_BLOCKS={mb}"] + ([f"TVM_BWD_RPC_FIXED={rpc}"] if rpc else [])
-    build.build(defines=defs, out=out)
+    build.build(defines=[f"TVM_SHADE_BWD_SMALL_BLOCKS={blocks}", f"TVM_SHADE_BWD_SMALL_ALWAYS={always}"], out=out)
     print(out)
