@@ -57,7 +57,7 @@ class _Render(torch.autograd.Function):
                                       _lib.ptr(ws), ws.numel(), _stream(dev)), "tvm_render_fwd")
         ctx.model, ctx.S, ctx.jit, ctx.rays_c, ctx.ws, ctx.bg = model, S, jit, rays_c, ws, bg_c
         ctx.ray_cols = rays.shape[1]
-        ctx.flags = flags
+        ctx.flags = flags & ~(_lib.F_MLP_TC3 | _lib.F_MLP_BF16)      # the backward kernels take the sampler bits only
         ctx.keys = (model._packed_key, model._mlp_key)
         if want_samples:
             ctx.mark_non_differentiable(depth, z, dists)
@@ -133,6 +133,11 @@ def render_with_grad(model, rays_chunk, white_bg, bg_color, N_samples, jitter, p
     flags = _lib.F_POINT_SAMPLES if point_samples else 0
     if not want_samples and model.early_term_eps > 0:
         flags |= _lib.F_EARLY_TERM
+    if (model.grad_forward_tc3 and model.native_shade and model._shade_mode() == "tc3"
+            and not any(p.requires_grad for p in _mlp_params(model))):
+        # frozen head (pose refinement): the forward shades on the tensor cores (bf16x3 split, 5e-7 from the FFMA
+        # kernel); tvm_shade_bwd re-derives the activations in fp32 either way
+        flags |= _lib.F_MLP_TC3
     return _Render.apply(model, rays, S, jitter, bg, flags, *planes, *lines, model.basis_mat.weight,
                          *_mlp_params(model))
 

@@ -120,6 +120,7 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
     # False returns None for them; rays then terminate at T < early_term_eps in forward AND backward, which is what the
     # pose-refinement loop wants (inerf/estimate_pose_inerf.py:166 reads rgb and opacity only).
     eval_sample_outputs = True
+    grad_forward_tc3 = True      # differentiable forward with a frozen MLP_Fea head (pose mode): tensor-core shading kernel
     ref_kernel_train = True      # `Ref` head, training: fused tail backward kernel (False: torch autograd through the head)
     ref_kernel = True            # `Ref` head, eval: fused tail kernel (False: the torch-op tail, kept for cross-checks)
     # transmittance below which an eval ray stops marching (error on rgb/acc <= this value)

@@ -66,13 +66,17 @@ def test_train_step_matches_reference_golden(lego, dev):
     m.zero_grad()
 
 
-def test_pose_gradients_match_reference_golden(lego, dev):
-    """inerf/estimate_pose_inerf.py:164-178: frozen factors, random background, MSE, gradient w.r.t. the rays."""
+@pytest.mark.parametrize("tc3_forward", [True, False])
+def test_pose_gradients_match_reference_golden(lego, dev, tc3_forward):
+    """inerf/estimate_pose_inerf.py:164-178: frozen factors, random background, MSE, gradient w.r.t. the rays.
+    With a frozen head the differentiable forward shades on the tensor cores (grad_forward_tc3) — both variants are
+    held to the reference's rgb and d(rays)."""
     fld, rays, m = lego
     g = H.golden("c5_pose")
     sub, _ = fx.subsample(rays, 512, seed=2)
     for p in m.parameters():
         p.requires_grad_(False)
+    m.grad_forward_tc3 = tc3_forward
     try:
         r = sub.to(dev).requires_grad_(True)
         rgb, _, acc, _, _, _ = m(r, bg_color=torch.from_numpy(g["bg"]).to(dev), is_train=False)
@@ -80,6 +84,7 @@ def test_pose_gradients_match_reference_golden(lego, dev):
         loss.backward()
         torch.cuda.synchronize()
     finally:
+        m.grad_forward_tc3 = type(m).grad_forward_tc3
         for p in m.parameters():
             p.requires_grad_(True)
     assert np.abs(rgb.detach().cpu().numpy() - g["rgb_map"]).max() <= 1e-4
