@@ -260,7 +260,10 @@ extern "C" int tvm_shade_ref_fwd(const tvm_field_desc* desc, const tvm_ref_head*
 // =====================================================================================================================
 namespace {
 
-constexpr int RB_RAYS = 64;
+#ifndef TVM_REF_BWD_RAYS
+#define TVM_REF_BWD_RAYS 64
+#endif
+constexpr int RB_RAYS = TVM_REF_BWD_RAYS;     // rays per CTA (one thread per ray in the per-ray phase)
 constexpr int RB_THREADS = 128;
 constexpr int RB_XT = 40;            // encoding tail (2 n_pairs + 1 <= 39) padded
 

@@ -7,9 +7,9 @@ from iffnerf_b200 import build
 
 out_dir = os.path.join(ROOT, "iffnerf_b200", "variants")
 os.makedirs(out_dir, exist_ok=True)
-combos = [(2, 1), (2, 0)]
-for blocks, always in combos:
-    tag = f"sbwd_b{blocks}_a{always}"
+combos = [32, 64, 128]
+for rays in combos:
+    tag = f"refbwd_r{rays}"
     out = os.path.join(out_dir, f"libtvm_{tag}.so")
-    build.build(defines=[f"TVM_SHADE_BWD_SMALL_BLOCKS={blocks}", f"TVM_SHADE_BWD_SMALL_ALWAYS={always}"], out=out)
+    build.build(defines=[f"TVM_REF_BWD_RAYS={rays}"], out=out)
     print(out)
