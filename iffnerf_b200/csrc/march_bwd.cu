@@ -21,6 +21,12 @@ namespace {
 #ifndef TVM_BWD_MIN_BLOCKS
 #define TVM_BWD_MIN_BLOCKS 3
 #endif
+#ifndef TVM_BWD_ROLL_APP
+#define TVM_BWD_ROLL_APP 1        // compact appearance pass (app_bwd_rolled); 0: fully unrolled app_bwd with gF in registers
+#endif
+#ifndef TVM_BWD_MIN_BLOCKS_POSE
+#define TVM_BWD_MIN_BLOCKS_POSE 4   // pose-only instantiation (no scatter): 128 registers, 16 warps/SM
+#endif
 #ifndef TVM_BWD_WARPS
 #define TVM_BWD_WARPS 4
 #endif
@@ -60,7 +66,8 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 template <int G, bool SCATTER, bool POSE, int CS4, int CA4>
-__global__ void __launch_bounds__(BWD_WARPS * 32, TVM_BWD_MIN_BLOCKS) march_bwd_kernel(const __grid_constant__ BwdArgs a) {
+__global__ void __launch_bounds__(BWD_WARPS * 32, SCATTER ? TVM_BWD_MIN_BLOCKS : TVM_BWD_MIN_BLOCKS_POSE)
+march_bwd_kernel(const __grid_constant__ BwdArgs a) {
     __shared__ int s_next;
     __shared__ float4 s_slot[BWD_WARPS][32];
     __shared__ float s_ret[BWD_WARPS][32];
@@ -186,7 +193,12 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, TVM_BWD_MIN_BLOCKS) march_bwd_
                         if (ci < na) {
                             const float4 s = s_slot[warp][ci];
                             const float q[3] = {s.x, s.y, s.z};
+#if TVM_BWD_ROLL_APP
+                            dot = app_bwd_rolled<G, SCATTER, POSE, CA4>(f, q, s.w, sub, a.d_ray_feat + r * a.ta, a.app_off,
+                                                                        a.g_factors, dn);
+#else
                             dot = app_bwd<G, SCATTER, POSE, CA4>(f, q, s.w, sub, gF, a.g_factors, dn);
+#endif
                         }
                         dot = quad_sum(dot);
                         if (POSE) {

@@ -269,6 +269,31 @@ TVM_HD float density_bwd(const tvm_field_desc& f, const float n[3], float dfeat,
     return tot;
 }
 
+// appearance, compact-code form: the upstream slices are re-read from the ray's d_ray_feat row (L1-resident, one
+// broadcast wavefront per slice) instead of living in 9 float4 registers, and the channel-group loop is not unrolled —
+// a third of the instructions of app_bwd for the same arithmetic.  gRow = d_ray_feat + r * ta (16-byte aligned).
+template <int G, bool SCATTER, bool POSE, int CA4 = 0>
+TVM_HD float app_bwd_rolled(const tvm_field_desc& f, const float n[3], float w, int sub, const float* __restrict__ gRow,
+                            const int (&app_off)[3], float* gbuf, float dn[3]) {
+    float dot = 0.f;
+    const SampleTaps st = make_sample_taps(f, n);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int C4 = CA4 > 0 ? CA4 : (f.n_app[k] >> 2);
+        const PlaneTaps t = make_taps(f, st, k, C4);
+        const float4* gk = reinterpret_cast<const float4*>(gRow + app_off[k]);
+#pragma unroll 1
+        for (int j = sub; j < C4; j += 4) {
+            const float4 g4 = TVM_LDG4(gk + j);
+            const float4 phi = vm_slice_bwd<SCATTER, POSE>(
+                f, reinterpret_cast<const float4*>(f.factors), reinterpret_cast<float4*>(gbuf),
+                (unsigned)(f.aplane_off[k] >> 2), (unsigned)(f.aline_off[k] >> 2), st, t, C4, j, f4_scale(w, g4), k, dn);
+            dot += f4_dot(g4, phi);
+        }
+    }
+    return dot;
+}
+
 // appearance: upstream on (plane (x) line)[c] is w * gF[c].  Returns this lane's share of gF . phi.
 template <int G, bool SCATTER, bool POSE, int CA4 = 0>
 TVM_HD float app_bwd(const tvm_field_desc& f, const float n[3], float w, int sub, const float4 (&gF)[3][G],

@@ -7,9 +7,9 @@ from iffnerf_b200 import build
 
 out_dir = os.path.join(ROOT, "iffnerf_b200", "variants")
 os.makedirs(out_dir, exist_ok=True)
-combos = [32, 64, 128]
-for rays in combos:
-    tag = f"refbwd_r{rays}"
+combos = [(0, 3), (1, 3), (1, 4)]
+for roll, mb in combos:
+    tag = f"bwd_roll{roll}_b{mb}"
     out = os.path.join(out_dir, f"libtvm_{tag}.so")
-    build.build(defines=[f"TVM_REF_BWD_RAYS={rays}"], out=out)
+    build.build(defines=[f"TVM_BWD_ROLL_APP={roll}", f"TVM_BWD_MIN_BLOCKS={mb}"], out=out)
     print(out)
