@@ -128,14 +128,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
         tc_fence_after();
         {
             // MLP input row (tensorBase.py:186-191): [feat | view | sin(feat 2^j) | cos | sin(view 2^j) | cos], zero pad.
-            // Every warp reads the 32 feature columns of its lanes; channel ch is encoded by column group ch & 3.
-            float v[32];
-            tmem_ld32(lane_base + COL0, v);
+            // Column group cg encodes channels 8 cg .. 8 cg + 7 of its lanes' rows (8 copies of the encoding code
+            // instead of 32: instruction-cache footprint).
+            float v[8];
+            tmem_ld8(lane_base + COL0 + 8 * cg, v);
 #pragma unroll
-            for (int ch = 0; ch < 32; ++ch) {
-                if ((ch & 3) != cg || ch >= nbase) continue;
+            for (int e = 0; e < 8; ++e) {
+                const int ch = 8 * cg + e;
+                if (ch >= nbase) continue;
                 const bool is_feat = ch < d.app_dim;
-                float x = v[ch];
+                float x = v[e];
                 if (!is_feat) x = live ? __ldg(a.rays + r * a.ray_stride + 3 + (ch - d.app_dim)) : 0.f;
                 *reinterpret_cast<__nv_bfloat16*>(s_x + canon_off(row, ch, d.k1)) = __float2bfloat16_rn(x);
                 const int nf = is_feat ? d.fea_pe : d.view_pe;

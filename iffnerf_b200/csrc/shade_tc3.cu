@@ -191,13 +191,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
         mbar_wait(bar, phase); phase ^= 1;
         tc_fence_after();
         {
-            float v[32];
-            tmem_ld32(lane_base + COL0, v);
+            // column group cg encodes channels 8 cg .. 8 cg + 7 of this row (8 copies of the encoding code, not 32:
+            // the unrolled 32-channel form was 131 KB of SASS and stalled on instruction fetch)
+            float v[8];
+            tmem_ld8(lane_base + COL0 + 8 * cg, v);
 #pragma unroll
-            for (int ch = 0; ch < 32; ++ch) {
-                if ((ch & 3) != cg || ch >= nbase) continue;
+            for (int e = 0; e < 8; ++e) {
+                const int ch = 8 * cg + e;
+                if (ch >= nbase) continue;
                 const bool is_feat = ch < d.app_dim;
-                float x = v[ch];
+                float x = v[e];
                 if (!is_feat) x = live ? __ldg(a.rays + r * a.ray_stride + 3 + (ch - d.app_dim)) : 0.f;
                 split_store1(s_ah, s_al, canon_off(row, ch, d.k1), x);
                 const int nf = is_feat ? d.fea_pe : d.view_pe;
