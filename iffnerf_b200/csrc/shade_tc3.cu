@@ -11,6 +11,11 @@
 // next tile's W1 under the last epilogues and the next staging; only the MMA-issuing thread ever waits for them.  One persistent CTA (16 warps) per SM, 128 rays per tile, TMEM lane == ray.
 #include "tvm_tc.cuh"
 
+#ifndef TVM_TC3_PE_UNROLL
+#define TVM_TC3_PE_UNROLL 8
+#endif
+constexpr int PE_UNROLL = TVM_TC3_PE_UNROLL;     // copies of the encoding body (sincosf is inlined with its slow path)
+
 namespace {
 using namespace tvmtc;
 
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
             // the unrolled 32-channel form was 131 KB of SASS and stalled on instruction fetch)
             float v[8];
             tmem_ld8(lane_base + COL0 + 8 * cg, v);
-#pragma unroll
+#pragma unroll PE_UNROLL
             for (int e = 0; e < 8; ++e) {
                 const int ch = 8 * cg + e;
                 if (ch >= nbase) continue;

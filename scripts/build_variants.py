@@ -7,9 +7,9 @@ from iffnerf_b200 import build
 
 out_dir = os.path.join(ROOT, "iffnerf_b200", "variants")
 os.makedirs(out_dir, exist_ok=True)
-combos = [(0, 3), (1, 3), (1, 4)]
-for roll, mb in combos:
-    tag = f"bwd_roll{roll}_b{mb}"
+combos = [1, 2, 8]
+for u in combos:
+    tag = f"tc3_pe{u}"
     out = os.path.join(out_dir, f"libtvm_{tag}.so")
-    build.build(defines=[f"TVM_BWD_ROLL_APP={roll}", f"TVM_BWD_MIN_BLOCKS={mb}"], out=out)
+    build.build(defines=[f"TVM_TC3_PE_UNROLL={u}"], out=out)
     print(out)
