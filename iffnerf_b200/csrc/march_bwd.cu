@@ -25,7 +25,7 @@ namespace {
 #define TVM_BWD_ROLL_APP 1        // compact appearance pass (app_bwd_rolled); 0: fully unrolled app_bwd with gF in registers
 #endif
 #ifndef TVM_BWD_MIN_BLOCKS_POSE
-#define TVM_BWD_MIN_BLOCKS_POSE 4   // pose-only instantiation (no scatter): 128 registers, 16 warps/SM
+#define TVM_BWD_MIN_BLOCKS_POSE 5   // pose-only instantiation (no scatter): 96 registers, 20 warps/SM (6 spills)
 #endif
 #ifndef TVM_BWD_WARPS
 #define TVM_BWD_WARPS 4

@@ -7,9 +7,9 @@ from iffnerf_b200 import build
 
 out_dir = os.path.join(ROOT, "iffnerf_b200", "variants")
 os.makedirs(out_dir, exist_ok=True)
-combos = [1, 2, 8]
-for u in combos:
-    tag = f"tc3_pe{u}"
+combos = [5, 6]
+for mb in combos:
+    tag = f"bwd_pose_b{mb}"
     out = os.path.join(out_dir, f"libtvm_{tag}.so")
-    build.build(defines=[f"TVM_TC3_PE_UNROLL={u}"], out=out)
+    build.build(defines=[f"TVM_BWD_MIN_BLOCKS_POSE={mb}"], out=out)
     print(out)
