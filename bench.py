@@ -522,7 +522,7 @@ def run_ours(args, rank, world, local_rank):
             for rep in range(4):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                _lib.check(lib.tvm_gather_microbench(_lib.ptr(pf), nbytes // gran * gran, gran, 128, _lib.ptr(sink),
+                _lib.check(_lib.load_bench().tvm_gather_microbench(_lib.ptr(pf), nbytes // gran * gran, gran, 128, _lib.ptr(sink),
                                                      C.byref(moved), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
                            "tvm_gather_microbench")
                 e1.record()

@@ -12,13 +12,16 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_B200_LIB lets the tuning scripts load a differently-compiled build of the SAME sources
 LIB_PATH = os.environ.get("TVM_B200_LIB") or os.path.join(_HERE, "libtvm_b200.so")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 F_EARLY_TERM = 1 << 0
 F_MLP_BF16 = 1 << 1
 F_NO_SHADE = 1 << 2
 F_POINT_SAMPLES = 1 << 3
 F_MLP_TC3 = 1 << 4
+F_SPLIT_APP = 1 << 5
+F_ZERO_UNLIT = 1 << 6
+F_MASK_ANYWHERE = 1 << 7
 
 _f3 = C.c_float * 3
 _f6 = C.c_float * 6
@@ -98,7 +101,11 @@ _SIGNATURES = {
     "tvm_pixel_rays_fwd": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _P, _P, C.c_int, C.c_int64, C.c_int, _P, _P]),
     "tvm_pixel_rays_bwd": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _P, _P, C.c_int, C.c_int64, C.c_int, _P, C.c_int,
                                      _P, _P]),
-    "tvm_gather_microbench": (C.c_int, [_P, C.c_size_t, C.c_int, C.c_int, _P, C.POINTER(C.c_ulonglong), _P]),
+    "tvm_dense_alpha_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "tvm_dense_alpha_mask": (C.c_int, [C.POINTER(FieldDesc), _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                       _P, _P, _P, C.c_size_t, _P]),
+    "tvm_resize_factor": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "tvm_rays_hit_box": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, _P, _P]),
     "tvm_workspace_layout": (C.c_int, [C.POINTER(FieldDesc), C.c_int64] + [C.POINTER(C.c_size_t)] * 6),
 }
 
@@ -127,6 +134,23 @@ def load():
         raise TvmError(f"libtvm_b200.so ABI {v} != binding ABI {ABI_VERSION}; rebuild the library")
     _lib = lib
     return lib
+
+
+_bench = None
+BENCH_LIB_PATH = os.path.join(_HERE, "libtvm_bench.so")
+
+
+def load_bench():
+    """Measurement aids (include/tvm_bench.h) — a separate library, never loaded by the render path."""
+    global _bench
+    if _bench is None:
+        if not os.path.exists(BENCH_LIB_PATH):
+            raise TvmError(f"{BENCH_LIB_PATH} not found; build it with `python -m iffnerf_b200.build`")
+        lib = C.CDLL(BENCH_LIB_PATH)
+        lib.tvm_gather_microbench.restype = C.c_int
+        lib.tvm_gather_microbench.argtypes = [_P, C.c_size_t, C.c_int, C.c_int, _P, C.POINTER(C.c_ulonglong), _P]
+        _bench = lib
+    return _bench
 
 
 def check(code: int, what: str):

@@ -13,7 +13,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtvm_b200.so")
-SOURCES = ["pack.cu", "march.cu", "march_bwd.cu", "shade.cu", "shade_bwd.cu", "shade_tc.cu", "shade_tc3.cu", "shade_ref.cu", "query.cu", "raygen.cu", "microbench.cu"]
+SOURCES = ["pack.cu", "march.cu", "march_bwd.cu", "shade.cu", "shade_bwd.cu", "shade_tc.cu", "shade_tc3.cu", "shade_ref.cu", "query.cu", "raygen.cu", "gridops.cu"]
+BENCH_LIB = os.path.join(HERE, "libtvm_bench.so")      # measurement aids (include/tvm_bench.h), not part of the product library
+BENCH_SOURCES = ["microbench.cu"]
 HEADERS = ["tvm_math.cuh", "tvm_common.cuh", "tvm_gather.cuh", "tvm_warp.cuh", "tvm_tc.cuh", os.path.join("..", "..", "include", "tvm_b200.h")]
 
 NVCC_FLAGS = [
@@ -33,7 +35,7 @@ def is_stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + BENCH_SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -51,6 +53,12 @@ def build(verbose=False, force=False, defines=(), out=None):
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libtvm_b200.so")
+    if out == LIB:
+        res = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-o", BENCH_LIB] + [os.path.join(CSRC, s) for s in BENCH_SOURCES],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed building libtvm_bench.so")
     return out
 
 

@@ -33,6 +33,15 @@ namespace {
 #ifndef TVM_MARCH_CARVEOUT
 #define TVM_MARCH_CARVEOUT 14          // % of the 228 KB given to shared memory; the rest is the L1 the gathers live in
 #endif
+#ifndef TVM_EMIT_MIN_BLOCKS
+#define TVM_EMIT_MIN_BLOCKS 8           // sigma-march kernel of the split path: 64 registers, 32 warps / SM
+#endif
+#ifndef TVM_APP_MIN_BLOCKS
+#define TVM_APP_MIN_BLOCKS 4
+#endif
+#ifndef TVM_APP_CARVEOUT
+#define TVM_APP_CARVEOUT 25
+#endif
 constexpr int MARCH_WARPS = TVM_MARCH_WARPS;
 constexpr int MARCH_RAYS_PER_CTA = TVM_MARCH_RAYS_PER_CTA;
 constexpr unsigned FULL = 0xffffffffu;
@@ -63,6 +72,10 @@ struct MarchArgs {
     int app_off[3];
     int rays_per_cta;
     TvmSections sec;
+    // split path (TVM_F_SPLIT_APP): per-ray appearance sample lists, TVM_APP_CAP entries per ray
+    float4* app_w;          // (frac_x, frac_y, frac_z, weight)
+    unsigned* app_i;        // packed base texel indices (tvm_slot_from_idx)
+    int spill_cap;          // fused kernel as the overflow pass: only rays with app_count > spill_cap are marched (0 = all)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -71,8 +84,15 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-template <int G, bool MASK_ONLY, int CS4, int CA4>
-__global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_fwd_kernel(const __grid_constant__ MarchArgs a) {
+// EMIT: split path, stage 1 — everything but the appearance gathers: samples with weight > rayMarch_weight_thres are
+// written to the ray's list (a.app_w / a.app_i) for app_gather_kernel instead of being gathered here, so the kernel
+// carries no accumulator and runs at twice the occupancy of the fused one.
+// MODE 2: the fused kernel as the split path's overflow pass (only rays whose list overflowed are marched); a separate
+// instantiation because the fused kernel sits exactly at its 128-register budget.
+template <int G, bool MASK_ONLY, int CS4, int CA4, int MODE>
+__global__ void __launch_bounds__(MARCH_WARPS * 32, MODE == 1 ? TVM_EMIT_MIN_BLOCKS : TVM_MARCH_MIN_BLOCKS)
+march_fwd_kernel(const __grid_constant__ MarchArgs a) {
+    constexpr bool EMIT = MODE == 1, SPILL = MODE == 2;
     __shared__ int s_next;
     __shared__ float4 s_slot[MARCH_WARPS][32];
     __shared__ float s_ret[MARCH_WARPS][32];
@@ -83,7 +103,16 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
     __syncthreads();
 
     const long long base = (long long)blockIdx.x * a.rays_per_cta;
+    if (SPILL) {        // overflow pass of the split path: almost always nothing to do
+        bool over = false;
+        for (int i = threadIdx.x; i < a.rays_per_cta; i += MARCH_WARPS * 32)
+            over = over || (base + i < a.n_rays && __ldg(a.app_count + base + i) > a.spill_cap);
+        if (!__syncthreads_or(over)) return;
+    }
     const bool sample_out = a.alpha || a.z_vals || a.dists;
+    // TVM_F_MASK_ANYWHERE (tvm_sample_mask only): the occupancy test alone decides, also outside the field's aabb —
+    // filtering_rays(bbox_only=False) tests alphaMask.sample_alpha on every sample (tensorBase.py:728-737)
+    const bool anywhere = MASK_ONLY && (a.flags & TVM_F_MASK_ANYWHERE) && f.occ_cells != nullptr;
     const bool visit_all = sample_out || a.valid_bits;          // every sample index must be written
     const bool early = (a.flags & TVM_F_EARLY_TERM) && !sample_out;
     const int S = a.S, words = (S + 31) >> 5;
@@ -92,6 +121,12 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
     while (local < a.rays_per_cta) {
         const long long r = base + local;
         if (r >= a.n_rays) break;
+        if (SPILL && __ldg(a.app_count + r) <= a.spill_cap) {
+            int nx = 0;
+            if (lane == 0) nx = atomicAdd(&s_next, 1);
+            local = __shfl_sync(FULL, nx, 0);
+            continue;
+        }
         TvmRay ray;
         {
             const float* rp = a.rays + r * a.ray_stride;
@@ -111,26 +146,28 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
 
         // empty-space skip mask (exact): blocks whose end-sample box misses the aabb / every occupied super-cell
         const TvmBlockMask bm = tvm_block_prepass(f, ray, S, lane);
-        if (a.valid_bits)
+        if (a.valid_bits && !anywhere)
             for (int w = lane; w < words; w += 32)
                 if (!bm.test(w)) a.valid_bits[r * words + w] = 0u;
 
         // visit the flagged blocks only (find-next-set-bit); per-sample outputs force a visit of every block
         const int nblk = words;
         int wi = 0;
-        unsigned todo = sample_out ? tvm_all_blocks_word(0, nblk) : bm.word(0);
+        const bool all_blocks = sample_out || anywhere;
+        unsigned todo = all_blocks ? tvm_all_blocks_word(0, nblk) : bm.word(0);
         for (;;) {
-            while (todo == 0u && ++wi < ((nblk + 31) >> 5)) todo = sample_out ? tvm_all_blocks_word(wi, nblk) : bm.word(wi);
+            while (todo == 0u && ++wi < ((nblk + 31) >> 5)) todo = all_blocks ? tvm_all_blocks_word(wi, nblk) : bm.word(wi);
             if (todo == 0u) break;
             const int blk = (wi << 5) + (__ffs(todo) - 1);
             todo &= todo - 1u;
             const int i0 = blk << 5;
-            const bool flagged = !sample_out || bm.test(blk);
+            const bool flagged = anywhere || !sample_out || bm.test(blk);
             const int i = i0 + lane;
             const bool in_range = i < S;
             const float z = tvm_sample_z(f, ray, i);
             float p[3];
-            const bool inside = flagged && tvm_sample_point(f, ray, z, p) && in_range;
+            const bool in_box = tvm_sample_point(f, ray, z, p);
+            const bool inside = flagged && (in_box || anywhere) && in_range;
             bool keep = inside;
             if (f.occ_cells != nullptr && inside) keep = tvm_occupancy_keep(f, p);
             const unsigned imask = __ballot_sync(FULL, inside);
@@ -188,7 +225,19 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                     // ---- appearance for samples with weight > rayMarch_weight_thres (:851)
                     const bool app = keep && (w > f.weight_thres);
                     const unsigned amask = __ballot_sync(FULL, app);
-                    if (amask) {
+                    if (EMIT) {
+                        if (amask) {
+                            const int slot = n_app + __popc(amask & lt_mask);
+                            if (app && slot < TVM_APP_CAP) {
+                                float4 sw;
+                                unsigned si;
+                                tvm_slot_from_idx(f, n, w, sw, si);
+                                a.app_w[r * TVM_APP_CAP + slot] = sw;
+                                a.app_i[r * TVM_APP_CAP + slot] = si;
+                            }
+                            n_app += __popc(amask);
+                        }
+                    } else if (amask) {
                         const int na = __popc(amask), ranka = __popc(amask & lt_mask);
                         if (app) s_slot[warp][ranka] = make_float4(n[0], n[1], n[2], w);
                         __syncwarp();
@@ -225,7 +274,7 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
 #pragma unroll
             for (int k = 0; k < 3; ++k)
 #pragma unroll
-                for (int g = 0; g < G; ++g) {
+                for (int g = 0; g < (EMIT ? 0 : G); ++g) {
                     float4 v = A[k][g];
                     if (n_app > 0) {            // warp-uniform; rays without appearance samples store their zeros
 #pragma unroll
@@ -245,6 +294,82 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_MARCH_MIN_BLOCKS) march_
                 a.app_count[r] = n_app;
                 if (a.app_count_out) a.app_count_out[r] = n_app;
             }
+        }
+        int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(&s_next, 1);
+        local = __shfl_sync(FULL, nxt, 0);
+    }
+}
+
+
+// Split path, stage 2 — the appearance gathers of compute_appfeature (models/tensoRF.py:237-256), weighted and summed per
+// ray (tensorBase.py:886-888, basis_mat hoisted): one warp per ray walks the ray's emitted sample list.  The list is
+// staged in shared memory once, then each quad walks a contiguous eighth of it plane by plane with the corner texels /
+// line taps of the current cell cached in registers (tvm_gather.cuh::app_run_plane), so a sample that stays in the cell
+// of its predecessor fetches nothing and a step to a neighbouring cell fetches only the texels that changed.  Rays without appearance samples are skipped (the
+// shading kernels never read their ray_feat rows) unless TVM_F_ZERO_UNLIT asks for zero rows; rays whose list
+// overflowed TVM_APP_CAP are left to the fused kernel's overflow pass.
+struct AppArgs {
+    tvm_field_desc f;
+    TvmSections sec;
+    const float4* app_w;
+    const unsigned* app_i;
+    const int* app_count;
+    float* ray_feat;
+    long long n_rays;
+    int ta;
+    int app_off[3];
+    int rays_per_cta;
+    int zero_unlit;
+};
+
+template <int G, int CA4>
+__global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_APP_MIN_BLOCKS) app_gather_kernel(const __grid_constant__ AppArgs a) {
+    __shared__ int s_next;
+    __shared__ float4 s_w[MARCH_WARPS][TVM_APP_CAP];
+    __shared__ unsigned s_i[MARCH_WARPS][TVM_APP_CAP];
+    const tvm_field_desc& f = a.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 3;
+    if (threadIdx.x == 0) s_next = MARCH_WARPS;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * a.rays_per_cta;
+    int local = warp;
+    while (local < a.rays_per_cta) {
+        const long long r = base + local;
+        if (r >= a.n_rays) break;
+        const int n = __ldg(a.app_count + r);
+        if (n > 0 && n <= TVM_APP_CAP) {
+            const float4* ew = a.app_w + r * TVM_APP_CAP;
+            const unsigned* ei = a.app_i + r * TVM_APP_CAP;
+            for (int t = lane; t < n; t += 32) {
+                s_w[warp][t] = __ldcs(ew + t);          // streamed once: do not displace the factor texels in L1
+                s_i[warp][t] = __ldcs(ei + t);
+            }
+            __syncwarp();
+            const int R = (n + 7) >> 3, b = (lane >> 2) * R, e = min(b + R, n);      // quad q walks the q-th eighth of the list
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float4 A[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) A[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                app_run_plane<G, CA4>(f, a.sec, k, s_w[warp], s_i[warp], b, e, sub, A);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    float4 v = A[g];
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        v.x += __shfl_xor_sync(FULL, v.x, o); v.y += __shfl_xor_sync(FULL, v.y, o);
+                        v.z += __shfl_xor_sync(FULL, v.z, o); v.w += __shfl_xor_sync(FULL, v.w, o);
+                    }
+                    const int j = sub + 4 * g;
+                    if (lane < 4 && j < (CA4 > 0 ? CA4 : (f.n_app[k] >> 2)))
+                        reinterpret_cast<float4*>(a.ray_feat + r * a.ta + a.app_off[k])[j] = v;
+                }
+            }
+            __syncwarp();
+        } else if (n <= 0 && a.zero_unlit) {
+            for (int j = lane; j < (a.ta >> 2); j += 32)
+                reinterpret_cast<float4*>(a.ray_feat + r * a.ta)[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         int nxt = 0;
         if (lane == 0) nxt = atomicAdd(&s_next, 1);
@@ -276,24 +401,37 @@ static int pick_rays_per_cta(long long n_rays, int warps, int max_rpc) {
     return (int)rpc;
 }
 
+// per-device "carve-out already set" memo: cudaFuncSetAttribute is per device and not a stream operation, so it is issued
+// once per (kernel, device) and never on a warmed-up path (CUDA-graph capture)
+static bool carveout_done(const void* kernel, int carveout) {
+    constexpr int SLOTS = 16, DEVS = 16;
+    static std::atomic<const void*> seen[DEVS][SLOTS];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto& row = seen[dev & (DEVS - 1)];
+    for (auto& s : row)
+        if (s.load(std::memory_order_relaxed) == kernel) return true;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+    for (auto& s : row) {
+        const void* expect = nullptr;
+        if (s.compare_exchange_strong(expect, kernel)) break;
+    }
+    return false;
+}
+
 template <typename K>
 int launch(K kernel, MarchArgs& a, cudaStream_t st) {
     if (a.n_rays == 0) return 0;
     a.rays_per_cta = pick_rays_per_cta(a.n_rays, MARCH_WARPS, MARCH_RAYS_PER_CTA);
+    if (a.spill_cap > 0) {
+        // overflow pass: one resident wave of CTAs, each scanning a long ray range (it almost always finds nothing
+        // and exits after the vectorised count check)
+        const long long per = (a.n_rays + TVM_SM_COUNT * TVM_MARCH_MIN_BLOCKS - 1) / (TVM_SM_COUNT * TVM_MARCH_MIN_BLOCKS);
+        if (per > a.rays_per_cta) a.rays_per_cta = (int)(per > (1 << 20) ? (1 << 20) : per);
+    }
     // small static smem per CTA: ask for a 32 KB carve-out (enough for every resident CTA) and leave the rest
     // of the 228 KB to L1, which is what serves the texel gathers
-    // set once per kernel instantiation (all instantiations share the pointer type K, so remember the pointers);
-    // a racing duplicate call is harmless
-    static std::atomic<const void*> seen[8];
-    bool done = false;
-    for (auto& s : seen) done = done || s.load(std::memory_order_relaxed) == (const void*)kernel;
-    if (!done) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, TVM_MARCH_CARVEOUT);
-        for (auto& s : seen) {
-            const void* expect = nullptr;
-            if (s.compare_exchange_strong(expect, (const void*)kernel)) break;
-        }
-    }
+    carveout_done((const void*)kernel, TVM_MARCH_CARVEOUT);
     const long long ctas = (a.n_rays + a.rays_per_cta - 1) / a.rays_per_cta;
     kernel<<<(unsigned)ctas, MARCH_WARPS * 32, 0, st>>>(a);
     TVM_LAUNCH_CHECK();
@@ -311,7 +449,7 @@ extern "C" int tvm_sample_mask(const tvm_field_desc* desc, const float* rays, in
     a.flags = flags;
     a.valid_bits = valid_bits;
     a.valid_count = counts;
-    return launch(march_fwd_kernel<1, true, 0, 0>, a, (cudaStream_t)stream);
+    return launch(march_fwd_kernel<1, true, 0, 0, 0>, a, (cudaStream_t)stream);
 }
 
 // march stage of tvm_render_fwd (shade.cu finishes the job)
@@ -341,8 +479,43 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
     for (int k = 0; k < 3; ++k) gmax = max(gmax, (desc->n_app[k] + 15) / 16);
     bool lego = true;     // the reference configs: 16 density / 48 appearance components on every plane
     for (int k = 0; k < 3; ++k) lego = lego && desc->n_sigma[k] == 16 && desc->n_app[k] == 48;
-    if (lego) return launch(march_fwd_kernel<3, false, 4, 12>, a, st);
-    if (gmax <= 1) return launch(march_fwd_kernel<1, false, 0, 0>, a, st);
-    if (gmax == 2) return launch(march_fwd_kernel<2, false, 0, 0>, a, st);
-    return launch(march_fwd_kernel<3, false, 0, 0>, a, st);
+
+    // ---- split path: sigma-march (emits per-ray appearance lists) -> appearance gather -> overflow pass
+    const TvmWorkspace ws_split = tvm_ws_layout(desc, n_rays, TVM_F_SPLIT_APP);
+    bool split = (flags & TVM_F_SPLIT_APP) && !alpha && !z_vals && !dists && !valid_bits && ws_bytes >= ws_split.total;
+    for (int k = 0; k < 3; ++k) split = split && desc->grid[k] <= TVM_PACKED_GRID_MAX;
+    if (split) {
+        a.app_w = (float4*)(base + ws_split.app_w);
+        a.app_i = (unsigned*)(base + ws_split.app_i);
+        rc = lego ? launch(march_fwd_kernel<1, false, 4, 12, 1>, a, st) : launch(march_fwd_kernel<1, false, 0, 0, 1>, a, st);
+        if (rc) return rc;
+        AppArgs g{};
+        g.f = *desc; g.sec = a.sec; g.app_w = a.app_w; g.app_i = a.app_i; g.app_count = a.app_count;
+        g.ray_feat = a.ray_feat; g.n_rays = n_rays; g.ta = a.ta;
+        g.app_off[0] = a.app_off[0]; g.app_off[1] = a.app_off[1]; g.app_off[2] = a.app_off[2];
+        g.rays_per_cta = a.rays_per_cta;
+        g.zero_unlit = (flags & TVM_F_ZERO_UNLIT) ? 1 : 0;
+        const unsigned ctas = (unsigned)((n_rays + g.rays_per_cta - 1) / g.rays_per_cta);
+        if (lego) {
+            carveout_done((const void*)app_gather_kernel<3, 12>, TVM_APP_CARVEOUT);
+            app_gather_kernel<3, 12><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+        } else if (gmax <= 1) {
+            carveout_done((const void*)app_gather_kernel<1, 0>, TVM_APP_CARVEOUT);
+            app_gather_kernel<1, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+        } else if (gmax == 2) {
+            carveout_done((const void*)app_gather_kernel<2, 0>, TVM_APP_CARVEOUT);
+            app_gather_kernel<2, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+        } else {
+            carveout_done((const void*)app_gather_kernel<3, 0>, TVM_APP_CARVEOUT);
+            app_gather_kernel<3, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+        }
+        TVM_LAUNCH_CHECK();
+        a.spill_cap = TVM_APP_CAP;          // rays whose list overflowed: the fused kernel recomputes them whole
+        if (lego) return launch(march_fwd_kernel<3, false, 4, 12, 2>, a, st);
+        return launch(march_fwd_kernel<3, false, 0, 0, 2>, a, st);
+    }
+    if (lego) return launch(march_fwd_kernel<3, false, 4, 12, 0>, a, st);
+    if (gmax <= 1) return launch(march_fwd_kernel<1, false, 0, 0, 0>, a, st);
+    if (gmax == 2) return launch(march_fwd_kernel<2, false, 0, 0, 0>, a, st);
+    return launch(march_fwd_kernel<3, false, 0, 0, 0>, a, st);
 }

@@ -283,11 +283,10 @@ extern "C" int tvm_unpack_mlp_grads(const tvm_field_desc* desc, const float* pac
 }
 
 extern "C" int tvm_workspace_bytes(const tvm_field_desc* desc, int64_t n_rays, uint32_t flags, size_t* out) {
-    (void)flags;
     int rc = tvm_check_desc(desc);
     if (rc) return rc;
     if (!out) return TVM_E_NULL;
-    *out = tvm_ws_layout(desc, n_rays).total;
+    *out = tvm_ws_layout(desc, n_rays, flags).total;
     return 0;
 }
 

@@ -115,8 +115,10 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const __grid_cons
     for (int i = tid; i < SH_RAYS * (ta >> 2); i += SH_THREADS) {
         const int ray = i / (ta >> 2), c4 = i - ray * (ta >> 2);
         const long long r = r0 + ray;
-        const float4 v = (r < a.n_rays) ? __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * ta) + c4)
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        // rows of rays without appearance samples are never written by the split march (and are not shaded)
+        const float4 v = (r < a.n_rays && __ldg(a.app_count + r) > 0)
+                             ? __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * ta) + c4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
         *reinterpret_cast<float4*>(sF + ray * fs + c4 * 4) = v;
     }
     __syncthreads();

@@ -174,11 +174,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
             w1_in_flight = true;
         }
         // ---- stage the ray_feat tile as split A operand (K0); W1 (hi|lo) is already in flight into the weight buffer
+        const bool lit_row = live && __ldg(a.app_count + r) > 0;      // unlit rows are never written by the split march
         for (int kc = cg; kc < d.k0 / 8; kc += 4) {
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = 0.f;
-            if (live && kc * 8 < d.ta) {
+            if (lit_row && kc * 8 < d.ta) {
                 const float4 lo = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8));
                 v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
                 if (kc * 8 + 4 < d.ta) {

@@ -67,6 +67,7 @@ TVM_HD SampleTaps make_sample_taps_idx(const tvm_field_desc& f, const float idx[
 // address instead of a 64-bit section pointer per plane / line).  Built on the host by the launchers.
 struct TvmSections {
     unsigned dP[3], dL[3], aP[3], aL[3];
+    unsigned dRow[3], aRow[3];          // plane row pitch in float4s (tvm_plane_pitch * channels / 4)
 };
 TVM_HD TvmSections tvm_sections(const tvm_field_desc& f) {
     TvmSections s;
@@ -74,9 +75,17 @@ TVM_HD TvmSections tvm_sections(const tvm_field_desc& f) {
     for (int k = 0; k < 3; ++k) {
         s.dP[k] = (unsigned)(f.dplane_off[k] >> 2); s.dL[k] = (unsigned)(f.dline_off[k] >> 2);
         s.aP[k] = (unsigned)(f.aplane_off[k] >> 2); s.aL[k] = (unsigned)(f.aline_off[k] >> 2);
+        s.dRow[k] = (unsigned)tvm_plane_pitch(f.grid[TVM_M0(k)]) * (unsigned)(f.n_sigma[k] >> 2);
+        s.aRow[k] = (unsigned)tvm_plane_pitch(f.grid[TVM_M0(k)]) * (unsigned)(f.n_app[k] >> 2);
     }
     return s;
 }
+// keeps a loop-invariant per-lane value in a register (ptxas otherwise re-derives it from %tid inside the loop)
+#if defined(__CUDA_ARCH__)
+#define TVM_KEEP_REG(v) asm volatile("" : "+r"(v))
+#else
+#define TVM_KEEP_REG(v) ((void)0)
+#endif
 
 // texel offsets (in float4 units, before adding the channel slice j) and weights of plane/line pair k.
 // Offsets are UNSIGNED 32-bit float4 indices so an address is one IMAD.WIDE.U32 off the section pointer
@@ -185,6 +194,116 @@ TVM_HD void app_accumulate_taps(const tvm_field_desc& f, const TvmSections& sec,
 template <int G, int CA4 = 0>
 TVM_HD void app_accumulate(const tvm_field_desc& f, const float n[3], float w, int sub, float4 (&A)[3][G]) {
     app_accumulate_taps<G, CA4>(f, tvm_sections(f), make_sample_taps(f, n), w, sub, A);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Appearance accumulation over a RUN of consecutive samples with a register texel cache (app_gather_kernel, the
+// second stage of the split forward march).
+//
+// Consecutive samples of a ray are half a voxel apart (step_ratio 0.5): on the bench image a sample needs 1.1 new plane
+// texels (of 4) and 0.28 new line taps (of 2) when the texels of its predecessor are still at hand.  A quad walks a
+// contiguous run of the ray's appearance samples one plane at a time.  Lane `sub` owns the float4 channel slices
+// sub + 4g and keeps, for the current plane, the 4 corner texels and the 2 line taps of the current cell in registers,
+// filed by the PARITY of their index (even/odd column x even/odd row; even/odd tap) and tagged with their float4
+// offset: a step to the neighbouring column, row or tap in either direction re-fetches exactly the texels that
+// changed, with no register moves, and a sample that stays in the cell fetches nothing.  The loads are predicated per
+// quad; the L1 data stage serves 8 lanes per wavefront, so a wavefront is saved when both quads of a lane octet skip.
+//
+// sw[t] = (frac_x, frac_y, frac_z, weight), si[t] = i0_x | i0_y << 10 | i0_z << 20 per compacted sample
+// (tvm_axis_tap_idx's clamped base index and idx - i0; grids up to TVM_PACKED_GRID_MAX per axis); the run is [begin, end).
+// ------------------------------------------------------------------------------------------------
+constexpr int TVM_PACKED_GRID_MAX = 1024;
+TVM_HD int tvm_unpack_i0(unsigned v, int a) { return (int)((v >> (10 * a)) & 1023u); }
+TVM_HD float tvm_pick(const float4& v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+TVM_HD void tvm_slot_from_idx(const tvm_field_desc& f, const float idx[3], float w, float4& sw, unsigned& si) {
+    const AxisTap tx = tvm_axis_tap_idx(idx[0], f.grid[0]);
+    const AxisTap ty = tvm_axis_tap_idx(idx[1], f.grid[1]);
+    const AxisTap tz = tvm_axis_tap_idx(idx[2], f.grid[2]);
+    sw = make_float4(tx.w1, ty.w1, tz.w1, w);
+    si = (unsigned)tx.i0 | ((unsigned)ty.i0 << 10) | ((unsigned)tz.i0 << 20);
+}
+
+// plane/line pair k over the run [begin, end): A[g] += sum_t w_t * (plane (x) line)[channels sub + 4g]
+template <int G, int CA4 = 0>
+TVM_HD void app_run_plane(const tvm_field_desc& f, const TvmSections& sec, int k, const float4* __restrict__ sw,
+                          const unsigned* __restrict__ si, int begin, int end, int sub, float4 (&A)[G]) {
+    const float4* F4 = reinterpret_cast<const float4*>(f.factors);
+    const int C4 = CA4 > 0 ? CA4 : (f.n_app[k] >> 2);
+    const unsigned prow = sec.aRow[k];
+    unsigned po = sec.aP[k] + (unsigned)sub, lo = sec.aL[k] + (unsigned)sub;         // this lane's slice
+    TVM_KEEP_REG(po);
+    TVM_KEEP_REG(lo);
+    // cache tags: float4 offset each register set was loaded from (texels [x parity][y parity], taps [parity])
+    unsigned tEE = ~0u, tOE = ~0u, tEO = ~0u, tOO = ~0u, tLE = ~0u, tLO = ~0u;
+    float4 TEE[G], TOE[G], TEO[G], TOO[G], LE[G], LO[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) TEE[g] = TOE[g] = TEO[g] = TOO[g] = LE[g] = LO[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int t = begin; t < end; ++t) {
+        const float4 w4 = sw[t];
+        const unsigned i3 = si[t];
+        const int x0 = tvm_unpack_i0(i3, TVM_M0(k)), y0 = tvm_unpack_i0(i3, TVM_M1(k)), l0 = tvm_unpack_i0(i3, TVM_V(k));
+        const float fx = tvm_pick(w4, TVM_M0(k)), fy = tvm_pick(w4, TVM_M1(k)), fl = tvm_pick(w4, TVM_V(k));
+        // the even and the odd member of {i0, i0+1} per axis and their interpolation weights
+        const unsigned xE = (unsigned)(x0 + 1) & ~1u, xO = (unsigned)x0 | 1u;
+        const unsigned yE = (unsigned)(y0 + 1) & ~1u, yO = (unsigned)y0 | 1u;
+        const unsigned lE = (unsigned)(l0 + 1) & ~1u, lO = (unsigned)l0 | 1u;
+        const bool xev = (x0 & 1) == 0, yev = (y0 & 1) == 0, lev = (l0 & 1) == 0;
+        const float wxE = xev ? 1.0f - fx : fx, wxO = xev ? fx : 1.0f - fx;
+        const float wyE = yev ? 1.0f - fy : fy, wyO = yev ? fy : 1.0f - fy;
+        const float wlE = lev ? 1.0f - fl : fl, wlO = lev ? fl : 1.0f - fl;
+        const unsigned rE = yE * prow + po, rO = yO * prow + po;
+        const unsigned oEE = rE + xE * (unsigned)C4, oOE = rE + xO * (unsigned)C4;
+        const unsigned oEO = rO + xE * (unsigned)C4, oOO = rO + xO * (unsigned)C4;
+        const unsigned oLE = lE * (unsigned)C4 + lo, oLO = lO * (unsigned)C4 + lo;
+        if (oEE != tEE) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if (sub + 4 * g < C4) TEE[g] = TVM_LDG4(F4 + oEE + 4 * g);
+            tEE = oEE;
+        }
+        if (oOE != tOE) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if (sub + 4 * g < C4) TOE[g] = TVM_LDG4(F4 + oOE + 4 * g);
+            tOE = oOE;
+        }
+        if (oEO != tEO) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if (sub + 4 * g < C4) TEO[g] = TVM_LDG4(F4 + oEO + 4 * g);
+            tEO = oEO;
+        }
+        if (oOO != tOO) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if (sub + 4 * g < C4) TOO[g] = TVM_LDG4(F4 + oOO + 4 * g);
+            tOO = oOO;
+        }
+        if (oLE != tLE) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if (sub + 4 * g < C4) LE[g] = TVM_LDG4(F4 + oLE + 4 * g);
+            tLE = oLE;
+        }
+        if (oLO != tLO) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if (sub + 4 * g < C4) LO[g] = TVM_LDG4(F4 + oLO + 4 * g);
+            tLO = oLO;
+        }
+        const float wEE = wxE * wyE, wOE = wxO * wyE, wEO = wxE * wyO, wOO = wxO * wyO;
+        const float bE = w4.w * wlE, bO = w4.w * wlO;
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+            if (sub + 4 * g < C4) {
+                float4 pl = f4_scale(wEE, TEE[g]);
+                pl = f4_fma(wOE, TOE[g], pl); pl = f4_fma(wEO, TEO[g], pl); pl = f4_fma(wOO, TOO[g], pl);
+                const float4 ln = f4_fma(bO, LO[g], f4_scale(bE, LE[g]));
+                A[g].x = fmaf(pl.x, ln.x, A[g].x); A[g].y = fmaf(pl.y, ln.y, A[g].y);
+                A[g].z = fmaf(pl.z, ln.z, A[g].z); A[g].w = fmaf(pl.w, ln.w, A[g].w);
+            }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

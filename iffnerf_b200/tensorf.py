@@ -131,6 +131,9 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
     #   "bf16"  tcgen05 tensor-core kernel, plain bf16 operands (rgb within 1e-2 — BASELINE.json's "bf16 MLP mode")
     #   "auto"  (default) "tc3" when the head's shape fits that kernel (fea_pe = view_pe = 2 does), else "fp32"
     mlp_precision = "auto"
+    # eval renders without per-sample outputs: two-kernel march (a 64-register sigma-march that emits per-ray appearance
+    # sample lists + an appearance-gather kernel with a register texel cache) instead of the fused one-kernel march
+    split_app = True
 
     def __init__(self, aabb, gridSize, device, density_n_comp=8, appearance_n_comp=24, app_dim=27,
                  shadingMode="MLP_PE", alphaMask=None, near_far=[2.0, 6.0], density_shift=-10,
@@ -510,9 +513,10 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
 
     # ------------------------------------------------------------------ kernels
     @torch.no_grad()
-    def sample_mask(self, rays, N_samples=-1, jitter=None, want_bits=True, point_samples=False):
+    def sample_mask(self, rays, N_samples=-1, jitter=None, want_bits=True, point_samples=False, anywhere=False):
         """`ray_valid` of TensorBase.forward (sample_ray + aabb + alphaMask, tensorBase.py:820-837) as packed bits
-        [N, ceil(S/32)] (int32 view of uint32 words) and per-ray counts.  Bit-exact w.r.t. the reference."""
+        [N, ceil(S/32)] (int32 view of uint32 words) and per-ray counts.  Bit-exact w.r.t. the reference.
+        `anywhere`: the occupancy test alone decides, also outside the aabb (filtering_rays, tensorBase.py:728-737)."""
         rays = self._prep_rays(rays)
         S = N_samples if N_samples > 0 else self.nSamples
         n = rays.shape[0]
@@ -522,7 +526,8 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         jit = None if jitter is None else jitter.detach().float().reshape(-1).contiguous()
         lib = _lib.load()
         _lib.check(lib.tvm_sample_mask(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, _lib.ptr(jit),
-                                       _lib.F_POINT_SAMPLES if point_samples else 0, _lib.ptr(bits),
+                                       (_lib.F_POINT_SAMPLES if point_samples else 0) |
+                                       (_lib.F_MASK_ANYWHERE if anywhere else 0), _lib.ptr(bits),
                                        _lib.ptr(counts), _stream(rays.device)), "tvm_sample_mask")
         return bits, counts
 
@@ -555,10 +560,15 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
             vcount = torch.empty((n,), dtype=torch.int32, device=dev)
             acount = torch.empty((n,), dtype=torch.int32, device=dev)
             out.update(valid_count=vcount, app_count=acount)
-        need = C.c_size_t(0)
-        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need)), "tvm_workspace_bytes")
-        ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
         flags = _lib.F_EARLY_TERM if (early_term and not sample_outputs) else 0
+        if self.split_app and not sample_outputs:
+            flags |= _lib.F_SPLIT_APP
+            head_kernel = self.native_shade or (self.ref_kernel and self.packed_ref_head() is not None)
+            if keep_workspace or not head_kernel:
+                flags |= _lib.F_ZERO_UNLIT          # someone reads the ray_feat rows of unlit rays
+        need = C.c_size_t(0)
+        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, flags & _lib.F_SPLIT_APP, C.byref(need)), "tvm_workspace_bytes")
+        ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
         if not self.native_shade:
             flags |= _lib.F_NO_SHADE
         elif self._shade_mode() == "bf16":

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 10
+#define TVM_ABI_VERSION 11
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define TVM_E_NULL        (-1)   /* required pointer is NULL                      */
@@ -33,12 +33,20 @@ extern "C" {
 #define TVM_E_WORKSPACE   (-3)   /* workspace too small                           */
 #define TVM_E_MODE        (-4)   /* unsupported activation / shading mode         */
 
-/* flags for tvm_render_fwd / tvm_render_bwd */
+/* flags for tvm_render_fwd / tvm_march_bwd / tvm_sample_mask */
 #define TVM_F_EARLY_TERM   (1u << 0)  /* eval only: stop a ray once T < early_term_eps                      */
 #define TVM_F_MLP_BF16     (1u << 1)  /* shade with the bf16 tensor-core MLP (tolerance 1e-2) instead of fp32 */
 #define TVM_F_NO_SHADE     (1u << 2)  /* stop after the march stage: workspace holds ray_feat/acc/depth      */
 #define TVM_F_MLP_TC3      (1u << 4)  /* shade on the tensor cores with bf16x3 SPLIT operands (hi.hi + hi.lo + lo.hi,
                                          fp32 accumulate): fp32-equivalent, rgb within ~1e-6 of the FFMA kernel   */
+#define TVM_F_SPLIT_APP    (1u << 5)  /* eval: split the march into a sigma-march that emits per-ray appearance sample lists
+                                         and an appearance-gather kernel (needs the larger workspace of
+                                         tvm_workspace_bytes(..., TVM_F_SPLIT_APP); ignored with per-sample outputs) */
+#define TVM_F_ZERO_UNLIT   (1u << 6)  /* with TVM_F_SPLIT_APP: also write zero ray_feat rows for rays without appearance
+                                         samples (callers that read the workspace themselves) */
+#define TVM_F_MASK_ANYWHERE (1u << 7) /* tvm_sample_mask: the occupancy test alone decides, also for samples outside the
+                                         field's aabb (filtering_rays(bbox_only=False), tensorBase.py:728-737) */
+#define TVM_APP_CAP        128        /* entries per ray in the appearance lists; longer rays take the fused kernel */
 #define TVM_F_POINT_SAMPLES (1u << 3) /* sampler of sample_point_color (tensorBase.py:623-638): n_samples samples
                                          centred on the ray origin, z_i = stepSize*(i - n_samples/2)          */
 
@@ -145,7 +153,7 @@ int tvm_workspace_bytes(const tvm_field_desc* desc, int64_t n_rays, uint32_t fla
  * bg: DEVICE pointer to the 3 background floats (train.py:267-271 draws it on the device).
  * Outputs (device, caller-allocated): rgb [n][3], depth [n], acc [n]; optional alpha/z_vals/dists
  * [n][n_samples] (train outputs; any may be NULL), optional valid_bits/valid_count/app_count as above.
- * `ws` keeps the per-ray accumulations tvm_render_bwd needs. */
+ * `ws` keeps the per-ray accumulations the backward (tvm_shade_bwd + tvm_march_bwd) needs. */
 int tvm_render_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,
                    const float* jitter, const float* bg /* device [3] */, uint32_t flags,
                    float* rgb, float* depth, float* acc,
@@ -249,12 +257,29 @@ int tvm_pixel_rays_bwd(const float* c2w, int pose_stride, const float* kinv_host
                        const int32_t* pose_index, int width, int64_t n, int flags, const float* g_rays, int g_stride,
                        float* g_c2w, void* stream);
 
-/* Measurement aid: quads of lanes gather random 64-B pieces (LDG.128 per lane, the march kernel's access shape) from
- * `granule_bytes`-sized granules (64 = density texel, 192 = appearance texel) inside `bytes` of `buf`: the factor set
- * size gives the L2 -> SM gather ceiling, a few KB the L1-resident one.  The caller times the launch with CUDA events;
- * *bytes_moved = bytes requested by the lanes.  Not used by the render path. */
-int tvm_gather_microbench(const void* buf, size_t bytes, int granule_bytes, int iters, float* sink,
-                          unsigned long long* bytes_moved, void* stream);
+/* ---- grid maintenance (csrc/gridops.cu) ------------------------------------------- */
+
+/* getDenseAlpha + updateAlphaMask (tensorBase.py:643-696) in one call: alpha = compute_alpha(dense_xyz, length) on the
+ * gx x gy x gz lattice dense_xyz = aabb0 (1 - s) + aabb1 s (lin_* = DEVICE copies of torch.linspace(0, 1, g), so the
+ * lattice is bit-identical to the reference's), clamp(0,1), 3x3x3 max-pool, threshold (>= thres -> 1 else 0) ->
+ * volume [gz][gy][gx] fp32 {0,1} (the layout AlphaGridMask keeps, :670-681), and box_out[7] = min xyz | max xyz of the
+ * occupied lattice points (:686-691) | number of occupied voxels.  The query is gated by the descriptor's CURRENT
+ * occupancy (:757-761).  ws: tvm_dense_alpha_workspace_bytes(gx, gy, gz). */
+size_t tvm_dense_alpha_workspace_bytes(int gx, int gy, int gz);
+int tvm_dense_alpha_mask(const tvm_field_desc* desc, const float* lin_x, const float* lin_y, const float* lin_z,
+                         int gx, int gy, int gz, float length, float thres, float* volume, float* box_out /* [7] */,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* One factor of up_sampling_VM / shrink (tensoRF.py:258-316), reference layout in and out: src [channels][h][w] ->
+ * dst [channels][h2][w2].  mode 0: F.interpolate(mode="bilinear", align_corners=True); mode 1: the crop
+ * dst[c][y][x] = src[c][y + y_off][x + x_off]. */
+int tvm_resize_factor(const float* src, int channels, int h, int w, float* dst, int h2, int w2, int mode, int y_off,
+                      int x_off, void* stream);
+
+/* filtering_rays(bbox_only=True) (tensorBase.py:716-726): out[i] = 1 iff the slab interval of ray i against the aabb is
+ * non-empty (t_max > t_min, no near/far clamp). */
+int tvm_rays_hit_box(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, uint8_t* out,
+                     void* stream);
 
 /* workspace layout helpers (byte offsets inside ws for n_rays) so the host can view the march outputs */
 int tvm_workspace_layout(const tvm_field_desc* desc, int64_t n_rays, size_t* ray_feat_off, size_t* acc_off,

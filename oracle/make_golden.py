@@ -91,6 +91,36 @@ def eval_case(R, name, fld, rays, white_bg=True, bg_color=None, extra=None):
           f"oracle==reference bit-exact")
 
 
+def full_image_case(R, name, fld, rays, width, stride=None, n_sub=65536):
+    """Full-size render by the UNMODIFIED reference (config 2: 640 000 rays, config 4: 2 073 600 rays).  Stored:
+    a strided subset of rgb/depth rows, a float64 checksum of every image row (rgb and depth), and the complete
+    per-ray `ray_valid` count (bit-exact quantity)."""
+    t = time.time()
+    m = build_reference_model(R, fld)
+    n = rays.shape[0]
+    counts = np.zeros(n, dtype=np.int16)
+    rgbs, depths = [], []
+    with torch.no_grad():
+        for a in range(0, n, 4096):
+            chunk = rays[a:a + 4096]
+            rgb, depth, *_ = m(chunk, white_bg=True, is_train=False, N_samples=-1)
+            rgbs.append(rgb)
+            depths.append(depth)
+            counts[a:a + 4096] = reference_valid_mask(m, chunk).sum(-1).numpy()
+    rgb, depth = torch.cat(rgbs), torch.cat(depths)
+    stride = stride or max(1, n // n_sub)
+    idx = np.arange(0, n, stride)
+    rows = n // width
+    rec = dict(ray_index=idx, rgb_sub=rgb[idx].numpy(), depth_sub=depth[idx].numpy(), valid_count=counts,
+               row_rgb_sum=rgb.double().view(rows, width, 3).sum((1, 2)).numpy(),
+               row_depth_sum=depth.double().view(rows, width).sum(1).numpy(),
+               n_samples=np.int32(m.nSamples), step_size=np.float32(m.stepSize.item()), width=np.int32(width),
+               param_checksum=fx.param_checksum(fld))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(f"[golden] {name}: rays={n} S={m.nSamples} valid/ray={counts.mean():.1f} rgb_mean={rgb.mean():.4f} "
+          f"({time.time()-t:.1f}s) reference outputs stored (subset {idx.shape[0]}, {rows} row checksums)")
+
+
 def sampled_entries(t, n=256, seed=7):
     g = torch.Generator().manual_seed(seed)
     idx = torch.randint(0, t.numel(), (n,), generator=g)
@@ -322,6 +352,12 @@ def main():
         ref_head_case(R, "c1_ref_head")
     if want("c5_raygen"):
         raygen_case(R, "c5_raygen")
+    if "c2_full" in only:        # minutes of CPU: only on request
+        fld, rays = fx.config2()
+        full_image_case(R, "c2_full", fld, rays, 800)
+    if "c4_full" in only:
+        fld, rays = fx.config4()
+        full_image_case(R, "c4_full", fld, rays, 1920)
     if want("c4_sub"):
         fld, rays = fx.config4()
         sub, idx = fx.subsample(rays, 2048, seed=0)

@@ -18,7 +18,7 @@ for nbytes in (16 << 10, 64 << 10, 128 << 10, 1 << 20, 69 << 20):
         for rep in range(4):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            _lib.check(lib.tvm_gather_microbench(_lib.ptr(buf), nbytes // gran * gran, gran, 256, _lib.ptr(sink), C.byref(moved), st), "mb")
+            _lib.check(_lib.load_bench().tvm_gather_microbench(_lib.ptr(buf), nbytes // gran * gran, gran, 256, _lib.ptr(sink), C.byref(moved), st), "mb")
             e1.record(); torch.cuda.synchronize()
             if rep: best = max(best, moved.value / (e0.elapsed_time(e1) / 1e3) / 1e9)
         print(json.dumps({"working_set_bytes": nbytes, "granule": gran, "gbs": round(best, 1)}), flush=True)

@@ -15,6 +15,7 @@ ap.add_argument("--no-early", action="store_true")
 ap.add_argument("--tag", default=os.environ.get("TVM_B200_LIB", "default"))
 ap.add_argument("--tile", default="", help="WxH: reorder the 800x800 rays so 32 consecutive rays form a WxH pixel tile (locality probe)")
 ap.add_argument("--march-only", action="store_true")
+ap.add_argument("--fused", action="store_true", help="one-kernel march (no TVM_F_SPLIT_APP)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 fld = fx.make_field([300] * 3, density_shift=0.0)
@@ -31,12 +32,12 @@ lib = _lib.load()
 m.mlp_precision = "fp32"
 d, keep = m.field_desc()
 need = C.c_size_t(0)
-lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need))
+lib.tvm_workspace_bytes(C.byref(d), n, 0 if a.fused else _lib.F_SPLIT_APP, C.byref(need))
 ws = torch.empty((need.value,), dtype=torch.uint8, device=dev)
 bg = m._bg(None, True, dev)
 rgb = torch.empty((n, 3), device=dev); depth = torch.empty(n, device=dev); acc = torch.empty(n, device=dev)
 st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-fl = 0 if a.no_early else _lib.F_EARLY_TERM
+fl = (0 if a.no_early else _lib.F_EARLY_TERM) | (0 if a.fused else (_lib.F_SPLIT_APP | _lib.F_ZERO_UNLIT))
 
 def march():
     _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, None, _lib.ptr(bg), fl | _lib.F_NO_SHADE,
@@ -59,7 +60,7 @@ def shade_tc():
     _lib.check(lib.tvm_shade_fwd(C.byref(d2), _lib.ptr(rays), n, rays.shape[1], _lib.ptr(bg), _lib.F_MLP_BF16, _lib.ptr(rgb),
                                  _lib.ptr(depth), _lib.ptr(acc), _lib.ptr(ws), ws.numel(), st), "shade_tc")
 if a.march_only:
-    out = {"tag": a.tag, "tile": a.tile, "march_ms": round(timeit(march), 4)}
+    out = {"tag": a.tag, "tile": a.tile, "fused": a.fused, "march_ms": round(timeit(march), 4)}
     v = m.workspace_views(d, ws, n)      # checksums of the march outputs (compare builds)
     out.update(feat_sum=float(v["ray_feat"].double().sum()), feat_abs=float(v["ray_feat"].double().abs().sum()),
                acc_sum=float(v["acc"].double().sum()), depth_sum=float(v["depth"].double().sum()),

@@ -10,6 +10,8 @@
 
 static int g_point_samples = 0;     // 1: sample_point_color sampler (TVM_F_POINT_SAMPLES)
 extern "C" void hc_set_point_samples(int on) { g_point_samples = on; }
+static int g_app_octets = 0;        // 1: appearance accumulated like app_gather_kernel does (quad runs over the ray's list, register texel cache)
+extern "C" void hc_set_app_octets(int on) { g_app_octets = on; }
 
 extern "C" void hc_pack_occupancy(const float* vol, int dx, int dy, int dz, uint8_t* cells) {
     for (int z = 0; z < dz; ++z)
@@ -83,6 +85,14 @@ extern "C" void hc_march(const tvm_field_desc* f, const float* rays, long long n
         int napp = 0;
         float4 A[4][3][3];
         memset(A, 0, sizeof(A));
+        // run mode: per-lane accumulators of the 32 emulated lanes + the ray's compacted appearance list
+        // (what the march kernel emits and app_gather_kernel walks: quad q takes the contiguous eighth q of the list)
+        float4 AL[32][3][3];
+        memset(AL, 0, sizeof(AL));
+        std::vector<float4> sw(S);
+        std::vector<unsigned> si(S);
+        int na = 0;
+        const TvmSections sec = tvm_sections(*f);
         for (int i = 0; i < S; ++i) {
             float p[3], nrm[3];
             const float z = tvm_sample_z(*f, ray, i);
@@ -102,12 +112,38 @@ extern "C" void hc_march(const tvm_field_desc* f, const float* rays, long long n
                 dep += w * z;
                 if (w > f->weight_thres) {
                     ++napp;
-                    for (int sub = 0; sub < 4; ++sub) { if (lego) app_accumulate<3, 12>(*f, nrm, w, sub, A[sub]); else app_accumulate<3, 0>(*f, nrm, w, sub, A[sub]); }
+                    if (g_app_octets) {
+                        float idx[3];
+                        for (int c = 0; c < 3; ++c) idx[c] = tvm_unnormalize(nrm[c], f->grid[c]);
+                        tvm_slot_from_idx(*f, idx, w, sw[na], si[na]);
+                        ++na;
+                    } else {
+                        for (int sub = 0; sub < 4; ++sub) { if (lego) app_accumulate<3, 12>(*f, nrm, w, sub, A[sub]); else app_accumulate<3, 0>(*f, nrm, w, sub, A[sub]); }
+                    }
                 }
                 T *= (1.f - alpha + 1e-10f);
             }
             if (alpha_out) alpha_out[r * S + i] = alpha;
         }
+        if (g_app_octets && na > 0) {
+            const int R = (na + 7) >> 3;
+            for (int lane = 0; lane < 32; ++lane) {
+                const int quad = lane >> 2, sub = lane & 3;
+                const int b = quad * R, e = (b + R < na) ? b + R : na;
+                for (int k = 0; k < 3; ++k) {
+                    if (lego) app_run_plane<3, 12>(*f, sec, k, sw.data(), si.data(), b, e, sub, AL[lane][k]);
+                    else app_run_plane<3, 0>(*f, sec, k, sw.data(), si.data(), b, e, sub, AL[lane][k]);
+                }
+            }
+        }
+        if (g_app_octets)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int k = 0; k < 3; ++k)
+                    for (int g = 0; g < 3; ++g) {
+                        float4& d = A[lane & 3][k][g];
+                        const float4 v = AL[lane][k][g];
+                        d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
+                    }
         for (int k = 0; k < 3; ++k)
             for (int sub = 0; sub < 4; ++sub)
                 for (int g = 0; g < 3; ++g) {

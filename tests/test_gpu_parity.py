@@ -76,6 +76,57 @@ def test_render_matches_reference_golden(name, early_term, mlp, dev):
 
 
 @pytest.mark.parametrize("name", ["c1_dense_mask", "c2_sub", "c4_sub"])
+def test_split_march_equals_fused_march(name, dev):
+    """The default eval path (sigma-march that emits per-ray appearance lists + app_gather_kernel with its register
+    texel cache) against the one-kernel march: identical sample decisions, ray_feat equal up to fp32 summation order."""
+    fld, rays, g, white, m = _case(name, dev)
+    outs = {}
+    for split in (True, False):
+        m.split_app = split
+        try:
+            o = m.render_eval(rays.to(dev), white_bg=bool(white), want_counts=True, keep_workspace=True)
+            torch.cuda.synchronize()
+        finally:
+            m.split_app = type(m).split_app
+        outs[split] = o
+    a, b = outs[True], outs[False]
+    assert torch.equal(a["valid_count"], b["valid_count"]) and torch.equal(a["app_count"], b["app_count"])
+    assert torch.equal(a["acc_map"], b["acc_map"]) and torch.equal(a["workspace"]["depth"], b["workspace"]["depth"])
+    fa, fb = a["workspace"]["ray_feat"], b["workspace"]["ray_feat"]
+    assert int(a["app_count"].max()) <= 128          # no list overflow in these fixtures: the gather kernel did the work
+    assert float((fa - fb).abs().max()) <= 2e-6 * max(1.0, float(fb.abs().max()))
+    assert float((a["rgb_map"] - b["rgb_map"]).abs().max()) <= 2e-6
+    assert np.abs(a["rgb_map"].cpu().numpy() - g["rgb_map"]).max() <= TOL
+
+
+def test_split_march_list_overflow_takes_the_fused_pass(dev):
+    """Rays with more than TVM_APP_CAP (128) appearance samples are re-marched by the fused kernel's overflow pass:
+    a thin medium (distance_scale 5: alpha ~ 0.017 per sample, ~300 samples above the weight threshold)."""
+    fld, rays = fx.config1(0.0, "sphere", 6)
+    fld.distance_scale = 5.0
+    sel = torch.arange(0, rays.shape[0], 3)
+    rays = rays[sel].contiguous()
+    m = H.module_from_field(fld, dev)
+    outs = {}
+    for split in (True, False):
+        m.split_app = split
+        o = m.render_eval(rays.to(dev), white_bg=True, want_counts=True, keep_workspace=True)
+        torch.cuda.synchronize()
+        outs[split] = o
+    a, b = outs[True], outs[False]
+    n_app = b["app_count"]
+    assert int((n_app > 128).sum()) > 100 and int(((n_app > 0) & (n_app <= 128)).sum()) > 10     # both kinds of rays
+    assert torch.equal(a["app_count"], n_app) and torch.equal(a["acc_map"], b["acc_map"])
+    over = n_app > 128
+    fa, fb = a["workspace"]["ray_feat"], b["workspace"]["ray_feat"]
+    assert torch.equal(fa[over], fb[over])            # same kernel, same arithmetic
+    assert float((fa - fb).abs().max()) <= 2e-6 * max(1.0, float(fb.abs().max()))
+    with torch.no_grad():
+        ref = orc.render_rays(fld, rays[:1024], white_bg=True)
+    assert float((a["rgb_map"][:1024].cpu() - ref["rgb_map"]).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("name", ["c1_dense_mask", "c2_sub", "c4_sub"])
 def test_bf16_tensor_core_mlp_mode(name, dev):
     """TVM_F_MLP_BF16: the tcgen05 shade kernel — rgb within 1e-2 of the reference (north_star's bf16 MLP mode);
     depth/acc do not go through the MLP and keep the fp32 bound."""
@@ -220,6 +271,40 @@ def test_full_size_properties(dev):
     o2 = m.render_eval(full[perm].to(dev), white_bg=True)
     assert torch.equal(o2["rgb_map"], rgb[perm.to(dev)])
     assert torch.equal(o2["depth_map"], o["depth_map"][perm.to(dev)])
+
+
+@pytest.mark.parametrize("name,build,width", [("c2_full", lambda: fx.config2(), 800),
+                                              ("c4_full", lambda: fx.config4(), 1920)])
+def test_full_size_render_matches_reference_golden(name, build, width, dev):
+    """BASELINE configs 2 (800x800 = 640 000 rays) and 4 (1920x1080 = 2 073 600 rays) rendered whole through
+    OctreeRender_trilinear_fast against the UNMODIFIED reference's full-size render (oracle/make_golden.py
+    full_image_case): every ray's valid-sample count bit-exact, a ~65 k-ray strided subset of rgb / depth within
+    1e-4, and the float64 checksum of every image row within the same per-pixel tolerance."""
+    import iffnerf_b200 as I
+    _cache.clear()
+    fld, rays = build()
+    g = H.golden(name)
+    H.check_params(fld, g)
+    m = H.module_from_field(fld, dev)
+    assert m.nSamples == int(g["n_samples"])
+    rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(rays, m, chunk=4096, N_samples=-1, white_bg=True,
+                                                        ndc_ray=False, device=dev)
+    counts = torch.cat([m.sample_mask(rays[a:a + (1 << 19)].to(dev), want_bits=False)[1]
+                        for a in range(0, rays.shape[0], 1 << 19)])
+    torch.cuda.synchronize()
+    assert np.array_equal(counts.cpu().numpy().astype(np.int16), g["valid_count"])
+    idx = torch.from_numpy(g["ray_index"]).to(dev)
+    assert np.abs(rgb[idx].cpu().numpy() - g["rgb_sub"]).max() <= TOL
+    assert np.abs(depth[idx].cpu().numpy() - g["depth_sub"]).max() <= TOL
+    rows = rays.shape[0] // width
+    row_rgb = rgb.double().view(rows, width, 3).sum((1, 2)).cpu().numpy()
+    row_dep = depth.double().view(rows, width).sum(1).cpu().numpy()
+    # row checksums: the MEAN error over a row stays well inside the per-pixel tolerance (depth carries the one-sided
+    # bias of early termination: the dropped tail is <= early_term_eps * z per lit ray)
+    assert np.abs(row_rgb - g["row_rgb_sum"]).max() <= TOL * 3 * width * 0.1
+    assert np.abs(row_dep - g["row_depth_sum"]).max() <= TOL * width * 0.4
+    del m
+    torch.cuda.empty_cache()
 
 
 @pytest.mark.parametrize("cfg", ["llff_like_16_4_4", "small_8_24_relu_nope"])

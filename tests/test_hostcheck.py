@@ -150,6 +150,32 @@ def test_march_math_matches_reference_golden(hc):
     np.testing.assert_allclose(depth, g["depth_map"][sel], atol=1e-4)
 
 
+def test_run_cache_appearance_matches_per_sample_path(hc):
+    """app_gather_kernel's gathers (quad runs over the ray's sample list with a register texel cache,
+    tvm_gather.cuh::app_run_plane) emulated lane by lane on the host == the per-sample accumulation of the fused
+    kernel (app_accumulate_taps), on cubic and non-cubic grids."""
+    for fld, rays in (fx.config1(0.0, "sphere", 6), fx.config4(24, 40)):
+        m, d, keep = _host_desc(hc, fld)
+        sel = np.arange(0, rays.shape[0], 5)[:400]
+        r = np.ascontiguousarray(rays.numpy()[sel], dtype=np.float32)
+        n, S = r.shape[0], m.nSamples
+        outs = []
+        for mode in (0, 1):
+            hc.hc_set_app_octets(mode)
+            feat = np.zeros((n, 144), dtype=np.float32)
+            acc = np.zeros(n, dtype=np.float32)
+            dep = np.zeros(n, dtype=np.float32)
+            napp = np.zeros(n, dtype=np.int32)
+            hc.hc_march(C.byref(d), C.c_void_p(r.ctypes.data), C.c_longlong(n), r.shape[1], S, None,
+                        C.c_void_p(feat.ctypes.data), C.c_void_p(acc.ctypes.data), C.c_void_p(dep.ctypes.data), None,
+                        C.c_void_p(napp.ctypes.data))
+            outs.append((feat, acc, napp))
+        hc.hc_set_app_octets(0)
+        assert outs[0][2].sum() > 1000 and np.array_equal(outs[0][2], outs[1][2])
+        scale = np.abs(outs[0][0]).max()
+        np.testing.assert_allclose(outs[1][0], outs[0][0], atol=2e-6 * max(scale, 1.0))
+
+
 def _unpack_host_grads(m, d, gbuf):
     out = {}
     for k in range(3):
