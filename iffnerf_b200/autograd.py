@@ -12,11 +12,47 @@ tests as an independent cross-check of tvm_shade_bwd.)
 from __future__ import annotations
 
 import ctypes as C
+import functools
 
 import torch
 import torch.nn.functional as F
+from torch.autograd.function import once_differentiable
 
 from . import _lib
+
+
+def _guard_fwd(fn):
+    """Runs a Function.forward(ctx, model, rays, ...) with the rays' GPU as the current device: the C-ABI launches go to
+    the calling thread's current device, while streams and tensors belong to the rays' device."""
+    @functools.wraps(fn)
+    def wrapped(ctx, model, rays, *rest):
+        if not rays.is_cuda:
+            return fn(ctx, model, rays, *rest)           # raises the no-CPU-path error
+        with torch.cuda.device(rays.device):
+            return fn(ctx, model, rays, *rest)
+    return wrapped
+
+
+def _guard_bwd(fn):
+    """Same for backward; also marks it once-differentiable (the kernels have no double backward: a
+    loss.backward(create_graph=True) as in the reference's adahessian option must raise, not return zeros)."""
+    @functools.wraps(fn)
+    def wrapped(ctx, *grads):
+        with torch.cuda.device(ctx.rays_c.device):
+            return fn(ctx, *grads)
+    return once_differentiable(wrapped)
+
+
+def _param_state(params):
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+def _check_unmodified(ctx):
+    """The backward re-marches with the CURRENT parameters against the forward's workspace: refuse if a parameter
+    changed in between (in-place optimiser step, .copy_, ...).  Edits through `.data` do not bump `_version`; call
+    model.invalidate_packed() after those."""
+    if _param_state(ctx.params) != ctx.param_state:
+        raise _lib.TvmError("parameters were modified between forward and backward")
 
 
 def _c(t):
@@ -34,6 +70,7 @@ class _Render(torch.autograd.Function):
     so forward and backward both stop a ray at T < early_term_eps."""
 
     @staticmethod
+    @_guard_fwd
     def forward(ctx, model, rays, S, jitter, bg, flags, *params):
         from .tensorf import _stream
         rays_c = model._prep_rays(rays)
@@ -58,7 +95,7 @@ class _Render(torch.autograd.Function):
         ctx.model, ctx.S, ctx.jit, ctx.rays_c, ctx.ws, ctx.bg = model, S, jit, rays_c, ws, bg_c
         ctx.ray_cols = rays.shape[1]
         ctx.flags = flags & ~(_lib.F_MLP_TC3 | _lib.F_MLP_BF16)      # the backward kernels take the sampler bits only
-        ctx.keys = (model._packed_key, model._mlp_key)
+        ctx.params, ctx.param_state = params, _param_state(params)
         if want_samples:
             ctx.mark_non_differentiable(depth, z, dists)
         else:
@@ -66,6 +103,7 @@ class _Render(torch.autograd.Function):
         return rgb, depth, acc, alpha, z, dists
 
     @staticmethod
+    @_guard_bwd
     def backward(ctx, g_rgb, g_depth, g_acc, g_alpha, g_z, g_dists):
         from .tensorf import _stream
         model, rays_c = ctx.model, ctx.rays_c
@@ -76,8 +114,7 @@ class _Render(torch.autograd.Function):
         want_factors = any(need[6:18])
         want_basis = need[18]
         want_mlp = any(need[19:25])
-        if (model._packed_key, model._mlp_key) != ctx.keys:
-            raise _lib.TvmError("parameters were modified between forward and backward")
+        _check_unmodified(ctx)
         d, keep = model.field_desc()
         lib = _lib.load()
         st = _stream(dev)
@@ -148,6 +185,7 @@ def render_with_grad(model, rays_chunk, white_bg, bg_color, N_samples, jitter, p
 # ----------------------------------------------------------------------------------------------------------------
 class _March(torch.autograd.Function):
     @staticmethod
+    @_guard_fwd
     def forward(ctx, model, rays, S, jitter, flags, *factors):
         from .tensorf import _stream
         rays_c = model._prep_rays(rays)
@@ -169,6 +207,7 @@ class _March(torch.autograd.Function):
         v = model.workspace_views(d, ws, n)
         ctx.model, ctx.S, ctx.jit, ctx.rays_c, ctx.ws, ctx.flags = model, S, jit, rays_c, ws, flags
         ctx.ray_cols = rays.shape[1]
+        ctx.params, ctx.param_state = factors, _param_state(factors)
         if want_samples:
             ctx.mark_non_differentiable(v["depth"], z, dists, v["app_count"])
         else:
@@ -176,6 +215,7 @@ class _March(torch.autograd.Function):
         return v["ray_feat"], v["acc"], v["depth"], alpha, z, dists, v["app_count"]
 
     @staticmethod
+    @_guard_bwd
     def backward(ctx, g_feat, g_acc, g_depth, g_alpha, g_z, g_dists, g_cnt):
         from .tensorf import _stream
         model, rays_c = ctx.model, ctx.rays_c
@@ -183,6 +223,7 @@ class _March(torch.autograd.Function):
         n = rays_c.shape[0]
         want_rays = ctx.needs_input_grad[1]
         want_factors = any(ctx.needs_input_grad[5:])
+        _check_unmodified(ctx)
         d, keep = model.field_desc()
         lib = _lib.load()
         g_packed = torch.zeros(int(d.n_factor_floats), device=dev) if want_factors else None
@@ -223,6 +264,7 @@ class _RefTail(torch.autograd.Function):
                 rm.specular_mlp[0]]
 
     @staticmethod
+    @_guard_fwd
     def forward(ctx, model, rays, bg, ray_feat, acc, depth_p, app_count, basis, *head):
         from .tensorf import _stream
         dev = ray_feat.device
@@ -245,11 +287,13 @@ class _RefTail(torch.autograd.Function):
                    "tvm_shade_ref_fwd")
         ctx.model, ctx.rays_c, ctx.bg, ctx.ray_cols = model, rays_c, bg_c, rays.shape[1]
         ctx.save_for_backward(ray_feat, acc, app_count)
-        ctx.key = model._ref_key
+        ctx.params = (basis,) + tuple(head)
+        ctx.param_state = _param_state(ctx.params)
         ctx.mark_non_differentiable(depth)
         return rgb, depth
 
     @staticmethod
+    @_guard_bwd
     def backward(ctx, g_rgb, g_depth):
         from .tensorf import _stream
         model, rays_c = ctx.model, ctx.rays_c
@@ -257,8 +301,7 @@ class _RefTail(torch.autograd.Function):
         dev = ray_feat.device
         n, ta = ray_feat.shape
         need = ctx.needs_input_grad
-        if model._ref_key != ctx.key:
-            raise _lib.TvmError("Ref head parameters were modified between forward and backward")
+        _check_unmodified(ctx)
         d, keep = model.field_desc()
         h, buf = model.packed_ref_head()
         lib = _lib.load()

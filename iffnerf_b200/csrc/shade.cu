@@ -296,7 +296,7 @@ extern "C" int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int6
     const size_t smem = (nB + nF + nX) * sizeof(float);
     if (smem > 227 * 1024) return TVM_E_SHAPE;
     {
-        static std::atomic<int> smem_set{0};
+        static TvmDevMemo smem_set;
         int rc_attr = tvm_ensure_dyn_smem(shade_fwd_kernel, smem, smem_set);
         if (rc_attr) return rc_attr;
     }

@@ -451,12 +451,12 @@ extern "C" int tvm_shade_bwd(const tvm_field_desc* desc, const float* rays, int6
     if (smem > 227 * 1024) return TVM_E_SHAPE;
     const long long ctas = (n_rays + (long long)tile - 1) / (long long)tile;
     if (small) {
-        static std::atomic<int> smem_set{0};
+        static TvmDevMemo smem_set;
         int rc_attr = tvm_ensure_dyn_smem(shade_bwd_kernel<32>, smem, smem_set);
         if (rc_attr) return rc_attr;
         shade_bwd_kernel<32><<<(unsigned)ctas, SB_THREADS, smem, (cudaStream_t)stream>>>(a);
     } else {
-        static std::atomic<int> smem_set{0};
+        static TvmDevMemo smem_set;
         int rc_attr = tvm_ensure_dyn_smem(shade_bwd_kernel<64>, smem, smem_set);
         if (rc_attr) return rc_attr;
         shade_bwd_kernel<64><<<(unsigned)ctas, SB_THREADS, smem, (cudaStream_t)stream>>>(a);

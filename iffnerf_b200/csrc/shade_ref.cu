@@ -236,7 +236,7 @@ extern "C" int tvm_shade_ref_fwd(const tvm_field_desc* desc, const tvm_ref_head*
     const unsigned ctas = (unsigned)(tiles < TVM_SM_COUNT * 6 ? tiles : TVM_SM_COUNT * 6);
     cudaStream_t st = (cudaStream_t)stream;
     if (head->in_c == 27) {
-        static std::atomic<int> smem_set{0};
+        static TvmDevMemo smem_set;
         int rc_attr = tvm_ensure_dyn_smem(shade_ref_kernel<27>, smem, smem_set);
         if (rc_attr) return rc_attr;
         shade_ref_kernel<27><<<ctas, REF_THREADS, smem, st>>>(a);
@@ -605,7 +605,7 @@ extern "C" int tvm_shade_ref_bwd(const tvm_field_desc* desc, const tvm_ref_head*
     const size_t floats = (size_t)L.total + (size_t)head->in_c * a.ta + (size_t)RB_RAYS * (2 * (in4 + 1) + 13 + 5 + (RB_XT + 1) + (head->feature_c + 1) + (a.ta + 4));
     const size_t smem = floats * sizeof(float);
     if (smem > 220 * 1024) return TVM_E_SHAPE;
-    static std::atomic<int> smem_set{0};
+    static TvmDevMemo smem_set;
     int rc_attr = tvm_ensure_dyn_smem(shade_ref_bwd_kernel<27>, smem, smem_set);
     if (rc_attr) return rc_attr;
     const unsigned ctas = (unsigned)((n_rays + RB_RAYS - 1) / RB_RAYS);

@@ -286,7 +286,7 @@ int tvm_shade_tc_launch(const tvm_field_desc* desc, const float* rays, int64_t n
     a.b1 = desc->mlp + m.b1; a.b2 = desc->mlp + m.b2; a.b3 = desc->mlp + m.b3;
     a.d = d;
     {
-        static std::atomic<int> smem_set{0};
+        static TvmDevMemo smem_set;
         int rc_attr = tvm_ensure_dyn_smem(shade_tc_kernel, smem, smem_set);
         if (rc_attr) return rc_attr;
     }

@@ -18,9 +18,17 @@
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when the requested size grows past what this process already
 // set for the kernel.  The attribute is per-process CUDA state anyway; skipping the redundant calls keeps a warmed-up
 // launch path free of non-stream API calls, so the entry points can be captured into CUDA graphs.
+// The attribute is per DEVICE, so the high-water mark is kept per device (a process may render on several GPUs).
 #include <atomic>
+struct TvmDevMemo {
+    std::atomic<int> v[16];
+    TvmDevMemo() { for (auto& x : v) x.store(0, std::memory_order_relaxed); }
+};
 template <typename K>
-static inline int tvm_ensure_dyn_smem(K kernel, size_t bytes, std::atomic<int>& high_water) {
+static inline int tvm_ensure_dyn_smem(K kernel, size_t bytes, TvmDevMemo& memo) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::atomic<int>& high_water = memo.v[dev & 15];
     if ((int)bytes <= high_water.load(std::memory_order_relaxed)) return 0;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;

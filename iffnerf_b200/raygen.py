@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -57,13 +58,15 @@ class _PixelRays(torch.autograd.Function):
         m = m.contiguous()
         rays = torch.empty((n, 7), dtype=torch.float32, device=dev)
         lib = _lib.load()
-        _lib.check(lib.tvm_pixel_rays_fwd(_lib.ptr(m), m.shape[1] * 4, kinv, _lib.ptr(pixels), _lib.ptr(pose_index),
-                                          width, n, flags, _lib.ptr(rays), _stream(dev)), "tvm_pixel_rays_fwd")
+        with torch.cuda.device(dev):
+            _lib.check(lib.tvm_pixel_rays_fwd(_lib.ptr(m), m.shape[1] * 4, kinv, _lib.ptr(pixels), _lib.ptr(pose_index),
+                                              width, n, flags, _lib.ptr(rays), _stream(dev)), "tvm_pixel_rays_fwd")
         ctx.save_for_backward(m, pixels, pose_index)
         ctx.meta = (kinv, width, n, flags, tuple(c2w.shape))
         return rays
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, g_rays):
         m, pixels, pose_index = ctx.saved_tensors
         kinv, width, n, flags, shape = ctx.meta
@@ -71,9 +74,10 @@ class _PixelRays(torch.autograd.Function):
         P = m.shape[0]
         g_c2w = torch.zeros((P, 3, 4), dtype=torch.float32, device=m.device)
         lib = _lib.load()
-        _lib.check(lib.tvm_pixel_rays_bwd(_lib.ptr(m), m.shape[1] * 4, kinv, _lib.ptr(pixels), _lib.ptr(pose_index),
-                                          width, n, flags, _lib.ptr(g), g.shape[1], _lib.ptr(g_c2w),
-                                          _stream(m.device)), "tvm_pixel_rays_bwd")
+        with torch.cuda.device(m.device):
+            _lib.check(lib.tvm_pixel_rays_bwd(_lib.ptr(m), m.shape[1] * 4, kinv, _lib.ptr(pixels), _lib.ptr(pose_index),
+                                              width, n, flags, _lib.ptr(g), g.shape[1], _lib.ptr(g_c2w),
+                                              _stream(m.device)), "tvm_pixel_rays_bwd")
         if m.shape[1] == 4:
             g_c2w = torch.cat([g_c2w, torch.zeros((P, 1, 4), device=m.device)], dim=1)
         return g_c2w.reshape(shape), None, None, None, None, None, None
@@ -98,6 +102,10 @@ def pixel_rays(K, c2w, pixels=None, pose_index=None, image_wh=None, renormalize=
             raise ValueError("full-image generation takes one pose (or an explicit pose_index)")
         n = width * int(image_wh[1])
     if pose_index is not None:
+        if not pose_index.is_cuda and pose_index.numel() > 0:      # host-side indices are range-checked for free
+            n_pose = 1 if c2w.dim() == 2 else int(c2w.shape[0])
+            if int(pose_index.min()) < 0 or int(pose_index.max()) >= n_pose:
+                raise ValueError(f"pose_index out of range for {n_pose} pose(s)")
         pose_index = pose_index.to(device=dev, dtype=torch.int32).contiguous()
     flags = NORMALIZE_VIEWDIRS | (RENORMALIZE if renormalize else 0)
     return _PixelRays.apply(c2w, _kinv(K), pixels, pose_index, width, n, flags)

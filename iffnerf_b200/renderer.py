@@ -20,6 +20,10 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("iffnerf_b200 renders on CUDA devices only (no CPU fallback); got device=%r" % (device,))
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    if rays.is_cuda and rays.device != dev:
+        rays = rays.to(dev)                      # outputs live on `device`, like the reference's per-chunk .to(device)
     n = rays.shape[0]
     grad_path = is_train or (torch.is_grad_enabled() and rays.requires_grad)
     if grad_path:

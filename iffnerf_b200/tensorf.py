@@ -75,8 +75,9 @@ class AlphaGridMask(torch.nn.Module):
             dz, dy, dx = v.shape
             lib = _lib.load()
             cells = torch.empty((lib.tvm_occupancy_bytes(dx, dy, dz),), dtype=torch.uint8, device=v.device)
-            _lib.check(lib.tvm_pack_occupancy(_lib.ptr(v), dx, dy, dz, _lib.ptr(cells), _stream(v.device)),
-                       "tvm_pack_occupancy")
+            with torch.cuda.device(v.device):
+                _lib.check(lib.tvm_pack_occupancy(_lib.ptr(v), dx, dy, dz, _lib.ptr(cells), _stream(v.device)),
+                           "tvm_pack_occupancy")
             self._cells, self._cells_key = cells, key
             self._cells_dims = (dx, dy, dz)
             self._coarse_off = int(lib.tvm_occupancy_coarse_offset(dx, dy, dz))
@@ -356,8 +357,9 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
             lib = _lib.load()
             srcs_p = [p.detach().contiguous() for p in planes]
             srcs_l = [p.detach().contiguous() for p in lines]
-            _lib.check(lib.tvm_pack_factors(C.byref(d), _lib.ptr_array(srcs_p), _lib.ptr_array(srcs_l),
-                                            _lib.ptr(self._packed), _stream(dev)), "tvm_pack_factors")
+            with torch.cuda.device(dev):
+                _lib.check(lib.tvm_pack_factors(C.byref(d), _lib.ptr_array(srcs_p), _lib.ptr_array(srcs_l),
+                                                _lib.ptr(self._packed), _stream(dev)), "tvm_pack_factors")
             self._packed_key = key
         return self._packed
 
@@ -373,9 +375,10 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
             if self._mlp_packed is None or self._mlp_packed.numel() != n or self._mlp_packed.device != dev:
                 self._mlp_packed = torch.zeros(int(n), dtype=torch.float32, device=dev)
             w1, w2, w3, b1, b2, b3 = [p.detach().contiguous() for p in ps]
-            _lib.check(lib.tvm_pack_mlp(C.byref(d), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2),
-                                        _lib.ptr(w3), _lib.ptr(b3), _lib.ptr(self._mlp_packed), _stream(dev)),
-                       "tvm_pack_mlp")
+            with torch.cuda.device(dev):
+                _lib.check(lib.tvm_pack_mlp(C.byref(d), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2),
+                                            _lib.ptr(w3), _lib.ptr(b3), _lib.ptr(self._mlp_packed), _stream(dev)),
+                           "tvm_pack_mlp")
             self._mlp_key = key
         return self._mlp_packed
 
@@ -408,8 +411,9 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
             if self._mlp_tc is None or self._mlp_tc.numel() != n or self._mlp_tc.device != dev:
                 self._mlp_tc = torch.zeros(int(n), dtype=torch.uint8, device=dev)
             b, w1, w2, w3 = [p.detach().contiguous() for p in ps]
-            _lib.check(pack_fn(C.byref(d), _lib.ptr(b), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3),
-                               _lib.ptr(self._mlp_tc), _stream(dev)), "tvm_pack_mlp_tc")
+            with torch.cuda.device(dev):
+                _lib.check(pack_fn(C.byref(d), _lib.ptr(b), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(w3),
+                                   _lib.ptr(self._mlp_tc), _stream(dev)), "tvm_pack_mlp_tc")
             self._mlp_tc_key = key
         return self._mlp_tc
 
@@ -497,7 +501,9 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
 
     def _bg(self, bg_color, white_bg, device):
         if bg_color is not None:
-            return bg_color.detach().to(device=device, dtype=torch.float32).contiguous()
+            if bg_color.numel() != 3:
+                raise ValueError(f"bg_color must hold 3 values (one colour for the batch), got shape {tuple(bg_color.shape)}")
+            return bg_color.detach().to(device=device, dtype=torch.float32).reshape(3).contiguous()
         key = (bool(white_bg), str(device))
         if key not in self._bg_cache:
             self._bg_cache[key] = (torch.ones if white_bg else torch.zeros)(3, device=device)
@@ -525,10 +531,11 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         counts = torch.empty((n,), dtype=torch.int32, device=rays.device)
         jit = None if jitter is None else jitter.detach().float().reshape(-1).contiguous()
         lib = _lib.load()
-        _lib.check(lib.tvm_sample_mask(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, _lib.ptr(jit),
-                                       (_lib.F_POINT_SAMPLES if point_samples else 0) |
-                                       (_lib.F_MASK_ANYWHERE if anywhere else 0), _lib.ptr(bits),
-                                       _lib.ptr(counts), _stream(rays.device)), "tvm_sample_mask")
+        with torch.cuda.device(rays.device):
+            _lib.check(lib.tvm_sample_mask(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, _lib.ptr(jit),
+                                           (_lib.F_POINT_SAMPLES if point_samples else 0) |
+                                           (_lib.F_MASK_ANYWHERE if anywhere else 0), _lib.ptr(bits),
+                                           _lib.ptr(counts), _stream(rays.device)), "tvm_sample_mask")
         return bits, counts
 
     @torch.no_grad()
@@ -540,6 +547,12 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         Returns a dict with rgb_map [N,3], depth_map [N], acc_map [N] and, when `sample_outputs`, the
         reference's per-sample outputs alpha / z_vals / dists [N,S] (which disables early termination)."""
         rays = self._prep_rays(rays)
+        with torch.cuda.device(rays.device):       # the C-ABI launches go to the thread's current device
+            return self._render_eval(rays, N_samples, white_bg, bg_color, jitter, sample_outputs, early_term, want_counts,
+                                     keep_workspace, out_rgb, out_depth, point_samples)
+
+    def _render_eval(self, rays, N_samples, white_bg, bg_color, jitter, sample_outputs, early_term, want_counts,
+                     keep_workspace, out_rgb, out_depth, point_samples):
         dev = rays.device
         S = N_samples if N_samples > 0 else self.nSamples
         n = rays.shape[0]

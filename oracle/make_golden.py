@@ -305,6 +305,103 @@ def raygen_case(R, name):
           f"oracle==reference bit-exact fwd+bwd")
 
 
+GRIDOPS_GRID = [32, 28, 36]
+GRIDOPS_LATTICE = (48, 40, 56)
+GRIDOPS_UPSAMPLE = [44, 38, 50]
+
+
+def gridops_fixture():
+    """Small non-cubic truck-shaped field + 960 rays (some miss the box) for the grid-maintenance / checkpoint cases."""
+    aabb = torch.tensor(fx.TRUCK_AABB)
+    fld = fx.make_field(GRIDOPS_GRID, aabb=aabb, near_far=(0.01, 6.0), occ_res=(30, 34, 26))
+    c2w = fx.look_at_c2w((2.2, 1.6, 0.9), target=(0.0, 0.0, 0.25))
+    rays = fx.pinhole_rays(24, 40, 0.5 * 40, c2w, cols=7)
+    return fld, rays
+
+
+def _state_checksums(m):
+    return {k: np.array([v.double().sum().item(), v.double().abs().sum().item()]) for k, v in m.state_dict().items()}
+
+
+def gridops_case(R, name, ckpt_name):
+    """SURVEY 8f-3 / 8f-4 on the UNMODIFIED reference: updateAlphaMask on a (48,40,56) lattice (threshold placed in the
+    widest gap of the pooled alpha values near their median, so the mask is robust to fp32 summation order),
+    filtering_rays in both modes, shrink, upsample_volume_grid, and `save()` of the resulting model; each step's
+    observable results are stored (mask bits, boxes, kept-ray masks, grid sizes, factor checksums, renders)."""
+    import torch.nn.functional as F
+    t = time.time()
+    fld, rays = gridops_fixture()
+    m = build_reference_model(R, fld)
+    rec = dict(param_checksum=fx.param_checksum(fld))
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        alpha, _ = m.getDenseAlpha(GRIDOPS_LATTICE)
+        pooled = F.max_pool3d(alpha.clamp(0, 1).transpose(0, 2).contiguous()[None, None], kernel_size=3, padding=1,
+                              stride=1).reshape(-1)
+        vals = torch.sort(pooled[pooled > 0]).values
+        mid = vals.numel() // 2
+        window = vals[mid - 400:mid + 400]
+        gaps = window[1:] - window[:-1]
+        j = int(torch.argmax(gaps))
+        thres = float((window[j].double() + window[j + 1].double()) / 2)
+        m.alphaMask_thres = thres
+        new_aabb = m.updateAlphaMask(GRIDOPS_LATTICE)
+        vol = m.alphaMask.alpha_volume.reshape(GRIDOPS_LATTICE[::-1])
+        rec.update(thres=np.float64(thres), thres_margin=np.float64(float(gaps[j]) / 2),
+                   mask_bits=np.packbits(vol.bool().numpy().reshape(-1)), mask_shape=np.array(vol.shape),
+                   mask_aabb=new_aabb.numpy(), mask_fraction=np.float64(vol.mean().item()))
+        index = torch.arange(rays.shape[0])[:, None].float()
+        for mode, bbox_only in (("box", True), ("occ", False)):
+            _, kept = m.filtering_rays(rays, index, N_samples=64, bbox_only=bbox_only)
+            keep = torch.zeros(rays.shape[0], dtype=torch.bool)
+            keep[kept.reshape(-1).long()] = True
+            rec[f"filter_{mode}"] = keep.numpy()
+        m.shrink(new_aabb)
+        rec.update(shrink_grid=np.array(m.gridSize.tolist()), shrink_aabb=m.aabb.numpy().copy(),
+                   shrink_step=np.float32(m.stepSize.item()), shrink_nsamples=np.int32(m.nSamples))
+        for k, v in _state_checksums(m).items():
+            rec[f"shrink_sum/{k}"] = v
+        rgb, _, depth, _, _ = R.OctreeRender_trilinear_fast(rays, m, chunk=4096, N_samples=-1, white_bg=True,
+                                                          ndc_ray=False, device="cpu")
+        rec.update(shrink_rgb=rgb.numpy(), shrink_depth=depth.numpy(),
+                   shrink_valid_count=reference_valid_mask(m, rays).sum(-1).numpy().astype(np.int32))
+        m.upsample_volume_grid(GRIDOPS_UPSAMPLE)
+        rec.update(up_grid=np.array(m.gridSize.tolist()), up_step=np.float32(m.stepSize.item()),
+                   up_nsamples=np.int32(m.nSamples))
+        for k, v in _state_checksums(m).items():
+            rec[f"up_sum/{k}"] = v
+        for k in range(3):      # a few exact entries of every resized factor
+            for nme, p in ((f"density_plane.{k}", m.density_plane[k]), (f"app_line.{k}", m.app_line[k])):
+                idx, val = sampled_entries(p.data, n=128, seed=3 + k)
+                rec[f"up_idx/{nme}"] = idx
+                rec[f"up_val/{nme}"] = val
+        rgb, _, depth, _, _ = R.OctreeRender_trilinear_fast(rays, m, chunk=4096, N_samples=-1, white_bg=True,
+                                                          ndc_ray=False, device="cpu")
+        rec.update(up_rgb=rgb.numpy(), up_depth=depth.numpy(),
+                   up_valid_count=reference_valid_mask(m, rays).sum(-1).numpy().astype(np.int32))
+        m.save(os.path.join(OUT, ckpt_name))                  # the reference's own `.th` (tensorBase.py:424-442)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    print(f"[golden] {name}: lattice {GRIDOPS_LATTICE} occupied {rec['mask_fraction']:.3f} (threshold margin "
+          f"{rec['thres_margin']:.2e}), kept rays box/occ {rec['filter_box'].sum()}/{rec['filter_occ'].sum()} of "
+          f"{rays.shape[0]}, shrink -> {rec['shrink_grid'].tolist()}, upsample -> {rec['up_grid'].tolist()}, "
+          f"checkpoint {ckpt_name} ({os.path.getsize(os.path.join(OUT, ckpt_name)) >> 10} KiB)  ({time.time()-t:.1f}s)")
+
+
+def check_product_checkpoint(R, path, rays):
+    """Reverse direction of the `.th` contract: a checkpoint written by the PRODUCT's save() is loaded by the
+    unmodified reference (the loader of train.py:40-45 / pose_estimation/model_utils.py:6-12) and must reproduce the
+    state and the render of the reference model it was copied from."""
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    kwargs = dict(ckpt["kwargs"])
+    kwargs.update(device="cpu")
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = R.TensorVMSplit(**kwargs)
+        m.load(ckpt)
+    with torch.no_grad():
+        rgb, _, depth, _, _ = R.OctreeRender_trilinear_fast(rays, m, chunk=4096, N_samples=-1, white_bg=True,
+                                                          ndc_ray=False, device="cpu")
+    return m, rgb, depth
+
+
 def point_rays(fld, n, seed=11):
     """Points near the occupied shell with isocell-like random directions (6-col rays)."""
     g = torch.Generator().manual_seed(seed)
@@ -358,6 +455,8 @@ def main():
     if "c4_full" in only:
         fld, rays = fx.config4()
         full_image_case(R, "c4_full", fld, rays, 1920)
+    if want("c_gridops"):
+        gridops_case(R, "c_gridops", "c_ckpt_reference.th")
     if want("c4_sub"):
         fld, rays = fx.config4()
         sub, idx = fx.subsample(rays, 2048, seed=0)
