@@ -22,6 +22,8 @@ F_MLP_TC3 = 1 << 4
 F_SPLIT_APP = 1 << 5
 F_ZERO_UNLIT = 1 << 6
 F_MASK_ANYWHERE = 1 << 7
+F_GATHER_ONLY = 1 << 8
+F_COUNT_FETCH = 1 << 9
 
 _f3 = C.c_float * 3
 _f6 = C.c_float * 6
@@ -65,6 +67,7 @@ _lib = None
 _P = C.c_void_p
 _SIGNATURES = {
     "tvm_abi_version": (C.c_int, []),
+    "tvm_launch_count": (C.c_ulonglong, []),
     "tvm_error_string": (C.c_char_p, [C.c_int]),
     "tvm_pack_factors": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(_P), C.POINTER(_P), _P, _P]),
     "tvm_unpack_factor_grads": (C.c_int, [C.POINTER(FieldDesc), _P, C.POINTER(_P), C.POINTER(_P), C.c_int, _P]),

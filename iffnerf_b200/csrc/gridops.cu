@@ -214,12 +214,12 @@ extern "C" int tvm_dense_alpha_mask(const tvm_field_desc* desc, const float* lin
     a.box = (int*)tail;
     a.count = (unsigned long long*)(tail + 32);
     const long long total = (long long)gx * gy * gz;
-    dense_box_init_kernel<<<1, 32, 0, st>>>(a.box, a.count);
+    tvm_count_launch(); dense_box_init_kernel<<<1, 32, 0, st>>>(a.box, a.count);
     long long ctas = (total + 63) / 64;
     if (ctas > TVM_SM_COUNT * 16) ctas = TVM_SM_COUNT * 16;
-    dense_alpha_kernel<<<(unsigned)ctas, 256, 0, st>>>(a);
-    dense_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
-    dense_box_final_kernel<<<1, 32, 0, st>>>(a.box, a.count, box_out);
+    tvm_count_launch(); dense_alpha_kernel<<<(unsigned)ctas, 256, 0, st>>>(a);
+    tvm_count_launch(); dense_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
+    tvm_count_launch(); dense_box_final_kernel<<<1, 32, 0, st>>>(a.box, a.count, box_out);
     TVM_LAUNCH_CHECK();
     return 0;
 }
@@ -231,7 +231,7 @@ extern "C" int tvm_resize_factor(const float* src, int channels, int h, int w, f
     if (mode == 1 && (y_off < 0 || x_off < 0 || y_off + h2 > h || x_off + w2 > w)) return TVM_E_SHAPE;
     ResizeArgs a{src, dst, channels, h, w, h2, w2, mode, y_off, x_off};
     const long long total = (long long)channels * h2 * w2;
-    resize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    tvm_count_launch(); resize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
     TVM_LAUNCH_CHECK();
     return 0;
 }
@@ -243,7 +243,7 @@ extern "C" int tvm_rays_hit_box(const tvm_field_desc* desc, const float* rays, i
     if (n_rays == 0) return 0;
     if (!rays || !out) return TVM_E_NULL;
     if (ray_stride < 6) return TVM_E_SHAPE;
-    rays_hit_box_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*desc, rays, n_rays,
+    tvm_count_launch(); rays_hit_box_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*desc, rays, n_rays,
                                                                                          ray_stride, out);
     TVM_LAUNCH_CHECK();
     return 0;

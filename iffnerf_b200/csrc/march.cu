@@ -321,9 +321,10 @@ struct AppArgs {
     int app_off[3];
     int rays_per_cta;
     int zero_unlit;
+    int* fetch_count;       // COUNT builds: 16-byte texel fetches issued per ray
 };
 
-template <int G, int CA4>
+template <int G, int CA4, bool COUNT = false>
 __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_APP_MIN_BLOCKS) app_gather_kernel(const __grid_constant__ AppArgs a) {
     __shared__ int s_next;
     __shared__ float4 s_w[MARCH_WARPS][TVM_APP_CAP];
@@ -347,12 +348,13 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_APP_MIN_BLOCKS) app_gath
             }
             __syncwarp();
             const int R = (n + 7) >> 3, b = (lane >> 2) * R, e = min(b + R, n);      // quad q walks the q-th eighth of the list
+            unsigned n_fetch = 0;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 float4 A[G];
 #pragma unroll
                 for (int g = 0; g < G; ++g) A[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                app_run_plane<G, CA4>(f, a.sec, k, s_w[warp], s_i[warp], b, e, sub, A);
+                app_run_plane<G, CA4, COUNT>(f, a.sec, k, s_w[warp], s_i[warp], b, e, sub, A, &n_fetch);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     float4 v = A[g];
@@ -365,6 +367,11 @@ __global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_APP_MIN_BLOCKS) app_gath
                     if (lane < 4 && j < (CA4 > 0 ? CA4 : (f.n_app[k] >> 2)))
                         reinterpret_cast<float4*>(a.ray_feat + r * a.ta + a.app_off[k])[j] = v;
                 }
+            }
+            if (COUNT) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) n_fetch += __shfl_xor_sync(FULL, n_fetch, o);
+                if (lane == 0) a.fetch_count[r] = (int)n_fetch;
             }
             __syncwarp();
         } else if (n <= 0 && a.zero_unlit) {
@@ -433,7 +440,7 @@ int launch(K kernel, MarchArgs& a, cudaStream_t st) {
     // of the 228 KB to L1, which is what serves the texel gathers
     carveout_done((const void*)kernel, TVM_MARCH_CARVEOUT);
     const long long ctas = (a.n_rays + a.rays_per_cta - 1) / a.rays_per_cta;
-    kernel<<<(unsigned)ctas, MARCH_WARPS * 32, 0, st>>>(a);
+    tvm_count_launch(); kernel<<<(unsigned)ctas, MARCH_WARPS * 32, 0, st>>>(a);
     TVM_LAUNCH_CHECK();
     return 0;
 }
@@ -487,8 +494,14 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
     if (split) {
         a.app_w = (float4*)(base + ws_split.app_w);
         a.app_i = (unsigned*)(base + ws_split.app_i);
-        rc = lego ? launch(march_fwd_kernel<1, false, 4, 12, 1>, a, st) : launch(march_fwd_kernel<1, false, 0, 0, 1>, a, st);
-        if (rc) return rc;
+        // TVM_F_GATHER_ONLY (measurement): re-run only the appearance-gather stage on the lists already in the workspace
+        const bool gather_only = (flags & TVM_F_GATHER_ONLY) != 0;
+        if (!gather_only) {
+            rc = lego ? launch(march_fwd_kernel<1, false, 4, 12, 1>, a, st) : launch(march_fwd_kernel<1, false, 0, 0, 1>, a, st);
+            if (rc) return rc;
+        } else {
+            a.rays_per_cta = pick_rays_per_cta(a.n_rays, MARCH_WARPS, MARCH_RAYS_PER_CTA);
+        }
         AppArgs g{};
         g.f = *desc; g.sec = a.sec; g.app_w = a.app_w; g.app_i = a.app_i; g.app_count = a.app_count;
         g.ray_feat = a.ray_feat; g.n_rays = n_rays; g.ta = a.ta;
@@ -496,20 +509,26 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
         g.rays_per_cta = a.rays_per_cta;
         g.zero_unlit = (flags & TVM_F_ZERO_UNLIT) ? 1 : 0;
         const unsigned ctas = (unsigned)((n_rays + g.rays_per_cta - 1) / g.rays_per_cta);
-        if (lego) {
+        if (flags & TVM_F_COUNT_FETCH) {           // measurement: per-ray count of the 16-byte fetches -> app_count output
+            if (!lego || !gather_only || !app_count) return TVM_E_MODE;
+            g.fetch_count = app_count;
+            carveout_done((const void*)app_gather_kernel<3, 12, true>, TVM_APP_CARVEOUT);
+            tvm_count_launch(); app_gather_kernel<3, 12, true><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+        } else if (lego) {
             carveout_done((const void*)app_gather_kernel<3, 12>, TVM_APP_CARVEOUT);
-            app_gather_kernel<3, 12><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+            tvm_count_launch(); app_gather_kernel<3, 12><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
         } else if (gmax <= 1) {
             carveout_done((const void*)app_gather_kernel<1, 0>, TVM_APP_CARVEOUT);
-            app_gather_kernel<1, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+            tvm_count_launch(); app_gather_kernel<1, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
         } else if (gmax == 2) {
             carveout_done((const void*)app_gather_kernel<2, 0>, TVM_APP_CARVEOUT);
-            app_gather_kernel<2, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+            tvm_count_launch(); app_gather_kernel<2, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
         } else {
             carveout_done((const void*)app_gather_kernel<3, 0>, TVM_APP_CARVEOUT);
-            app_gather_kernel<3, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+            tvm_count_launch(); app_gather_kernel<3, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
         }
         TVM_LAUNCH_CHECK();
+        if (gather_only) return 0;
         a.spill_cap = TVM_APP_CAP;          // rays whose list overflowed: the fused kernel recomputes them whole
         if (lego) return launch(march_fwd_kernel<3, false, 4, 12, 2>, a, st);
         return launch(march_fwd_kernel<3, false, 0, 0, 2>, a, st);

@@ -320,9 +320,9 @@ template <int G, int CS4, int CA4>
 int dispatch(const BwdArgs& a, cudaStream_t st) {
     const long long ctas = (a.n_rays + a.rays_per_cta - 1) / a.rays_per_cta;
     const bool scatter = a.g_factors != nullptr, pose = a.g_rays != nullptr;
-    if (scatter && pose) march_bwd_kernel<G, true, true, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a);
-    else if (scatter) march_bwd_kernel<G, true, false, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a);
-    else if (pose) march_bwd_kernel<G, false, true, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a);
+    if (scatter && pose) { tvm_count_launch(); march_bwd_kernel<G, true, true, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a); }
+    else if (scatter) { tvm_count_launch(); march_bwd_kernel<G, true, false, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a); }
+    else if (pose) { tvm_count_launch(); march_bwd_kernel<G, false, true, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a); }
     TVM_LAUNCH_CHECK();
     return 0;
 }

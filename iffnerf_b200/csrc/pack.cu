@@ -163,6 +163,8 @@ void factor_views(const tvm_field_desc* d, FactorView planes[6], FactorView line
 
 }  // namespace
 
+std::atomic<unsigned long long> g_tvm_launch_count{0};
+extern "C" unsigned long long tvm_launch_count(void) { return g_tvm_launch_count.load(std::memory_order_relaxed); }
 extern "C" int tvm_abi_version(void) { return TVM_ABI_VERSION; }
 
 extern "C" const char* tvm_error_string(int code) {
@@ -191,7 +193,7 @@ extern "C" int tvm_pack_factors(const tvm_field_desc* desc, const float* const p
         jobs.j[6 + i] = {lines[i], packed + lv[i].off, lv[i].C, lv[i].P, lv[i].W, lv[i].pitch};
         maxP = max(maxP, max(pv[i].P, lv[i].P));
     }
-    cp_to_pc_kernel<<<dim3((unsigned)((maxP + TP - 1) / TP), 12), 256, 0, (cudaStream_t)stream>>>(jobs);
+    tvm_count_launch(); cp_to_pc_kernel<<<dim3((unsigned)((maxP + TP - 1) / TP), 12), 256, 0, (cudaStream_t)stream>>>(jobs);
     TVM_LAUNCH_CHECK();
     return 0;
 }
@@ -211,7 +213,7 @@ extern "C" int tvm_unpack_factor_grads(const tvm_field_desc* desc, const float* 
         jobs.j[6 + i] = {packed_grad + lv[i].off, lines[i], lv[i].C, lv[i].P, lv[i].W, lv[i].pitch};
         maxP = max(maxP, max(pv[i].P, lv[i].P));
     }
-    pc_to_cp_kernel<<<dim3((unsigned)((maxP + TP - 1) / TP), 12), 256, 0, (cudaStream_t)stream>>>(jobs);
+    tvm_count_launch(); pc_to_cp_kernel<<<dim3((unsigned)((maxP + TP - 1) / TP), 12), 256, 0, (cudaStream_t)stream>>>(jobs);
     TVM_LAUNCH_CHECK();
     return 0;
 }
@@ -227,10 +229,10 @@ extern "C" int tvm_pack_occupancy(const float* volume, int dx, int dy, int dz, u
     if (!volume || !cells) return TVM_E_NULL;
     if (dx < 1 || dy < 1 || dz < 1) return TVM_E_SHAPE;
     const long long n = (long long)dx * dy * dz;
-    occupancy_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(volume, dx, dy, dz, cells);
+    tvm_count_launch(); occupancy_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(volume, dx, dy, dz, cells);
     const int cx = (dx + 15) / 16, cy = (dy + 15) / 16, cz = (dz + 15) / 16;
     const int warps = cx * cy * cz;
-    occupancy_coarse_kernel<<<(warps * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+    tvm_count_launch(); occupancy_coarse_kernel<<<(warps * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         cells, dx, dy, dz, cx, cy, cz, cells + tvm_occupancy_coarse_offset(dx, dy, dz));
     TVM_LAUNCH_CHECK();
     return 0;
@@ -248,14 +250,14 @@ extern "C" int tvm_pack_mlp(const tvm_field_desc* desc, const float* w1, const f
     const TvmMlpLayout m = tvm_mlp_layout(desc);
     const int FC = TVM_FEATURE_C;
     cudaStream_t st = (cudaStream_t)stream;
-    transpose_small_kernel<<<(m.k1 * FC + 255) / 256, 256, 0, st>>>(w1, packed + m.w1t, FC, m.in_c, m.k1);
-    copy_small_kernel<<<1, 256, 0, st>>>(b1, packed + m.b1, FC, FC, 0);
-    transpose_small_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(w2, packed + m.w2t, FC, FC, FC);
-    copy_small_kernel<<<1, 256, 0, st>>>(b2, packed + m.b2, FC, FC, 0);
-    copy_small_kernel<<<2, 256, 0, st>>>(w3, packed + m.w3, 3 * FC, 3 * FC, 0);
-    copy_small_kernel<<<1, 32, 0, st>>>(b3, packed + m.b3, 3, 4, 0);
-    pad_cols_kernel<<<(FC * m.k1 + 255) / 256, 256, 0, st>>>(w1, packed + m.w1n, FC, m.in_c, m.k1);
-    copy_small_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(w2, packed + m.w2n, FC * FC, FC * FC, 0);
+    tvm_count_launch(); transpose_small_kernel<<<(m.k1 * FC + 255) / 256, 256, 0, st>>>(w1, packed + m.w1t, FC, m.in_c, m.k1);
+    tvm_count_launch(); copy_small_kernel<<<1, 256, 0, st>>>(b1, packed + m.b1, FC, FC, 0);
+    tvm_count_launch(); transpose_small_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(w2, packed + m.w2t, FC, FC, FC);
+    tvm_count_launch(); copy_small_kernel<<<1, 256, 0, st>>>(b2, packed + m.b2, FC, FC, 0);
+    tvm_count_launch(); copy_small_kernel<<<2, 256, 0, st>>>(w3, packed + m.w3, 3 * FC, 3 * FC, 0);
+    tvm_count_launch(); copy_small_kernel<<<1, 32, 0, st>>>(b3, packed + m.b3, 3, 4, 0);
+    tvm_count_launch(); pad_cols_kernel<<<(FC * m.k1 + 255) / 256, 256, 0, st>>>(w1, packed + m.w1n, FC, m.in_c, m.k1);
+    tvm_count_launch(); copy_small_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(w2, packed + m.w2n, FC * FC, FC * FC, 0);
     TVM_LAUNCH_CHECK();
     return 0;
 }
@@ -272,12 +274,12 @@ extern "C" int tvm_unpack_mlp_grads(const tvm_field_desc* desc, const float* pac
     const TvmMlpLayout m = tvm_mlp_layout(desc);
     const int FC = TVM_FEATURE_C;
     cudaStream_t st = (cudaStream_t)stream;
-    if (w1) untranspose_small_kernel<<<(FC * m.in_c + 255) / 256, 256, 0, st>>>(packed_grad + m.w1t, w1, FC, m.in_c, accumulate);
-    if (b1) copy_small_kernel<<<1, 256, 0, st>>>(packed_grad + m.b1, b1, FC, FC, accumulate);
-    if (w2) untranspose_small_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(packed_grad + m.w2t, w2, FC, FC, accumulate);
-    if (b2) copy_small_kernel<<<1, 256, 0, st>>>(packed_grad + m.b2, b2, FC, FC, accumulate);
-    if (w3) copy_small_kernel<<<2, 256, 0, st>>>(packed_grad + m.w3, w3, 3 * FC, 3 * FC, accumulate);
-    if (b3) copy_small_kernel<<<1, 32, 0, st>>>(packed_grad + m.b3, b3, 3, 3, accumulate);
+    if (w1) { tvm_count_launch(); untranspose_small_kernel<<<(FC * m.in_c + 255) / 256, 256, 0, st>>>(packed_grad + m.w1t, w1, FC, m.in_c, accumulate); }
+    if (b1) { tvm_count_launch(); copy_small_kernel<<<1, 256, 0, st>>>(packed_grad + m.b1, b1, FC, FC, accumulate); }
+    if (w2) { tvm_count_launch(); untranspose_small_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(packed_grad + m.w2t, w2, FC, FC, accumulate); }
+    if (b2) { tvm_count_launch(); copy_small_kernel<<<1, 256, 0, st>>>(packed_grad + m.b2, b2, FC, FC, accumulate); }
+    if (w3) { tvm_count_launch(); copy_small_kernel<<<2, 256, 0, st>>>(packed_grad + m.w3, w3, 3 * FC, 3 * FC, accumulate); }
+    if (b3) { tvm_count_launch(); copy_small_kernel<<<1, 32, 0, st>>>(packed_grad + m.b3, b3, 3, 3, accumulate); }
     TVM_LAUNCH_CHECK();
     return 0;
 }

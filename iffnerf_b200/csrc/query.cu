@@ -163,7 +163,7 @@ extern "C" int tvm_point_appfeature(const tvm_field_desc* desc, const float* poi
     const long long quads_per_cta = 128 / 4;
     long long ctas = (n_points + quads_per_cta - 1) / quads_per_cta;
     if (ctas > TVM_SM_COUNT * 16) ctas = TVM_SM_COUNT * 16;
-    point_appfeature_kernel<<<(unsigned)ctas, 128, 0, (cudaStream_t)stream>>>(a);
+    tvm_count_launch(); point_appfeature_kernel<<<(unsigned)ctas, 128, 0, (cudaStream_t)stream>>>(a);
     TVM_LAUNCH_CHECK();
     return 0;
 }
@@ -180,7 +180,7 @@ extern "C" int tvm_point_density(const tvm_field_desc* desc, const float* points
     const long long quads_per_cta = 256 / 4;
     long long ctas = (n_points + quads_per_cta - 1) / quads_per_cta;
     if (ctas > TVM_SM_COUNT * 16) ctas = TVM_SM_COUNT * 16;
-    point_density_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a);
+    tvm_count_launch(); point_density_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(a);
     TVM_LAUNCH_CHECK();
     return 0;
 }

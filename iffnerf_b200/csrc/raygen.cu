@@ -177,7 +177,7 @@ extern "C" int tvm_pixel_rays_fwd(const float* c2w, int pose_stride, const float
     if (rc) return rc;
     if (n == 0) return 0;
     if (!rays) return TVM_E_NULL;
-    pixel_rays_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, rays);
+    tvm_count_launch(); pixel_rays_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, rays);
     TVM_LAUNCH_CHECK();
     return 0;
 }
@@ -191,7 +191,7 @@ extern "C" int tvm_pixel_rays_bwd(const float* c2w, int pose_stride, const float
     if (n == 0) return 0;
     if (!g_rays || !g_c2w) return TVM_E_NULL;
     if (g_stride < 6) return TVM_E_SHAPE;
-    pixel_rays_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, g_rays, g_stride, g_c2w);
+    tvm_count_launch(); pixel_rays_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, g_rays, g_stride, g_c2w);
     TVM_LAUNCH_CHECK();
     return 0;
 }

@@ -19,11 +19,11 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
                          cudaStream_t st);
 
 int tvm_shade_tc_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, const float* bg,
-                        float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes, cudaStream_t st);
+                        float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes, cudaStream_t st, const tvm_scatter_out* sc);
 
 int tvm_shade_tc3_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
                          const float* bg, float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes,
-                         cudaStream_t st);
+                         cudaStream_t st, const tvm_scatter_out* sc);
 
 namespace {
 
@@ -40,6 +40,7 @@ struct ShadeArgs {
     float* rgb;
     float* depth_out;
     float* acc_out;
+    TvmPeers peers;
     const float* ray_feat;
     const float* acc;
     const float* depth;
@@ -95,9 +96,9 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const __grid_cons
             if (live) {
                 const float ac = __ldg(a.acc + r);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) a.rgb[r * 3 + c] = fminf(fmaxf(__ldg(a.bg + c) * (1.f - ac), 0.f), 1.f);
+                for (int c = 0; c < 3; ++c) tvm_put_rgb(a.peers, a.rgb, r, c, fminf(fmaxf(__ldg(a.bg + c) * (1.f - ac), 0.f), 1.f));
                 const float last = __ldg(a.rays + r * a.ray_stride + a.ray_stride - 1);
-                if (a.depth_out) a.depth_out[r] = __ldg(a.depth + r) + (1.f - ac) * last;
+                tvm_put_depth(a.peers, a.depth_out, r, __ldg(a.depth + r) + (1.f - ac) * last);
                 if (a.acc_out) a.acc_out[r] = ac;
             }
             return;
@@ -245,10 +246,10 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const __grid_cons
                 const float ac = __ldg(a.acc + r);
                 float out = c * ac + __ldg(a.bg + lane) * (1.f - ac);
                 out = fminf(fmaxf(out, 0.f), 1.f);
-                a.rgb[r * 3 + lane] = out;
+                tvm_put_rgb(a.peers, a.rgb, r, lane, out);
                 if (lane == 0) {
                     const float last = __ldg(a.rays + r * a.ray_stride + a.ray_stride - 1);
-                    if (a.depth_out) a.depth_out[r] = __ldg(a.depth + r) + (1.f - ac) * last;
+                    tvm_put_depth(a.peers, a.depth_out, r, __ldg(a.depth + r) + (1.f - ac) * last);
                     if (a.acc_out) a.acc_out[r] = ac;
                 }
             }
@@ -258,21 +259,21 @@ __global__ void __launch_bounds__(SH_THREADS) shade_fwd_kernel(const __grid_cons
 
 }  // namespace
 
-extern "C" int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
-                             const float* bg, uint32_t flags, float* rgb, float* depth, float* acc, const void* ws,
-                             size_t ws_bytes, void* stream) {
+static int shade_fwd_core(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
+                          const float* bg, uint32_t flags, float* rgb, float* depth, float* acc, const void* ws,
+                          size_t ws_bytes, void* stream, const tvm_scatter_out* sc) {
     int rc = tvm_check_desc(desc);
     if (rc) return rc;
     if (n_rays == 0) return 0;
-    if (!rays || !rgb || !ws || !desc->basis || !desc->mlp || !bg) return TVM_E_NULL;
+    if (!rays || (!rgb && !sc) || !ws || !desc->basis || !desc->mlp || !bg) return TVM_E_NULL;
     if (desc->feature_c != FC) return TVM_E_SHAPE;
     if (desc->app_dim > 32 || desc->app_dim <= 0) return TVM_E_SHAPE;
     if (flags & TVM_F_MLP_TC3)                        // tcgen05 bf16x3 split variant (shade_tc3.cu), fp32-equivalent
         return tvm_shade_tc3_launch(desc, rays, n_rays, ray_stride, bg, rgb, depth, acc, ws, ws_bytes,
-                                    (cudaStream_t)stream);
+                                    (cudaStream_t)stream, sc);
     if (flags & TVM_F_MLP_BF16)                       // tcgen05 bf16 variant (shade_tc.cu), tolerance 1e-2
         return tvm_shade_tc_launch(desc, rays, n_rays, ray_stride, bg, rgb, depth, acc, ws, ws_bytes,
-                                   (cudaStream_t)stream);
+                                   (cudaStream_t)stream, sc);
     const TvmWorkspace w = tvm_ws_layout(desc, n_rays);
     if (ws_bytes < w.total) return TVM_E_WORKSPACE;
     const TvmMlpLayout m = tvm_mlp_layout(desc);
@@ -281,6 +282,8 @@ extern "C" int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int6
     a.rays = rays; a.n_rays = n_rays; a.ray_stride = ray_stride;
     a.bg = bg;
     a.rgb = rgb; a.depth_out = depth; a.acc_out = acc;
+    rc = tvm_fill_peers(a.peers, sc);
+    if (rc) return rc;
     a.ray_feat = (const float*)(base + w.ray_feat);
     a.acc = (const float*)(base + w.acc);
     a.depth = (const float*)(base + w.depth);
@@ -301,9 +304,22 @@ extern "C" int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int6
         if (rc_attr) return rc_attr;
     }
     const long long ctas = (n_rays + SH_RAYS - 1) / SH_RAYS;
-    shade_fwd_kernel<<<(unsigned)ctas, SH_THREADS, smem, (cudaStream_t)stream>>>(a);
+    tvm_count_launch(); shade_fwd_kernel<<<(unsigned)ctas, SH_THREADS, smem, (cudaStream_t)stream>>>(a);
     TVM_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int tvm_shade_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
+                             const float* bg, uint32_t flags, float* rgb, float* depth, float* acc, const void* ws,
+                             size_t ws_bytes, void* stream) {
+    return shade_fwd_core(desc, rays, n_rays, ray_stride, bg, flags, rgb, depth, acc, ws, ws_bytes, stream, nullptr);
+}
+
+extern "C" int tvm_shade_fwd_scatter(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
+                                     const float* bg, uint32_t flags, const tvm_scatter_out* out, float* acc,
+                                     const void* ws, size_t ws_bytes, void* stream) {
+    if (!out) return TVM_E_NULL;
+    return shade_fwd_core(desc, rays, n_rays, ray_stride, bg, flags, nullptr, nullptr, acc, ws, ws_bytes, stream, out);
 }
 
 extern "C" int tvm_render_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,

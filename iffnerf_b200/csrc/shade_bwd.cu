@@ -454,12 +454,12 @@ extern "C" int tvm_shade_bwd(const tvm_field_desc* desc, const float* rays, int6
         static TvmDevMemo smem_set;
         int rc_attr = tvm_ensure_dyn_smem(shade_bwd_kernel<32>, smem, smem_set);
         if (rc_attr) return rc_attr;
-        shade_bwd_kernel<32><<<(unsigned)ctas, SB_THREADS, smem, (cudaStream_t)stream>>>(a);
+        tvm_count_launch(); shade_bwd_kernel<32><<<(unsigned)ctas, SB_THREADS, smem, (cudaStream_t)stream>>>(a);
     } else {
         static TvmDevMemo smem_set;
         int rc_attr = tvm_ensure_dyn_smem(shade_bwd_kernel<64>, smem, smem_set);
         if (rc_attr) return rc_attr;
-        shade_bwd_kernel<64><<<(unsigned)ctas, SB_THREADS, smem, (cudaStream_t)stream>>>(a);
+        tvm_count_launch(); shade_bwd_kernel<64><<<(unsigned)ctas, SB_THREADS, smem, (cudaStream_t)stream>>>(a);
     }
     TVM_LAUNCH_CHECK();
     return 0;

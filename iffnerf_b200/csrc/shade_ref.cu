@@ -59,6 +59,7 @@ struct RefArgs {
     float* rgb;
     float* depth;
     float* acc_out;
+    TvmPeers peers;
     const float* ray_feat;
     const float* acc;
     const float* depth_part;
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(REF_THREADS) shade_ref_kernel(const __grid_con
     if (a.app_count[r] <= 0) {       // no appearance sample: the head is not evaluated (tensorBase.py:876-896), rgb = bg (1 - acc)
         const float acc0 = a.acc[r];
 #pragma unroll
-        for (int o = 0; o < 3; ++o) a.rgb[r * 3 + o] = fminf(fmaxf(__ldg(a.bg + o) * (1.0f - acc0), 0.f), 1.f);
-        a.depth[r] = a.depth_part[r] + (1.0f - acc0) * __ldg(rp + a.ray_stride - 1);
+        for (int o = 0; o < 3; ++o) tvm_put_rgb(a.peers, a.rgb, r, o, fminf(fmaxf(__ldg(a.bg + o) * (1.0f - acc0), 0.f), 1.f));
+        tvm_put_depth(a.peers, a.depth, r, a.depth_part[r] + (1.0f - acc0) * __ldg(rp + a.ray_stride - 1));
         if (a.acc_out) a.acc_out[r] = acc0;
         continue;
     }
@@ -187,9 +188,9 @@ __global__ void __launch_bounds__(REF_THREADS) shade_ref_kernel(const __grid_con
 #pragma unroll
     for (int o = 0; o < 3; ++o) {
         const float c = (rgb[o] * lit) * acc + __ldg(a.bg + o) * (1.0f - acc);
-        a.rgb[r * 3 + o] = fminf(fmaxf(c, 0.f), 1.f);
+        tvm_put_rgb(a.peers, a.rgb, r, o, fminf(fmaxf(c, 0.f), 1.f));
     }
-    a.depth[r] = a.depth_part[r] + (1.0f - acc) * __ldg(rp + a.ray_stride - 1);
+    tvm_put_depth(a.peers, a.depth, r, a.depth_part[r] + (1.0f - acc) * __ldg(rp + a.ray_stride - 1));
     if (a.acc_out) a.acc_out[r] = acc;
     }
 }
@@ -206,14 +207,14 @@ extern "C" int tvm_ref_head_layout(const tvm_ref_head* head, int32_t offs[8]) {
     return 0;
 }
 
-extern "C" int tvm_shade_ref_fwd(const tvm_field_desc* desc, const tvm_ref_head* head, const float* rays,
-                                 int64_t n_rays, int ray_stride, const float* bg, float* rgb, float* depth,
-                                 float* acc, const void* ws, size_t ws_bytes, void* stream) {
+static int shade_ref_fwd_core(const tvm_field_desc* desc, const tvm_ref_head* head, const float* rays,
+                              int64_t n_rays, int ray_stride, const float* bg, float* rgb, float* depth,
+                              float* acc, const void* ws, size_t ws_bytes, void* stream, const tvm_scatter_out* sc) {
     int rc = tvm_check_desc(desc);
     if (rc) return rc;
     if (!head) return TVM_E_NULL;
     if (n_rays == 0) return 0;
-    if (!rays || !bg || !rgb || !depth || !ws || !desc->basis || !head->params) return TVM_E_NULL;
+    if (!rays || !bg || ((!rgb || !depth) && !sc) || !ws || !desc->basis || !head->params) return TVM_E_NULL;
     if (ray_stride < 6 || head->in_c != desc->app_dim || head->in_c > REF_MAX_IN || head->n_pairs <= 0 ||
         head->n_pairs > REF_MAX_PAIRS || head->l_max <= 0 || head->l_max > REF_MAX_L || head->feature_c <= 0)
         return TVM_E_SHAPE;
@@ -224,6 +225,8 @@ extern "C" int tvm_shade_ref_fwd(const tvm_field_desc* desc, const tvm_ref_head*
     RefArgs a{};
     a.f = *desc; a.h = *head; a.rays = rays; a.n = n_rays; a.ray_stride = ray_stride; a.bg = bg;
     a.rgb = rgb; a.depth = depth; a.acc_out = acc;
+    rc = tvm_fill_peers(a.peers, sc);
+    if (rc) return rc;
     const char* base = (const char*)ws;
     a.ray_feat = (const float*)(base + w.ray_feat);
     a.acc = (const float*)(base + w.acc);
@@ -239,12 +242,25 @@ extern "C" int tvm_shade_ref_fwd(const tvm_field_desc* desc, const tvm_ref_head*
         static TvmDevMemo smem_set;
         int rc_attr = tvm_ensure_dyn_smem(shade_ref_kernel<27>, smem, smem_set);
         if (rc_attr) return rc_attr;
-        shade_ref_kernel<27><<<ctas, REF_THREADS, smem, st>>>(a);
+        tvm_count_launch(); shade_ref_kernel<27><<<ctas, REF_THREADS, smem, st>>>(a);
     } else {
         return TVM_E_SHAPE;          // app_dim = 27 is what every reference config uses (configs/*.txt)
     }
     TVM_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int tvm_shade_ref_fwd(const tvm_field_desc* desc, const tvm_ref_head* head, const float* rays,
+                                 int64_t n_rays, int ray_stride, const float* bg, float* rgb, float* depth,
+                                 float* acc, const void* ws, size_t ws_bytes, void* stream) {
+    return shade_ref_fwd_core(desc, head, rays, n_rays, ray_stride, bg, rgb, depth, acc, ws, ws_bytes, stream, nullptr);
+}
+
+extern "C" int tvm_shade_ref_fwd_scatter(const tvm_field_desc* desc, const tvm_ref_head* head, const float* rays,
+                                         int64_t n_rays, int ray_stride, const float* bg, const tvm_scatter_out* out,
+                                         float* acc, const void* ws, size_t ws_bytes, void* stream) {
+    if (!out) return TVM_E_NULL;
+    return shade_ref_fwd_core(desc, head, rays, n_rays, ray_stride, bg, nullptr, nullptr, acc, ws, ws_bytes, stream, out);
 }
 
 // =====================================================================================================================
@@ -609,7 +625,7 @@ extern "C" int tvm_shade_ref_bwd(const tvm_field_desc* desc, const tvm_ref_head*
     int rc_attr = tvm_ensure_dyn_smem(shade_ref_bwd_kernel<27>, smem, smem_set);
     if (rc_attr) return rc_attr;
     const unsigned ctas = (unsigned)((n_rays + RB_RAYS - 1) / RB_RAYS);
-    shade_ref_bwd_kernel<27><<<ctas, RB_THREADS, smem, (cudaStream_t)stream>>>(a);
+    tvm_count_launch(); shade_ref_bwd_kernel<27><<<ctas, RB_THREADS, smem, (cudaStream_t)stream>>>(a);
     TVM_LAUNCH_CHECK();
     return 0;
 }

@@ -24,6 +24,7 @@ struct TcArgs {
     float* rgb;
     float* depth_out;
     float* acc_out;
+    TvmPeers peers;
     const float* ray_feat;
     const float* acc;
     const float* depth;
@@ -96,9 +97,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
             if (cg == 0 && live) {
                 const float ac = __ldg(a.acc + r);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) a.rgb[r * 3 + c] = fminf(fmaxf(__ldg(a.bg + c) * (1.f - ac), 0.f), 1.f);
+                for (int c = 0; c < 3; ++c) tvm_put_rgb(a.peers, a.rgb, r, c, fminf(fmaxf(__ldg(a.bg + c) * (1.f - ac), 0.f), 1.f));
                 const float last = __ldg(a.rays + r * a.ray_stride + a.ray_stride - 1);
-                if (a.depth_out) a.depth_out[r] = __ldg(a.depth + r) + (1.f - ac) * last;
+                tvm_put_depth(a.peers, a.depth_out, r, __ldg(a.depth + r) + (1.f - ac) * last);
                 if (a.acc_out) a.acc_out[r] = ac;
             }
             continue;
@@ -218,10 +219,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc_kernel(const __grid_co
                 for (int c = 0; c < 3; ++c) {
                     const float col = lit ? 1.f / (1.f + expf(-(v[c] + s_bias[2 * FC + c]))) : 0.f;
                     const float out = col * ac + __ldg(a.bg + c) * (1.f - ac);
-                    a.rgb[r * 3 + c] = fminf(fmaxf(out, 0.f), 1.f);
+                    tvm_put_rgb(a.peers, a.rgb, r, c, fminf(fmaxf(out, 0.f), 1.f));
                 }
                 const float last = __ldg(a.rays + r * a.ray_stride + a.ray_stride - 1);
-                if (a.depth_out) a.depth_out[r] = __ldg(a.depth + r) + (1.f - ac) * last;
+                tvm_put_depth(a.peers, a.depth_out, r, __ldg(a.depth + r) + (1.f - ac) * last);
                 if (a.acc_out) a.acc_out[r] = ac;
             }
         }
@@ -255,17 +256,17 @@ extern "C" int tvm_pack_mlp_tc(const tvm_field_desc* desc, const float* basis, c
     if (tc_smem_bytes(d) > 227 * 1024) return TVM_E_SHAPE;
     unsigned char* out = (unsigned char*)packed;
     cudaStream_t st = (cudaStream_t)stream;
-    pack_bf16_operand_kernel<<<(N0 * d.k0 + 255) / 256, 256, 0, st>>>(basis, d.app_dim, d.ta, N0, d.k0, out + d.img0, 0);
-    pack_bf16_operand_kernel<<<(FC * d.k1 + 255) / 256, 256, 0, st>>>(w1, FC, d.in_c, FC, d.k1, out + d.img1, 0);
-    pack_bf16_operand_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(w2, FC, FC, FC, FC, out + d.img2, 0);
-    pack_bf16_operand_kernel<<<(N3 * FC + 255) / 256, 256, 0, st>>>(w3, 3, FC, N3, FC, out + d.img3, 0);
+    tvm_count_launch(); pack_bf16_operand_kernel<<<(N0 * d.k0 + 255) / 256, 256, 0, st>>>(basis, d.app_dim, d.ta, N0, d.k0, out + d.img0, 0);
+    tvm_count_launch(); pack_bf16_operand_kernel<<<(FC * d.k1 + 255) / 256, 256, 0, st>>>(w1, FC, d.in_c, FC, d.k1, out + d.img1, 0);
+    tvm_count_launch(); pack_bf16_operand_kernel<<<(FC * FC + 255) / 256, 256, 0, st>>>(w2, FC, FC, FC, FC, out + d.img2, 0);
+    tvm_count_launch(); pack_bf16_operand_kernel<<<(N3 * FC + 255) / 256, 256, 0, st>>>(w3, 3, FC, N3, FC, out + d.img3, 0);
     TVM_LAUNCH_CHECK();
     return 0;
 }
 
 // called by tvm_shade_fwd when TVM_F_MLP_BF16 is set
 int tvm_shade_tc_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, const float* bg,
-                        float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes, cudaStream_t st) {
+                        float* rgb, float* depth, float* acc, const void* ws, size_t ws_bytes, cudaStream_t st, const tvm_scatter_out* sc) {
     if (!desc->mlp_tc || !desc->mlp) return TVM_E_NULL;
     if (desc->feature_c != FC || desc->app_dim + 3 > N0 || desc->app_dim <= 0) return TVM_E_SHAPE;   // feat|view fit 32 cols
     const TcDims d = tc_dims(desc);
@@ -278,6 +279,7 @@ int tvm_shade_tc_launch(const tvm_field_desc* desc, const float* rays, int64_t n
     TcArgs a{};
     a.rays = rays; a.n_rays = n_rays; a.ray_stride = ray_stride; a.bg = bg;
     a.rgb = rgb; a.depth_out = depth; a.acc_out = acc;
+    { int rc_p = tvm_fill_peers(a.peers, sc); if (rc_p) return rc_p; }
     a.ray_feat = (const float*)(base + w.ray_feat);
     a.acc = (const float*)(base + w.acc);
     a.depth = (const float*)(base + w.depth);
@@ -292,7 +294,7 @@ int tvm_shade_tc_launch(const tvm_field_desc* desc, const float* rays, int64_t n
     }
     const long long tiles = (n_rays + TC_RAYS - 1) / TC_RAYS;
     const unsigned grid = (unsigned)(tiles < TVM_SM_COUNT ? tiles : TVM_SM_COUNT);
-    shade_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+    tvm_count_launch(); shade_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
     TVM_LAUNCH_CHECK();
     return 0;
 }

@@ -36,6 +36,47 @@ static inline int tvm_ensure_dyn_smem(K kernel, size_t bytes, TvmDevMemo& memo) 
     return 0;
 }
 
+// kernels launched by the library since it was loaded (tvm_launch_count(): bench.py reports the launches of its timed
+// region from this counter instead of a hand-maintained constant)
+extern std::atomic<unsigned long long> g_tvm_launch_count;
+static inline void tvm_count_launch() { g_tvm_launch_count.fetch_add(1, std::memory_order_relaxed); }
+
+// Output placement of the forward shading kernels (device side of tvm_scatter_out): with n == 0 results go to the
+// kernel's own rgb / depth arrays at the ray's index; otherwise ray r is written at offset dst_index[r] (identity when
+// NULL) of EVERY destination — the image buffers of all ranks of a ray-sharded render, mapped through NVLink peer
+// memory, so the shading epilogue is also the all-gather (iffnerf_b200/sharding.py).
+struct TvmPeers {
+    const long long* dst_index;
+    int n;
+    float* rgb[TVM_MAX_PEERS];
+    float* depth[TVM_MAX_PEERS];
+};
+#if defined(__CUDACC__)
+__device__ __forceinline__ void tvm_put_rgb(const TvmPeers& p, float* rgb, long long r, int c, float v) {
+    if (p.n == 0) { rgb[r * 3 + c] = v; return; }
+    const long long o = p.dst_index ? __ldg(p.dst_index + r) : r;
+    for (int i = 0; i < p.n; ++i) p.rgb[i][o * 3 + c] = v;
+}
+__device__ __forceinline__ void tvm_put_depth(const TvmPeers& p, float* depth, long long r, float v) {
+    if (p.n == 0) { if (depth) depth[r] = v; return; }
+    const long long o = p.dst_index ? __ldg(p.dst_index + r) : r;
+    for (int i = 0; i < p.n; ++i) p.depth[i][o] = v;
+}
+#endif
+static inline int tvm_fill_peers(TvmPeers& p, const tvm_scatter_out* sc) {
+    p = TvmPeers{};
+    if (!sc) return 0;
+    if (sc->n_dst <= 0 || sc->n_dst > TVM_MAX_PEERS) return TVM_E_SHAPE;
+    p.dst_index = (const long long*)sc->dst_index;
+    p.n = sc->n_dst;
+    for (int i = 0; i < sc->n_dst; ++i) {
+        if (!sc->rgb[i] || !sc->depth[i]) return TVM_E_NULL;
+        p.rgb[i] = sc->rgb[i];
+        p.depth[i] = sc->depth[i];
+    }
+    return 0;
+}
+
 constexpr int TVM_SM_COUNT = 148;        // B200: 2 dies x 74 SMs
 constexpr int TVM_MAX_SIGMA_C = 16;
 constexpr int TVM_MAX_APP_C = 48;

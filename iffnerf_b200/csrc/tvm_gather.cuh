@@ -224,9 +224,11 @@ TVM_HD void tvm_slot_from_idx(const tvm_field_desc& f, const float idx[3], float
 }
 
 // plane/line pair k over the run [begin, end): A[g] += sum_t w_t * (plane (x) line)[channels sub + 4g]
-template <int G, int CA4 = 0>
+// COUNT: also count the 16-byte fetches this lane issues (measurement builds: bench.py's fetched-bytes roofline)
+template <int G, int CA4 = 0, bool COUNT = false>
 TVM_HD void app_run_plane(const tvm_field_desc& f, const TvmSections& sec, int k, const float4* __restrict__ sw,
-                          const unsigned* __restrict__ si, int begin, int end, int sub, float4 (&A)[G]) {
+                          const unsigned* __restrict__ si, int begin, int end, int sub, float4 (&A)[G],
+                          unsigned* n_fetch = nullptr) {
     const float4* F4 = reinterpret_cast<const float4*>(f.factors);
     const int C4 = CA4 > 0 ? CA4 : (f.n_app[k] >> 2);
     const unsigned prow = sec.aRow[k];
@@ -259,37 +261,37 @@ TVM_HD void app_run_plane(const tvm_field_desc& f, const TvmSections& sec, int k
         if (oEE != tEE) {
 #pragma unroll
             for (int g = 0; g < G; ++g)
-                if (sub + 4 * g < C4) TEE[g] = TVM_LDG4(F4 + oEE + 4 * g);
+                if (sub + 4 * g < C4) { TEE[g] = TVM_LDG4(F4 + oEE + 4 * g); if (COUNT) ++*n_fetch; }
             tEE = oEE;
         }
         if (oOE != tOE) {
 #pragma unroll
             for (int g = 0; g < G; ++g)
-                if (sub + 4 * g < C4) TOE[g] = TVM_LDG4(F4 + oOE + 4 * g);
+                if (sub + 4 * g < C4) { TOE[g] = TVM_LDG4(F4 + oOE + 4 * g); if (COUNT) ++*n_fetch; }
             tOE = oOE;
         }
         if (oEO != tEO) {
 #pragma unroll
             for (int g = 0; g < G; ++g)
-                if (sub + 4 * g < C4) TEO[g] = TVM_LDG4(F4 + oEO + 4 * g);
+                if (sub + 4 * g < C4) { TEO[g] = TVM_LDG4(F4 + oEO + 4 * g); if (COUNT) ++*n_fetch; }
             tEO = oEO;
         }
         if (oOO != tOO) {
 #pragma unroll
             for (int g = 0; g < G; ++g)
-                if (sub + 4 * g < C4) TOO[g] = TVM_LDG4(F4 + oOO + 4 * g);
+                if (sub + 4 * g < C4) { TOO[g] = TVM_LDG4(F4 + oOO + 4 * g); if (COUNT) ++*n_fetch; }
             tOO = oOO;
         }
         if (oLE != tLE) {
 #pragma unroll
             for (int g = 0; g < G; ++g)
-                if (sub + 4 * g < C4) LE[g] = TVM_LDG4(F4 + oLE + 4 * g);
+                if (sub + 4 * g < C4) { LE[g] = TVM_LDG4(F4 + oLE + 4 * g); if (COUNT) ++*n_fetch; }
             tLE = oLE;
         }
         if (oLO != tLO) {
 #pragma unroll
             for (int g = 0; g < G; ++g)
-                if (sub + 4 * g < C4) LO[g] = TVM_LDG4(F4 + oLO + 4 * g);
+                if (sub + 4 * g < C4) { LO[g] = TVM_LDG4(F4 + oLO + 4 * g); if (COUNT) ++*n_fetch; }
             tLO = oLO;
         }
         const float wEE = wxE * wyE, wOE = wxO * wyE, wEO = wxE * wyO, wOO = wxO * wyO;

@@ -46,6 +46,10 @@ extern "C" {
                                          samples (callers that read the workspace themselves) */
 #define TVM_F_MASK_ANYWHERE (1u << 7) /* tvm_sample_mask: the occupancy test alone decides, also for samples outside the
                                          field's aabb (filtering_rays(bbox_only=False), tensorBase.py:728-737) */
+#define TVM_F_GATHER_ONLY  (1u << 8)  /* measurement, with TVM_F_SPLIT_APP: run only the appearance-gather stage on the lists
+                                         a previous call left in the same workspace */
+#define TVM_F_COUNT_FETCH  (1u << 9)  /* measurement, with TVM_F_GATHER_ONLY: app_count[] receives the number of 16-byte texel
+                                         fetches the gather issued per ray (16/48-component fields) */
 #define TVM_APP_CAP        128        /* entries per ray in the appearance lists; longer rays take the fused kernel */
 #define TVM_F_POINT_SAMPLES (1u << 3) /* sampler of sample_point_color (tensorBase.py:623-638): n_samples samples
                                          centred on the ray origin, z_i = stepSize*(i - n_samples/2)          */
@@ -101,6 +105,8 @@ typedef struct tvm_field_desc {
 } tvm_field_desc;
 
 int  tvm_abi_version(void);
+/* number of kernels this library has launched in the process so far (all entry points) */
+unsigned long long tvm_launch_count(void);
 /* last error string for a returned code (static storage) */
 const char* tvm_error_string(int code);
 
@@ -136,6 +142,18 @@ int tvm_mlp_tc3_supported(const tvm_field_desc* desc);   /* 1 if the head's shap
 size_t tvm_mlp_tc3_pack_bytes(const tvm_field_desc* desc);
 int tvm_pack_mlp_tc3(const tvm_field_desc* desc, const float* basis, const float* w1, const float* w2, const float* w3,
                      void* packed, void* stream);
+
+/* Output placement for ray-sharded renders: ray i of the call is written at offset dst_index[i] (i when
+ * dst_index is NULL) of EVERY destination image — rgb[k] [N][3] and depth[k] [N] for k < n_dst, typically the image
+ * buffers of all ranks mapped through NVLink peer memory (CUDA IPC / symmetric memory), so the shading epilogue is the
+ * all-gather.  All pointers are device-accessible from the launching GPU. */
+#define TVM_MAX_PEERS 8
+typedef struct tvm_scatter_out {
+    const int64_t* dst_index;          /* device [n_rays] destination ray offsets, or NULL                        */
+    int32_t        n_dst;              /* 1 .. TVM_MAX_PEERS                                                     */
+    float*         rgb[TVM_MAX_PEERS];
+    float*         depth[TVM_MAX_PEERS];
+} tvm_scatter_out;
 
 /* ---- the hot path ---------------------------------------------------------------------------------- */
 
@@ -220,6 +238,15 @@ typedef struct tvm_ref_head {
 } tvm_ref_head;
 size_t tvm_ref_head_floats(const tvm_ref_head* head);
 int tvm_ref_head_layout(const tvm_ref_head* head, int32_t offs[8]);
+/* tvm_shade_fwd / tvm_shade_ref_fwd with the results placed through `out` (see tvm_scatter_out) instead of into local
+ * rgb / depth arrays; acc (local, per call ray) stays optional. */
+int tvm_shade_fwd_scatter(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
+                          const float* bg /* device [3] */, uint32_t flags, const tvm_scatter_out* out, float* acc,
+                          const void* ws, size_t ws_bytes, void* stream);
+int tvm_shade_ref_fwd_scatter(const tvm_field_desc* desc, const tvm_ref_head* head, const float* rays, int64_t n_rays,
+                              int ray_stride, const float* bg /* device [3] */, const tvm_scatter_out* out, float* acc,
+                              const void* ws, size_t ws_bytes, void* stream);
+
 /* Per-ray tail with this head (tensorBase.py:886-908), reading the march-stage partials from ws like tvm_shade_fwd. */
 int tvm_shade_ref_fwd(const tvm_field_desc* desc, const tvm_ref_head* head, const float* rays, int64_t n_rays,
                       int ray_stride, const float* bg /* device [3] */, float* rgb, float* depth, float* acc,

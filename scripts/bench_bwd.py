@@ -6,13 +6,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from iffnerf_b200 import _lib
-from oracle import fixtures as fx
-from tests import helpers as H
+from iffnerf_b200 import synthetic as syn
 dev = torch.device("cuda:0")
-fld = fx.make_field([300] * 3, density_shift=0.0)
-m = H.module_from_field(fld, dev)
+m = syn.config2_model(dev)
 lib = _lib.load()
-allrays = fx.config2_rays()
+allrays = syn.config2_rays()
 g = torch.Generator().manual_seed(0)
 d, keep = m.field_desc()
 st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)

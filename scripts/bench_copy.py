@@ -5,12 +5,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import iffnerf_b200 as I
-from oracle import fixtures as fx
-from tests import helpers as H
+from iffnerf_b200 import synthetic as syn
 dev = torch.device("cuda:0")
-fld = fx.make_field([300] * 3, density_shift=0.0)
-m = H.module_from_field(fld, dev)
-rays = fx.config2_rays().pin_memory()
+m = syn.config2_model(dev)
+rays = syn.config2_rays().pin_memory()
 n = rays.shape[0]
 out = torch.empty((n, 4)).pin_memory()
 rgb = torch.empty((n, 3), device=dev); depth = torch.empty(n, device=dev)

@@ -6,8 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from iffnerf_b200 import _lib
-from oracle import fixtures as fx
-from tests import helpers as H
+from iffnerf_b200 import synthetic as syn
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=5)
@@ -18,9 +17,8 @@ ap.add_argument("--march-only", action="store_true")
 ap.add_argument("--fused", action="store_true", help="one-kernel march (no TVM_F_SPLIT_APP)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-fld = fx.make_field([300] * 3, density_shift=0.0)
-m = H.module_from_field(fld, dev)
-rays = fx.config2_rays()
+m = syn.config2_model(dev)
+rays = syn.config2_rays()
 if a.tile:
     tw, th = (int(v) for v in a.tile.split("x"))
     img = rays.view(800, 800, -1)

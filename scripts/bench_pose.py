@@ -5,17 +5,15 @@ import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from oracle import fixtures as fx
-from tests import helpers as H
+from iffnerf_b200 import synthetic as syn
 dev = torch.device("cuda:0")
-fld = fx.make_field([300] * 3, density_shift=0.0)
-m = H.module_from_field(fld, dev)
+m = syn.config2_model(dev)
 m.eval()
 for p in m.parameters():
     p.requires_grad_(False)
 m.eval_sample_outputs = "--samples" in sys.argv
 g = torch.Generator().manual_seed(0)
-allrays = fx.config2_rays()
+allrays = syn.config2_rays()
 prays = allrays[torch.randint(0, allrays.shape[0], (64 * 1024,), generator=g)].to(dev)
 target = torch.rand(64 * 1024, 3, device=dev)
 bg = torch.rand(3, device=dev)

@@ -5,16 +5,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import iffnerf_b200 as I
-from oracle import fixtures as fx
-from oracle.make_golden import REF_KW
+from iffnerf_b200 import synthetic as syn
 dev = torch.device("cuda:0")
-aabb = torch.tensor([[-1.5] * 3, [1.5] * 3])
-torch.manual_seed(fx.SEED)
-with contextlib.redirect_stdout(io.StringIO()):
-    m = I.TensorVMSplit(aabb.clone().to(dev), [300] * 3, dev, **REF_KW)
-occ = fx.sphere_occupancy(aabb, 200, radius=1.0)
-m.alphaMask = I.AlphaGridMask(dev, occ.aabb.clone().to(dev), occ.volume.clone().to(dev))
-rays = fx.config2_rays().to(dev)
+m = syn.build_model([300] * 3, dev, shading="Ref")
+rays = syn.config2_rays().to(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def timeit(fn, reps=5):
     fn(); fn(); torch.cuda.synchronize(); tot = 0.0
@@ -31,7 +25,7 @@ m.native_shade_backup = None
 print(json.dumps(out))
 # train step with this head (4096 rays, S=1039): fused tail backward kernel vs torch autograd through the head
 g = torch.Generator().manual_seed(0)
-allrays = fx.config2_rays()
+allrays = syn.config2_rays()
 tr = allrays[torch.randint(0, allrays.shape[0], (4096,), generator=g)].to(dev)
 target = torch.rand(4096, 3, device=dev)
 ones = torch.ones(3, device=dev)

@@ -5,8 +5,7 @@ import argparse, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from oracle import fixtures as fx
-from tests import helpers as H
+from iffnerf_b200 import synthetic as syn
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--rays", type=int, default=4096)
@@ -14,10 +13,9 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--adam", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-fld = fx.make_field([300] * 3, density_shift=0.0)
-m = H.module_from_field(fld, dev)
+m = syn.config2_model(dev)
 m.train()
-allrays = fx.config2_rays()
+allrays = syn.config2_rays()
 g = torch.Generator().manual_seed(0)
 opt = torch.optim.Adam(m.get_optparam_groups(0.02, 1e-3), betas=(0.9, 0.99)) if a.adam else None
 ev = lambda: torch.cuda.Event(enable_timing=True)
