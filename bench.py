@@ -476,33 +476,45 @@ def strong_config4(dev, syn, world, dist):
     m.eval()
     rays = rays.to(dev)
 
-    def step():
+    def step(placement="auto"):
         if world > 1:
-            return sharding.render_sharded(rays, m, I.OctreeRender_trilinear_fast, white_bg=True, device=dev)
+            return sharding.render_sharded(rays, m, I.OctreeRender_trilinear_fast, white_bg=True, device=dev,
+                                           placement=placement)
         rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(rays, m, white_bg=True, device=dev)
         return rgb, depth
-    for _ in range(2):
-        out = step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        out = step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    t = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
+
+    def time_it(placement):
+        for _ in range(2):
+            out = step(placement)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            out = step(placement)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), out
+    ms, out = time_it("auto")
     res = {"rays": int(rays.shape[0]), "grid": m.gridSize.tolist(), "ms_per_image": ms,
            "rays_per_s": rays.shape[0] / (ms / 1e3), "scaling": "strong", "gathered": world > 1}
     if world > 1:
+        res["placement"] = ("nccl all_gather (symmetric memory unavailable: %s)" % sharding._peer_fallback_reason
+                            if sharding._peer_fallback_reason else
+                            "shading epilogue stores into every rank's image over NVLink peer memory + 1 barrier")
         rgb1, _, depth1, _, _ = I.OctreeRender_trilinear_fast(rays, m, white_bg=True, device=dev)
-        same = torch.tensor([int(torch.equal(out[0], rgb1) and torch.equal(out[1], depth1))], device=dev)
+        ok = torch.equal(out[0], rgb1) and torch.equal(out[1], depth1)
+        ms_g, out_g = time_it("gather")
+        ok_g = torch.equal(out_g[0], rgb1) and torch.equal(out_g[1], depth1)
+        res["ms_per_image_nccl_gather"] = ms_g
+        same = torch.tensor([int(ok), int(ok_g)], device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
-        res["parity"] = {"sharded_image_equals_single_gpu_render": bool(same.item()),
+        res["parity"] = {"sharded_image_equals_single_gpu_render": bool(same[0].item()),
+                         "nccl_gather_path_equals_single_gpu_render": bool(same[1].item()),
                          "compared": "rgb and depth, every rank"}
     del m
     torch.cuda.empty_cache()

@@ -58,6 +58,15 @@ class RefHead(C.Structure):
     ]
 
 
+MAX_PEERS = 8
+
+
+class ScatterOut(C.Structure):
+    """Mirror of `tvm_scatter_out` (include/tvm_b200.h)."""
+    _fields_ = [("dst_index", C.c_void_p), ("n_dst", C.c_int32), ("rgb", C.c_void_p * MAX_PEERS),
+                ("depth", C.c_void_p * MAX_PEERS)]
+
+
 class TvmError(RuntimeError):
     pass
 
@@ -89,6 +98,10 @@ _SIGNATURES = {
                                 _P, _P, C.c_size_t, _P]),
     "tvm_shade_fwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, _P, C.c_uint32, _P, _P, _P, _P,
                                 C.c_size_t, _P]),
+    "tvm_shade_fwd_scatter": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, _P, C.c_uint32, C.POINTER(ScatterOut),
+                                        _P, _P, C.c_size_t, _P]),
+    "tvm_shade_ref_fwd_scatter": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(RefHead), _P, C.c_int64, C.c_int, _P,
+                                            C.POINTER(ScatterOut), _P, _P, C.c_size_t, _P]),
     "tvm_shade_bwd": (C.c_int, [C.POINTER(FieldDesc), _P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                 C.c_size_t, _P]),
     "tvm_mlp_grad_floats": (C.c_size_t, [C.POINTER(FieldDesc)]),

@@ -29,6 +29,7 @@ def shard_tiles(n_rays: int, world: int, rank: int, tile: int = DEFAULT_TILE) ->
 
 
 _index_cache = {}
+_peer_fallback_reason = None      # why "auto" placement fell back to the NCCL gather (None: it did not)
 
 
 def shard_index(n_rays: int, world: int, rank: int, tile: int = DEFAULT_TILE, device=None) -> torch.Tensor:
@@ -56,14 +57,78 @@ def local_rays(rays: torch.Tensor, world: int, rank: int, tile: int = DEFAULT_TI
     return rays.index_select(0, idx), idx
 
 
+class PeerImages:
+    """Image buffers (rgb [N,3] + depth [N]) of every rank of a group in NVLink peer memory (torch symmetric memory):
+    `rgb_ptrs[k]` / `depth_ptrs[k]` are rank k's buffers as seen from THIS GPU, so a kernel here can store into all of
+    them.  Double-buffered: a frame's result stays valid until the second-next frame of the same size starts."""
+
+    def __init__(self, n, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        pg = group if group is not None else dist.group.WORLD
+        self.n, self.frames, self.flip = n, [], 0
+        for _ in range(2):
+            buf = symm.empty((4 * n,), dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(buf, pg.group_name)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            self.frames.append({"buf": buf, "hdl": hdl, "rgb": buf[:3 * n].view(n, 3), "depth": buf[3 * n:],
+                                "rgb_ptrs": ptrs, "depth_ptrs": [p + 12 * n for p in ptrs]})
+
+    def next_frame(self):
+        self.flip ^= 1
+        return self.frames[self.flip]
+
+
+_peer_cache = {}
+
+
+def peer_images(n, device, group=None):
+    key = (n, str(device), id(group))
+    if key not in _peer_cache:
+        if len(_peer_cache) > 8:
+            _peer_cache.clear()
+        _peer_cache[key] = PeerImages(n, device, group)
+    return _peer_cache[key]
+
+
+def render_sharded_peer(rays, tensorf, group=None, tile: int = DEFAULT_TILE, device=None, **render_kw):
+    """Ray-sharded render whose shading epilogue IS the all-gather: every rank renders its cyclic tiles and its shading
+    kernel stores each ray's rgb / depth straight into the image buffers of ALL ranks at the ray's original offset
+    (NVLink peer stores through torch symmetric memory, tvm_scatter_out); one device-side barrier publishes the frame.
+    No index_put / pad / all_gather / permute.  Returns (rgb [N,3], depth [N]) views of this rank's buffer; they stay
+    valid until the second-next call with the same N (double buffering)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = rays.shape[0]
+    dev = torch.device(device) if device is not None else rays.device
+    mine, idx = local_rays(rays.to(dev) if rays.device != dev else rays, world, rank, tile)
+    frame = peer_images(n, dev, group).next_frame()
+    kw = {k: v for k, v in render_kw.items() if k in ("N_samples", "white_bg", "bg_color")}
+    tensorf.render_eval(mine, scatter=(idx, frame["rgb_ptrs"], frame["depth_ptrs"]), **kw)
+    frame["hdl"].barrier(channel=0)          # on the current stream: every rank's stores have landed when it completes
+    return frame["rgb"], frame["depth"]
+
+
 def render_sharded(rays, tensorf, renderer, group=None, tile: int = DEFAULT_TILE, gather: bool = True,
-                   device=None, **render_kw):
+                   device=None, placement: str = "auto", **render_kw):
     """Renders this rank's cyclic tiles of `rays` with `renderer` (OctreeRender_trilinear_fast signature) and
     returns (rgb [N,3], depth [N]) for ALL rays when `gather` (every rank gets the full image), else the local
-    slice plus its ray indices.  No collective touches the render itself."""
+    slice plus its ray indices.  No collective touches the render itself.
+
+    placement (with gather): "peer" = the shading kernel writes into every rank's image over NVLink peer memory
+    (render_sharded_peer; CUDA, device-resident rays), "gather" = NCCL all_gather_into_tensor of 16 B/ray + one
+    permuted copy, "auto" = "peer" when torch symmetric memory is available, else "gather"."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = rays.shape[0]
+    if gather and world > 1 and placement in ("auto", "peer") and rays.is_cuda and hasattr(tensorf, "render_eval") \
+            and world <= 8 and not render_kw.get("is_train", False):
+        try:
+            return render_sharded_peer(rays, tensorf, group=group, tile=tile, device=device, **render_kw)
+        except (ImportError, RuntimeError, AttributeError) as exc:
+            if placement == "peer":
+                raise
+            global _peer_fallback_reason
+            _peer_fallback_reason = f"{type(exc).__name__}: {exc}"
     mine, idx = local_rays(rays, world, rank, tile)
     kw = dict(render_kw)
     if device is not None:

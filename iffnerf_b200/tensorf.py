@@ -541,7 +541,7 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
     @torch.no_grad()
     def render_eval(self, rays, N_samples=-1, white_bg=False, bg_color=None, jitter=None, sample_outputs=False,
                     early_term=True, want_counts=False, keep_workspace=False, out_rgb=None, out_depth=None,
-                    point_samples=False):
+                    point_samples=False, scatter=None):
         """One launch pair (march + shade) over `rays` [N,6|7] on the GPU; no autograd.
 
         Returns a dict with rgb_map [N,3], depth_map [N], acc_map [N] and, when `sample_outputs`, the
@@ -549,10 +549,13 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         rays = self._prep_rays(rays)
         with torch.cuda.device(rays.device):       # the C-ABI launches go to the thread's current device
             return self._render_eval(rays, N_samples, white_bg, bg_color, jitter, sample_outputs, early_term, want_counts,
-                                     keep_workspace, out_rgb, out_depth, point_samples)
+                                     keep_workspace, out_rgb, out_depth, point_samples, scatter)
 
     def _render_eval(self, rays, N_samples, white_bg, bg_color, jitter, sample_outputs, early_term, want_counts,
-                     keep_workspace, out_rgb, out_depth, point_samples):
+                     keep_workspace, out_rgb, out_depth, point_samples, scatter=None):
+        """scatter = (dst_index int64 [N] | None, [rgb base pointers], [depth base pointers]): the shading epilogue writes
+        ray i at offset dst_index[i] of every destination image (tvm_scatter_out; sharding.render_sharded's peer
+        placement) instead of into local rgb_map / depth_map tensors, which are then absent from the result."""
         dev = rays.device
         S = N_samples if N_samples > 0 else self.nSamples
         n = rays.shape[0]
@@ -560,10 +563,13 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         lib = _lib.load()
         if n == 0:
             out_rgb = out_depth = None
-        out = {"rgb_map": out_rgb if out_rgb is not None else torch.empty((n, 3), device=dev),
-               "depth_map": out_depth if out_depth is not None else torch.empty((n,), device=dev),
-               "acc_map": torch.empty((n,), device=dev)}
-        assert out["rgb_map"].is_contiguous() and out["depth_map"].is_contiguous()
+        if scatter is not None:
+            out = {"rgb_map": None, "depth_map": None, "acc_map": torch.empty((n,), device=dev)}
+        else:
+            out = {"rgb_map": out_rgb if out_rgb is not None else torch.empty((n, 3), device=dev),
+                   "depth_map": out_depth if out_depth is not None else torch.empty((n,), device=dev),
+                   "acc_map": torch.empty((n,), device=dev)}
+            assert out["rgb_map"].is_contiguous() and out["depth_map"].is_contiguous()
         alpha = z = dists = None
         if sample_outputs:
             alpha, z, dists = (torch.empty((n, S), device=dev) for _ in range(3))
@@ -582,7 +588,12 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         need = C.c_size_t(0)
         _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, flags & _lib.F_SPLIT_APP, C.byref(need)), "tvm_workspace_bytes")
         ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
-        if not self.native_shade:
+        shade_flags = 0
+        if self.native_shade and self._shade_mode() == "bf16":
+            shade_flags = _lib.F_MLP_BF16
+        elif self.native_shade and self._shade_mode() == "tc3":
+            shade_flags = _lib.F_MLP_TC3
+        if not self.native_shade or scatter is not None:
             flags |= _lib.F_NO_SHADE
         elif self._shade_mode() == "bf16":
             flags |= _lib.F_MLP_BF16
@@ -597,6 +608,29 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
                                       _lib.ptr(out["acc_map"]), _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(dists),
                                       None, _lib.ptr(vcount), _lib.ptr(acount), _lib.ptr(ws), ws.numel(),
                                       _stream(dev)), "tvm_render_fwd")
+        if scatter is not None and n > 0:
+            idx, rgb_ptrs, depth_ptrs = scatter
+            sc = _lib.ScatterOut()
+            if idx is not None:
+                idx = idx.to(device=dev, dtype=torch.int64).contiguous()
+                sc.dst_index = idx.data_ptr()
+            sc.n_dst = len(rgb_ptrs)
+            for k, (pr, pd) in enumerate(zip(rgb_ptrs, depth_ptrs)):
+                sc.rgb[k], sc.depth[k] = int(pr), int(pd)
+            if self.native_shade:
+                _lib.check(lib.tvm_shade_fwd_scatter(C.byref(d), _lib.ptr(rays), n, rays.shape[1], _lib.ptr(bg), shade_flags,
+                                                     C.byref(sc), _lib.ptr(out["acc_map"]), _lib.ptr(ws), ws.numel(),
+                                                     _stream(dev)), "tvm_shade_fwd_scatter")
+            else:
+                head = self.packed_ref_head() if self.ref_kernel else None
+                if head is None:
+                    raise _lib.TvmError("peer placement needs a fused shading kernel (MLP_Fea, or Ref with app_dim 27)")
+                _lib.check(lib.tvm_shade_ref_fwd_scatter(C.byref(d), C.byref(head[0]), _lib.ptr(rays), n, rays.shape[1],
+                                                         _lib.ptr(bg), C.byref(sc), _lib.ptr(out["acc_map"]), _lib.ptr(ws),
+                                                         ws.numel(), _stream(dev)), "tvm_shade_ref_fwd_scatter")
+            if keep_workspace:
+                out["workspace"] = self.workspace_views(d, ws, n)
+            return out
         if keep_workspace or not self.native_shade:
             views = self.workspace_views(d, ws, n)
             if keep_workspace:

@@ -35,10 +35,17 @@ def _worker(rank, world, port, tmp):
         fld, rays = fx.config1(0.0, "sphere", 7)
         m = H.module_from_field(fld, dev)
         # ---- sharded eval: every rank ends up with the full image, identical to a single-GPU render
-        rgb, depth = sharding.render_sharded(rays, m, I.OctreeRender_trilinear_fast, tile=512, gather=True,
-                                             device=dev, white_bg=True)
         ref_rgb, _, ref_depth, _, _ = I.OctreeRender_trilinear_fast(rays, m, white_bg=True, device=dev)
+        rgb, depth = sharding.render_sharded(rays, m, I.OctreeRender_trilinear_fast, tile=512, gather=True,
+                                             device=dev, white_bg=True, placement="gather")
         assert torch.equal(rgb, ref_rgb) and torch.equal(depth, ref_depth)
+        # ---- the same with the shading epilogue storing into every rank's image over NVLink peer memory; three frames
+        # so both buffers of the double-buffered pair are reused once
+        rays_dev = rays.to(dev)
+        for _ in range(3):
+            rgb, depth = sharding.render_sharded(rays_dev, m, I.OctreeRender_trilinear_fast, tile=512, gather=True,
+                                                 device=dev, white_bg=True, placement="peer")
+            assert torch.equal(rgb, ref_rgb) and torch.equal(depth, ref_depth)
         # ---- data-parallel train step == single-GPU step on the whole batch
         torch.manual_seed(3)
         batch = rays[torch.randperm(rays.shape[0])[:2048]].to(dev)
