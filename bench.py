@@ -414,33 +414,46 @@ def dp_train(model, dev, syn, world, rank, dist):
     def loss_of(rgb, alpha, tgt):
         return torch.mean((rgb - tgt) ** 2) + 0.1 * torch.mean(torch.exp(torch.abs(alpha)))
 
-    sync = sharding.GradSync(model, average=True).install() if world > 1 else None
+    state = {"sync": None}
 
     def step():
+        sync = state["sync"]
         model.zero_grad(set_to_none=True)
         rgb, _, _, alpha, _, _ = model(rays, bg_color=ones, is_train=True, N_samples=1039, jitter=jit)
         loss_of(rgb, alpha, target).backward()
         if sync is not None:
             sync.finish()
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize(dev)
+
+    def time_steps():
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+    ms_nccl = None
     if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
+        state["sync"] = sharding.GradSync(model, average=True, transport="nccl").install()
+        ms_nccl = time_steps()
+        state["sync"].remove()
+        state["sync"] = sharding.GradSync(model, average=True).install()     # "auto": NVLink peer memory when available
+    sync = state["sync"]
+    ms = time_steps()
     out = {"rays_global": n_local * world, "rays_per_rank": n_local, "ms_fwd_bwd_allreduce": ms,
            "rays_per_s": n_local * world / (ms / 1e3), "scaling": "weak"}
     if world > 1:
-        out["allreduce_bytes_per_step"] = sync.bytes // max(sync.calls // 2, 1)
+        out["allreduce_bytes_per_step"] = sync.bytes // max(sync.calls, 1)
+        out["allreduce_transport"] = sync.transport_used
+        out["ms_fwd_bwd_allreduce_nccl"] = ms_nccl
         # parity: gradients after the all-reduce vs the single-process gradients of the global batch (every rank computes
         # them rank-batch by rank-batch; both losses are means, so the global loss is the mean of the per-rank losses)
         names = [n for n, _ in model.named_parameters()]

@@ -80,6 +80,9 @@ _SIGNATURES = {
     "tvm_error_string": (C.c_char_p, [C.c_int]),
     "tvm_pack_factors": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(_P), C.POINTER(_P), _P, _P]),
     "tvm_unpack_factor_grads": (C.c_int, [C.POINTER(FieldDesc), _P, C.POINTER(_P), C.POINTER(_P), C.c_int, _P]),
+    "tvm_unpack_factor_grads_scaled": (C.c_int, [C.POINTER(FieldDesc), _P, C.POINTER(_P), C.POINTER(_P), C.c_int, C.c_float,
+                                                 C.c_int, _P]),
+    "tvm_allreduce_sum_peer": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int64, _P, _P]),
     "tvm_occupancy_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "tvm_occupancy_coarse_offset": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "tvm_pack_occupancy": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
@@ -178,6 +181,13 @@ def check(code: int, what: str):
 def ptr(t):
     """Device pointer of a torch tensor (or None)."""
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def ptr_array_int(addresses):
+    arr = (_P * len(addresses))()
+    for i, a in enumerate(addresses):
+        arr[i] = int(a)
+    return arr
 
 
 def ptr_array(tensors):

@@ -124,34 +124,49 @@ class _Render(torch.autograd.Function):
         d_feat = torch.empty((n, ta), device=dev)
         d_acc = torch.empty((n,), device=dev)
         d_view = torch.empty((n, 3), device=dev) if want_rays else None
-        g_basis = torch.zeros_like(model.basis_mat.weight) if want_basis else None
-        g_mlp = torch.zeros(int(lib.tvm_mlp_grad_floats(C.byref(d))), device=dev) if want_mlp else None
+        # parameter gradients accumulate in the model's persistent, pre-zeroed workspace [factors | MLP | basis]
+        want_params = want_factors or want_basis or want_mlp
+        ws_all = ws_f = ws_m = ws_b = None
+        if want_params:
+            ws_all, ws_f, ws_m, ws_b = model.grad_workspace(dev)
+        g_basis_buf = ws_b if want_basis else None
+        g_mlp = ws_m if want_mlp else None
         _lib.check(lib.tvm_shade_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], _lib.ptr(ctx.bg),
                                      _lib.ptr(g_rgb), _lib.ptr(g_acc), _lib.ptr(d_feat), _lib.ptr(d_acc),
-                                     _lib.ptr(g_basis), _lib.ptr(g_mlp), _lib.ptr(d_view), _lib.ptr(ctx.ws),
+                                     _lib.ptr(g_basis_buf), _lib.ptr(g_mlp), _lib.ptr(d_view), _lib.ptr(ctx.ws),
                                      ctx.ws.numel(), st), "tvm_shade_bwd")
-        g_packed = torch.zeros(int(d.n_factor_floats), device=dev) if want_factors else None
+        g_packed = ws_f if want_factors else None
         g_rays6 = torch.zeros((n, 6), device=dev) if want_rays else None
         _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], ctx.S, _lib.ptr(ctx.jit),
                                      ctx.flags, _lib.ptr(d_feat), _lib.ptr(d_acc), _lib.ptr(g_alpha), _lib.ptr(g_packed),
                                      _lib.ptr(g_rays6), _lib.ptr(ctx.ws), ctx.ws.numel(), st), "tvm_march_bwd")
+        scale = 1.0
+        sync = getattr(model, "grad_sync", None)
+        if sync is not None and want_params:
+            # data parallel: ONE all-reduce of the whole workspace (factors + MLP + basis), on this stream, before
+            # unpacking; the 1/world of the mean rides on the unpack
+            scale = sync.reduce_sum(ws_all, covers_small_params=True)
         factor_grads = [None] * 12
         if want_factors:
-            sync = getattr(model, "grad_sync", None)
-            if sync is not None:
-                # data parallel: ONE all-reduce of the flat packed buffer, on this stream, before unpacking
-                sync.reduce_packed_factor_grads(g_packed)
             planes, lines = model._factor_params()
             gp = [torch.empty_like(p) for p in planes]
             gl = [torch.empty_like(p) for p in lines]
-            _lib.check(lib.tvm_unpack_factor_grads(C.byref(d), _lib.ptr(g_packed), _lib.ptr_array(gp),
-                                                   _lib.ptr_array(gl), 0, st), "tvm_unpack_factor_grads")
+            _lib.check(lib.tvm_unpack_factor_grads_scaled(C.byref(d), _lib.ptr(g_packed), _lib.ptr_array(gp),
+                                                          _lib.ptr_array(gl), 0, scale, 1, st), "tvm_unpack_factor_grads")
             factor_grads = gp + gl
         mlp_grads = [None] * 6
-        if want_mlp:
-            mlp_grads = [torch.empty_like(p) for p in _mlp_params(model)]
-            _lib.check(lib.tvm_unpack_mlp_grads(C.byref(d), _lib.ptr(g_mlp), *[_lib.ptr(t) for t in mlp_grads], 0, st),
-                       "tvm_unpack_mlp_grads")
+        g_basis = None
+        if want_mlp or want_basis:
+            small = ws_all[ws_f.numel():]
+            if scale != 1.0:
+                small.mul_(scale)
+            if want_mlp:
+                mlp_grads = [torch.empty_like(p) for p in _mlp_params(model)]
+                _lib.check(lib.tvm_unpack_mlp_grads(C.byref(d), _lib.ptr(g_mlp), *[_lib.ptr(t) for t in mlp_grads], 0, st),
+                           "tvm_unpack_mlp_grads")
+            if want_basis:
+                g_basis = ws_b.clone()
+            small.zero_()
         d_rays = None
         if want_rays:
             d_rays = torch.zeros((n, ctx.ray_cols), device=dev)

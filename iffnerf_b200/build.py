@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtvm_b200.so")
-SOURCES = ["pack.cu", "march.cu", "march_bwd.cu", "shade.cu", "shade_bwd.cu", "shade_tc.cu", "shade_tc3.cu", "shade_ref.cu", "query.cu", "raygen.cu", "gridops.cu"]
+SOURCES = ["pack.cu", "march.cu", "march_bwd.cu", "shade.cu", "shade_bwd.cu", "shade_tc.cu", "shade_tc3.cu", "shade_ref.cu", "query.cu", "raygen.cu", "gridops.cu", "collective.cu"]
 BENCH_LIB = os.path.join(HERE, "libtvm_bench.so")      # measurement aids (include/tvm_bench.h), not part of the product library
 BENCH_SOURCES = ["microbench.cu"]
 HEADERS = ["tvm_math.cuh", "tvm_common.cuh", "tvm_gather.cuh", "tvm_warp.cuh", "tvm_tc.cuh", os.path.join("..", "..", "include", "tvm_b200.h")]

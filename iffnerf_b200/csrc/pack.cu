@@ -33,7 +33,7 @@ __device__ __forceinline__ long long padded_pixel(const TileOrigin& t, long long
     while (x >= W) { x -= W; ++y; }
     return y * pitch + x;
 }
-struct TransposeJobs { TransposeJob j[12]; int accumulate; };
+struct TransposeJobs { TransposeJob j[12]; int accumulate; float scale; int rezero; };
 
 // src [C][P] -> dst [P][C]
 __global__ void __launch_bounds__(256) cp_to_pc_kernel(const __grid_constant__ TransposeJobs jobs) {
@@ -74,9 +74,16 @@ __global__ void __launch_bounds__(256) pc_to_cp_kernel(const __grid_constant__ T
     const TileOrigin org = tile_origin(p0, W);
     for (int i = threadIdx.x; i < lim; i += 256) {
         const int p = i / C, c = i - p * C;
-        tile[c][p] = __ldg(src + padded_pixel(org, p0, p, W, pitch) * C + c);
+        tile[c][p] = jobs.scale * __ldg(src + padded_pixel(org, p0, p, W, pitch) * C + c);
     }
     __syncthreads();
+    if (jobs.rezero) {            // leave the scatter buffer zeroed for the next step (stores only: a separate loop keeps
+        float* z = const_cast<float*>(src);     // the loads above independent of them, several in flight per thread)
+        for (int i = threadIdx.x; i < lim; i += 256) {
+            const int p = i / C, c = i - p * C;
+            z[padded_pixel(org, p0, p, W, pitch) * C + c] = 0.f;
+        }
+    }
     const int px = threadIdx.x & 31, cy = threadIdx.x >> 5;
     const long long p = p0 + px;
     if (p < P)
@@ -186,6 +193,7 @@ extern "C" int tvm_pack_factors(const tvm_field_desc* desc, const float* const p
     FactorView pv[6], lv[6];
     factor_views(desc, pv, lv);
     TransposeJobs jobs{};
+    jobs.scale = 1.0f;
     long long maxP = 0;
     for (int i = 0; i < 6; ++i) {
         if (!planes[i] || !lines[i]) return TVM_E_NULL;
@@ -200,6 +208,12 @@ extern "C" int tvm_pack_factors(const tvm_field_desc* desc, const float* const p
 
 extern "C" int tvm_unpack_factor_grads(const tvm_field_desc* desc, const float* packed_grad, float* const planes[6],
                                        float* const lines[6], int accumulate, void* stream) {
+    return tvm_unpack_factor_grads_scaled(desc, const_cast<float*>(packed_grad), planes, lines, accumulate, 1.0f, 0, stream);
+}
+
+extern "C" int tvm_unpack_factor_grads_scaled(const tvm_field_desc* desc, float* packed_grad, float* const planes[6],
+                                              float* const lines[6], int accumulate, float scale, int rezero,
+                                              void* stream) {
     int rc = tvm_check_desc(desc);
     if (rc) return rc;
     if (!planes || !lines || !packed_grad) return TVM_E_NULL;
@@ -207,6 +221,8 @@ extern "C" int tvm_unpack_factor_grads(const tvm_field_desc* desc, const float* 
     factor_views(desc, pv, lv);
     TransposeJobs jobs{};
     jobs.accumulate = accumulate;
+    jobs.scale = scale;
+    jobs.rezero = rezero;
     long long maxP = 0;
     for (int i = 0; i < 6; ++i) {
         jobs.j[i] = {packed_grad + pv[i].off, planes[i], pv[i].C, pv[i].P, pv[i].W, pv[i].pitch};

@@ -160,10 +160,42 @@ class GradSync:
     autograd backward (before it is unpacked), and `finish()` — called after loss.backward() — reduces the
     small basis/MLP bucket.  With losses normalised by the LOCAL ray count use average=True (global mean)."""
 
-    def __init__(self, model, group=None, average: bool = True):
+    def __init__(self, model, group=None, average: bool = True, transport: str = "auto"):
+        """transport: "peer" = the gradient workspace lives in NVLink peer memory (torch symmetric memory) and is reduced
+        by the library's own two-shot kernel (tvm_allreduce_sum_peer: NVSwitch multicast ld_reduce / st when available,
+        else peer loads and stores); "nccl" = dist.all_reduce; "auto" = "peer" when symmetric memory can be set up on a
+        CUDA/NCCL group of <= 8 ranks, else "nccl"."""
         self.model, self.group, self.average = model, group, average
+        self.transport = transport
         self.calls = 0
         self.bytes = 0
+        self._small_done = False
+        self._peer = None             # {"buf", "hdl", "ptrs", "mc"} once the peer workspace exists
+        self.transport_used = "nccl"
+
+    # ---- peer-memory workspace (called by TensorVMSplit.grad_workspace while this sync is installed)
+    def alloc_workspace(self, n_floats: int, device):
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        want_peer = self.transport in ("auto", "peer") and world > 1 and world <= 8 and torch.device(device).type == "cuda"
+        if want_peer:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                pg = self.group if self.group is not None else dist.group.WORLD
+                n = (n_floats + 3) // 4 * 4
+                buf = symm.empty((n,), dtype=torch.float32, device=device)
+                buf.zero_()
+                hdl = symm.rendezvous(buf, pg.group_name)
+                self._peer = {"buf": buf, "hdl": hdl, "ptrs": [int(p) for p in hdl.buffer_ptrs],
+                              "mc": int(getattr(hdl, "multicast_ptr", 0) or 0)}
+                hdl.barrier(channel=0)
+                self.transport_used = "peer-multicast" if self._peer["mc"] else "peer"
+                return buf[:n_floats]
+            except (ImportError, RuntimeError, AttributeError) as exc:
+                if self.transport == "peer":
+                    raise
+                self.transport_used = f"nccl ({type(exc).__name__}: {exc})"[:200]
+        self._peer = None
+        return torch.zeros(n_floats, dtype=torch.float32, device=device)
 
     def install(self):
         self.model.grad_sync = self
@@ -182,6 +214,32 @@ class GradSync:
         self.bytes += flat.numel() * flat.element_size()
         return flat
 
+    def reduce_sum(self, flat: torch.Tensor, covers_small_params: bool = False) -> float:
+        """SUM all-reduce of a flat gradient workspace in place (no division); returns the factor the caller applies while
+        unpacking (1/world when averaging).  covers_small_params: the workspace also holds the basis / MLP gradients of
+        this step, so finish() has nothing left to reduce."""
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world > 1:
+            pk = self._peer
+            if pk is not None and flat.data_ptr() == pk["buf"].data_ptr() and flat.numel() <= pk["buf"].numel():
+                import ctypes as C
+                from . import _lib
+                lib = _lib.load()
+                rank = dist.get_rank(self.group)
+                pk["hdl"].barrier(channel=0)             # every rank's scatter into its workspace has completed
+                with torch.cuda.device(flat.device):
+                    _lib.check(lib.tvm_allreduce_sum_peer(_lib.ptr_array_int(pk["ptrs"]), world, rank, pk["buf"].numel(),
+                                                          C.c_void_p(pk["mc"] or None),
+                                                          C.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream)),
+                               "tvm_allreduce_sum_peer")
+                pk["hdl"].barrier(channel=0)             # every slice has been written into every workspace
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.calls += 1
+            self.bytes += flat.numel() * flat.element_size()
+        self._small_done = covers_small_params
+        return 1.0 / world if (self.average and world > 1) else 1.0
+
     def reduce_packed_factor_grads(self, g_packed: torch.Tensor):
         """Called by the backward with the flat packed factor-gradient buffer (in place)."""
         return self._reduce(g_packed)
@@ -191,7 +249,11 @@ class GradSync:
         return [m.basis_mat.weight] + list(m.renderModule.parameters())
 
     def finish(self):
-        """Reduce basis_mat + MLP gradients as one flat bucket (call once per step, after backward)."""
+        """Reduce basis_mat + MLP gradients as one flat bucket (call once per step, after backward).  A no-op when the
+        backward already reduced them together with the factor gradients (MLP_Fea head: one workspace, one all-reduce)."""
+        if self._small_done:
+            self._small_done = False
+            return
         ps = [p for p in self.small_params() if p.grad is not None]
         if not ps:
             return

@@ -335,6 +335,25 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
         d.n_factor_floats = lay["total"]
         return d
 
+    def grad_workspace(self, device):
+        """Persistent flat fp32 gradient workspace of the backward kernels: [packed factor gradients | packed MLP
+        gradients | basis_mat gradient].  Zero on entry of every backward (the unpack kernels clear what they read), so
+        no per-step 70 MB memset / allocation, and data-parallel training all-reduces it as ONE bucket."""
+        d = self._base_desc()
+        lib = _lib.load()
+        nf, nm = int(d.n_factor_floats), int(lib.tvm_mlp_grad_floats(C.byref(d))) if self.native_shade else 0
+        nb = self.basis_mat.weight.numel()
+        sync = self.grad_sync if hasattr(self.grad_sync, "alloc_workspace") else None
+        key = (nf, nm, nb, str(device), id(sync))
+        if getattr(self, "_grad_ws_key", None) != key:
+            # data parallel: the sync object decides where the workspace lives (NVLink peer memory when it can; the
+            # allocation is then a collective, which is fine: every rank reaches its first backward together)
+            self._grad_ws = (sync.alloc_workspace(nf + nm + nb, device) if sync is not None
+                             else torch.zeros(nf + nm + nb, dtype=torch.float32, device=device))
+            self._grad_ws_key = key
+        w = self._grad_ws
+        return w, w[:nf], w[nf:nf + nm], w[nf + nm:].view_as(self.basis_mat.weight)
+
     def invalidate_packed(self):
         """Forget the cache keys of every packed parameter shadow: the next use re-packs from the parameters.  (Needed
         after in-place updates that bypass autograd version counters, e.g. an optimiser step replayed by a CUDA graph.)"""

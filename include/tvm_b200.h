@@ -120,6 +120,11 @@ int tvm_pack_factors(const tvm_field_desc* desc, const float* const planes[6], c
  * (so torch-side regularisers, train.py:299-325, keep adding into the same .grad). */
 int tvm_unpack_factor_grads(const tvm_field_desc* desc, const float* packed_grad, float* const planes[6],
                             float* const lines[6], int accumulate, void* stream);
+/* The same with the values multiplied by `scale` on the way out (1/world after a data-parallel SUM all-reduce) and,
+ * when rezero != 0, the packed buffer cleared behind the read so that it can be scattered into again without a
+ * separate memset (a persistent gradient workspace). */
+int tvm_unpack_factor_grads_scaled(const tvm_field_desc* desc, float* packed_grad, float* const planes[6],
+                                   float* const lines[6], int accumulate, float scale, int rezero, void* stream);
 /* alphaMask volume [Dz][Dy][Dx] fp32 (>0 = occupied) -> `cells`: per-cell 8-corner codes [Dz][Dy][Dx] (bytes)
  * followed, at byte offset tvm_occupancy_coarse_offset(), by the 16^3 super-cell summary [cz][cy][cx] used to
  * skip empty space.  `cells` must hold tvm_occupancy_bytes() bytes. */
@@ -283,6 +288,16 @@ int tvm_pixel_rays_fwd(const float* c2w, int pose_stride, const float* kinv_host
 int tvm_pixel_rays_bwd(const float* c2w, int pose_stride, const float* kinv_host, const int32_t* pixels,
                        const int32_t* pose_index, int width, int64_t n, int flags, const float* g_rays, int g_stride,
                        float* g_c2w, void* stream);
+
+/* ---- the one exchange step (csrc/collective.cu) --------------------------------------- */
+
+/* SUM all-reduce of a flat fp32 buffer that every rank holds in NVLink peer memory: peer_bufs[k] (HOST array of n_ranks
+ * device pointers) is rank k's buffer as addressable from this GPU, multicast the NVSwitch multicast address of the same
+ * buffer or NULL.  Rank `rank` reduces its 1/n_ranks slice over all ranks and stores the result into every rank's
+ * buffer (multimem.ld_reduce / multimem.st when multicast != NULL, else peer loads / stores).  n_floats % 4 == 0.
+ * The caller brackets the call with a device-side barrier across the ranks (all producers done / all slices written). */
+int tvm_allreduce_sum_peer(void* const* peer_bufs, int n_ranks, int rank, int64_t n_floats, void* multicast,
+                           void* stream);
 
 /* ---- grid maintenance (csrc/gridops.cu) ------------------------------------------- */
 

@@ -62,14 +62,18 @@ def _worker(rank, world, port, tmp):
             return [p.grad.clone() for p in m.parameters()]
 
         full = step(torch.arange(2048, device=dev), None)
-        sync = sharding.GradSync(m, average=True).install()
         mine = sharding.shard_index(2048, world, rank, tile=2048 // world, device=dev)
-        sharded = step(mine, sync)
-        sync.remove()
-        assert sync.calls == 2
-        for a, b in zip(sharded, full):
-            scale = b.abs().max().item()
-            assert (a - b).abs().max().item() <= 1e-4 * scale + 1e-9, ((a - b).abs().max().item(), scale)
+        # "peer": the library's own all-reduce kernel over NVLink peer memory; "nccl": dist.all_reduce
+        for transport in ("peer", "nccl"):
+            sync = sharding.GradSync(m, average=True, transport=transport).install()
+            for _ in range(2):          # twice: the workspace must come back zeroed from the first step
+                sharded = step(mine, sync)
+            sync.remove()
+            assert sync.calls == 2      # ONE all-reduce per step: factors + MLP + basis share the gradient workspace
+            assert sync.transport_used.startswith(transport)
+            for a, b in zip(sharded, full):
+                scale = b.abs().max().item()
+                assert (a - b).abs().max().item() <= 1e-4 * scale + 1e-9, (transport, (a - b).abs().max().item(), scale)
         torch.cuda.synchronize()
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
