@@ -24,6 +24,7 @@ F_ZERO_UNLIT = 1 << 6
 F_MASK_ANYWHERE = 1 << 7
 F_GATHER_ONLY = 1 << 8
 F_COUNT_FETCH = 1 << 9
+F_BWD_RUNS = 1 << 10
 
 _f3 = C.c_float * 3
 _f6 = C.c_float * 6

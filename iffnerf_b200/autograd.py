@@ -185,6 +185,8 @@ def render_with_grad(model, rays_chunk, white_bg, bg_color, N_samples, jitter, p
     flags = _lib.F_POINT_SAMPLES if point_samples else 0
     if not want_samples and model.early_term_eps > 0:
         flags |= _lib.F_EARLY_TERM
+    if getattr(model, "bwd_runs", False):
+        flags |= _lib.F_BWD_RUNS                # opt-in: run-aggregated gradient scatter (see csrc/march_bwd.cu)
     if (model.grad_forward_tc3 and model.native_shade and model._shade_mode() == "tc3"
             and not any(p.requires_grad for p in _mlp_params(model))):
         # frozen head (pose refinement): the forward shades on the tensor cores (bf16x3 split, 5e-7 from the FFMA

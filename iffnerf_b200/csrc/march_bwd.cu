@@ -52,6 +52,7 @@ struct BwdArgs {
     int ta;
     int app_off[3];
     int rays_per_cta;
+    TvmSections sec;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -73,6 +74,17 @@ march_bwd_kernel(const __grid_constant__ BwdArgs a) {
     __shared__ float s_ret[BWD_WARPS][32];
     __shared__ float s_z[BWD_WARPS][32];
     __shared__ float4 s_dn[BWD_WARPS][32];      // pose-only mode: d(sigma_feature)/d(normalised coords) per sample
+    // training instantiation (scatter, no pose), TVM_F_BWD_RUNS: run-aggregated scatter (tvm_gather.cuh::vm_run_bwd) —
+    // per-(sample, plane) tap records, the upstream scalar of each compacted sample, the per-lane shares of gF . phi.
+    // Measured (65 536 rays): L2 reduction traffic -60 % (lts 56 % -> 21 %) but +71 % instructions; the kernel is
+    // latency-bound at 12 warps/SM, not L2-bound, so it is slower (5.18 vs 3.74 ms) and stays opt-in.
+    constexpr bool RUNS = SCATTER && !POSE;
+    __shared__ CellTaps s_cell[RUNS ? BWD_WARPS : 1][RUNS ? 32 * 3 : 1];
+    __shared__ float s_wt[RUNS ? BWD_WARPS : 1][32];
+    __shared__ __align__(16) float s_part[RUNS ? BWD_WARPS : 1][RUNS ? 128 : 4];
+    const bool runs = RUNS && (a.flags & TVM_F_BWD_RUNS);
+    const float4* F4 = reinterpret_cast<const float4*>(a.f.factors);
+    float4* G4 = reinterpret_cast<float4*>(a.g_factors);
     const tvm_field_desc& f = a.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 3, quad = lane >> 2;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -181,7 +193,39 @@ march_bwd_kernel(const __grid_constant__ BwdArgs a) {
                 float c = g_acc;
                 const bool app = keep && (w > f.weight_thres);
                 const unsigned amask = __ballot_sync(FULL, app);
-                if (amask && a.d_ray_feat) {
+                if (RUNS && runs && amask && a.d_ray_feat) {
+                    // quad q walks the contiguous run q of the block's appearance samples, one (plane, slice) at a time,
+                    // with the pending corner / tap gradients in registers
+                    const int na = __popc(amask), ranka = __popc(amask & lt_mask);
+                    __syncwarp();
+                    if (app) {
+                        const SampleTaps st = make_sample_taps(f, n);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const unsigned C4 = CA4 > 0 ? CA4 : (unsigned)(f.n_app[k] >> 2);
+                            s_cell[warp][ranka * 3 + k] = make_cell_taps(st, k, a.sec.aRow[k], C4, a.sec.aP[k], a.sec.aL[k]);
+                        }
+                        s_wt[warp][ranka] = w;
+                        *reinterpret_cast<float4*>(&s_part[warp][ranka * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    __syncwarp();
+                    const int R = (na + 7) >> 3, b = quad * R, e = min(b + R, na);
+                    const float* gRow = a.d_ray_feat + r * a.ta;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int C4 = CA4 > 0 ? CA4 : (f.n_app[k] >> 2);
+                        const float4* gk = reinterpret_cast<const float4*>(gRow + a.app_off[k]);
+#pragma unroll 1
+                        for (int j = sub; j < C4; j += 4)
+                            vm_run_bwd<true>(F4, G4, s_cell[warp], k, s_wt[warp], b, e, (unsigned)j, TVM_LDG4(gk + j),
+                                             s_part[warp], sub);
+                    }
+                    __syncwarp();
+                    if (app) {
+                        const float4 pp = *reinterpret_cast<const float4*>(&s_part[warp][ranka * 4]);
+                        c += (pp.x + pp.y) + (pp.z + pp.w);
+                    }
+                } else if (amask && a.d_ray_feat) {
                     const int na = __popc(amask), ranka = __popc(amask & lt_mask);
                     __syncwarp();
                     if (app) { s_slot[warp][ranka] = make_float4(n[0], n[1], n[2], w); s_z[warp][ranka] = z; }
@@ -249,7 +293,29 @@ march_bwd_kernel(const __grid_constant__ BwdArgs a) {
                 // ---- density scatter (quads again)
                 const bool live = !(POSE && !SCATTER) && keep && dfeat != 0.f;
                 const unsigned dmask = __ballot_sync(FULL, live);
-                if (dmask) {
+                if (RUNS && runs && dmask) {
+                    const int nd = __popc(dmask), rankd = __popc(dmask & lt_mask);
+                    __syncwarp();
+                    if (live) {
+                        const SampleTaps st = make_sample_taps(f, n);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const unsigned C4 = CS4 > 0 ? CS4 : (unsigned)(f.n_sigma[k] >> 2);
+                            s_cell[warp][rankd * 3 + k] = make_cell_taps(st, k, a.sec.dRow[k], C4, a.sec.dP[k], a.sec.dL[k]);
+                        }
+                        s_wt[warp][rankd] = dfeat;
+                    }
+                    __syncwarp();
+                    const int R = (nd + 7) >> 3, b = quad * R, e = min(b + R, nd);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int C4 = CS4 > 0 ? CS4 : (f.n_sigma[k] >> 2);
+                        if (sub < C4)
+                            vm_run_bwd<false>(F4, G4, s_cell[warp], k, s_wt[warp], b, e, (unsigned)sub,
+                                              make_float4(1.f, 1.f, 1.f, 1.f), nullptr, sub);
+                    }
+                    __syncwarp();
+                } else if (dmask) {
                     const int nd = __popc(dmask), rankd = __popc(dmask & lt_mask);
                     __syncwarp();
                     if (live) { s_slot[warp][rankd] = make_float4(n[0], n[1], n[2], dfeat); s_z[warp][rankd] = z; }
@@ -350,6 +416,7 @@ extern "C" int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int6
     a.acc = (const float*)((const char*)ws + w.acc);
     a.ta = tvm_total_app(desc);
     a.app_off[0] = 0; a.app_off[1] = desc->n_app[0]; a.app_off[2] = desc->n_app[0] + desc->n_app[1];
+    a.sec = tvm_sections(*desc);
     {
         long long rpc = n_rays / (TVM_SM_COUNT * 8);
         a.rays_per_cta = (int)(rpc < BWD_WARPS ? BWD_WARPS : (rpc > BWD_RAYS_PER_CTA ? BWD_RAYS_PER_CTA : rpc));

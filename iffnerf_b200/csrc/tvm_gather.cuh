@@ -370,6 +370,89 @@ TVM_HD float4 vm_slice_bwd(const tvm_field_desc& f, const float4* __restrict__ F
     return f4_mul(pl, ln);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward scatter over a RUN of consecutive samples with register aggregation (march_bwd_kernel, training).
+//
+// The gradient of a sample lands on the 4 corner texels of its plane cell and the 2 taps of its line cell.  Consecutive
+// samples of a ray mostly stay in the same cell, so a quad that walks a contiguous run of the block's samples keeps
+// one pending gradient per (x parity, y parity) corner and per tap parity in registers, tagged with the texel offset,
+// and issues the red.global.add.v4 only when the tag changes (or the run ends): equal addresses of neighbouring samples
+// are added in registers instead of in the L2 reduction units.  CellTaps is the per-(sample, plane) record the owning
+// lane prepares once in shared memory.
+// ------------------------------------------------------------------------------------------------
+struct alignas(16) CellTaps {
+    unsigned oEE, oOE, oEO, oOO;        // float4 offsets (slice 0) of the corner texels: [x parity][y parity]
+    float wEE, wOE, wEO, wOO;           // their bilinear weights
+    unsigned oLE, oLO;                  // float4 offsets (slice 0) of the even / odd line tap
+    float wLE, wLO;
+};
+TVM_HD CellTaps make_cell_taps(const SampleTaps& s, int k, unsigned prow, unsigned C4, unsigned pbase, unsigned lbase) {
+    const AxisTap& tx = s.a[TVM_M0(k)];
+    const AxisTap& ty = s.a[TVM_M1(k)];
+    const AxisTap& tl = s.a[TVM_V(k)];
+    const unsigned xE = (unsigned)(tx.i0 + 1) & ~1u, xO = (unsigned)tx.i0 | 1u;
+    const unsigned yE = (unsigned)(ty.i0 + 1) & ~1u, yO = (unsigned)ty.i0 | 1u;
+    const unsigned lE = (unsigned)(tl.i0 + 1) & ~1u, lO = (unsigned)tl.i0 | 1u;
+    const bool xev = (tx.i0 & 1) == 0, yev = (ty.i0 & 1) == 0, lev = (tl.i0 & 1) == 0;
+    const float wxE = xev ? tx.w0 : tx.w1, wxO = xev ? tx.w1 : tx.w0;
+    const float wyE = yev ? ty.w0 : ty.w1, wyO = yev ? ty.w1 : ty.w0;
+    CellTaps c;
+    const unsigned rE = pbase + yE * prow, rO = pbase + yO * prow;
+    c.oEE = rE + xE * C4; c.oOE = rE + xO * C4; c.oEO = rO + xE * C4; c.oOO = rO + xO * C4;
+    c.wEE = wxE * wyE; c.wOE = wxO * wyE; c.wEO = wxE * wyO; c.wOO = wxO * wyO;
+    c.oLE = lbase + lE * C4; c.oLO = lbase + lO * C4;
+    c.wLE = lev ? tl.w0 : tl.w1; c.wLO = lev ? tl.w1 : tl.w0;
+    return c;
+}
+TVM_HD float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+// pending gradient of one register slot: flush when the destination changes
+TVM_HD void tvm_pend(float4* __restrict__ G4, unsigned& tag, float4& acc, unsigned o, float4 v) {
+    if (o != tag) {
+        if (tag != ~0u) TVM_RED4(G4 + tag, acc);
+        acc = v;
+        tag = o;
+    } else {
+        acc = f4_add(acc, v);
+    }
+}
+
+// One float4 channel slice j of plane/line pair k over the run [begin, end) of the block's compacted samples:
+// up[t] = wts[t] * g4 is the upstream gradient on (plane (x) line)[slice]; returns nothing, adds this lane's share of
+// g4 . phi_t into part[t * 4 + sub] (appearance: c_i of the alpha gradient; ignored for density).
+template <bool WANT_DOT>
+TVM_HD void vm_run_bwd(const float4* __restrict__ F4, float4* __restrict__ G4, const CellTaps* __restrict__ cells, int k,
+                       const float* __restrict__ wts, int begin, int end, unsigned j, float4 g4, float* __restrict__ part,
+                       int sub) {
+    unsigned tEE = ~0u, tOE = ~0u, tEO = ~0u, tOO = ~0u, tLE = ~0u, tLO = ~0u;
+    float4 aEE = make_float4(0.f, 0.f, 0.f, 0.f), aOE = aEE, aEO = aEE, aOO = aEE, aLE = aEE, aLO = aEE;
+#pragma unroll 1
+    for (int t = begin; t < end; ++t) {
+        const CellTaps c = cells[t * 3 + k];
+        const float w = wts[t];
+        const unsigned oEE = c.oEE + j, oOE = c.oOE + j, oEO = c.oEO + j, oOO = c.oOO + j, oLE = c.oLE + j, oLO = c.oLO + j;
+        const float4 vEE = TVM_LDG4(F4 + oEE), vOE = TVM_LDG4(F4 + oOE), vEO = TVM_LDG4(F4 + oEO), vOO = TVM_LDG4(F4 + oOO);
+        const float4 vLE = TVM_LDG4(F4 + oLE), vLO = TVM_LDG4(F4 + oLO);
+        float4 pl = f4_scale(c.wEE, vEE);
+        pl = f4_fma(c.wOE, vOE, pl); pl = f4_fma(c.wEO, vEO, pl); pl = f4_fma(c.wOO, vOO, pl);
+        const float4 ln = f4_fma(c.wLO, vLO, f4_scale(c.wLE, vLE));
+        if (WANT_DOT) part[t * 4 + sub] += f4_dot(g4, f4_mul(pl, ln));
+        const float4 up = f4_scale(w, g4);
+        const float4 up_ln = f4_mul(up, ln), up_pl = f4_mul(up, pl);
+        tvm_pend(G4, tEE, aEE, oEE, f4_scale(c.wEE, up_ln));
+        tvm_pend(G4, tOE, aOE, oOE, f4_scale(c.wOE, up_ln));
+        tvm_pend(G4, tEO, aEO, oEO, f4_scale(c.wEO, up_ln));
+        tvm_pend(G4, tOO, aOO, oOO, f4_scale(c.wOO, up_ln));
+        tvm_pend(G4, tLE, aLE, oLE, f4_scale(c.wLE, up_pl));
+        tvm_pend(G4, tLO, aLO, oLO, f4_scale(c.wLO, up_pl));
+    }
+    if (tEE != ~0u) TVM_RED4(G4 + tEE, aEE);
+    if (tOE != ~0u) TVM_RED4(G4 + tOE, aOE);
+    if (tEO != ~0u) TVM_RED4(G4 + tEO, aEO);
+    if (tOO != ~0u) TVM_RED4(G4 + tOO, aOO);
+    if (tLE != ~0u) TVM_RED4(G4 + tLE, aLE);
+    if (tLO != ~0u) TVM_RED4(G4 + tLO, aLO);
+}
+
 // density: upstream dfeat (scalar, same for every channel).  Returns this lane's share of sigma_feature.
 template <bool SCATTER, bool POSE, int CS4 = 0>
 TVM_HD float density_bwd(const tvm_field_desc& f, const float n[3], float dfeat, int sub, float* gbuf, float dn[3]) {

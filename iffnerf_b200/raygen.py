@@ -109,3 +109,12 @@ def pixel_rays(K, c2w, pixels=None, pose_index=None, image_wh=None, renormalize=
         pose_index = pose_index.to(device=dev, dtype=torch.int32).contiguous()
     flags = NORMALIZE_VIEWDIRS | (RENORMALIZE if renormalize else 0)
     return _PixelRays.apply(c2w, _kinv(K), pixels, pose_index, width, n, flags)
+
+
+def pixel_rays_lie(K, c2w_se3, pixels=None, pose_index=None, image_wh=None, renormalize=True):
+    """`get_rays_lie` (ray_utils.py:103-140; no caller in the reference): the same rays from a pose given as a Lie-group
+    element — any object with `.rotation.matrix()` ([...,3,3]) and `.t` ([...,3]) like kornia's `Se3`.  The 3x4 pose
+    is assembled with torch ops, so gradients flow back into the group parameters through `pixel_rays`."""
+    rot = c2w_se3.rotation.matrix()
+    c2w = torch.cat([rot, c2w_se3.t.unsqueeze(-1)], dim=-1)
+    return pixel_rays(K, c2w, pixels=pixels, pose_index=pose_index, image_wh=image_wh, renormalize=renormalize)

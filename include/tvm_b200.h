@@ -50,6 +50,9 @@ extern "C" {
                                          a previous call left in the same workspace */
 #define TVM_F_COUNT_FETCH  (1u << 9)  /* measurement, with TVM_F_GATHER_ONLY: app_count[] receives the number of 16-byte texel
                                          fetches the gather issued per ray (16/48-component fields) */
+#define TVM_F_BWD_RUNS     (1u << 10) /* tvm_march_bwd, training scatter: quads walk runs of the block's samples and add equal
+                                         texel addresses in registers before one red.v4 (-60 % L2 reduction traffic, +71 %
+                                         instructions; slower at the measured sizes, opt-in) */
 #define TVM_APP_CAP        128        /* entries per ray in the appearance lists; longer rays take the fused kernel */
 #define TVM_F_POINT_SAMPLES (1u << 3) /* sampler of sample_point_color (tensorBase.py:623-638): n_samples samples
                                          centred on the ray origin, z_i = stepSize*(i - n_samples/2)          */

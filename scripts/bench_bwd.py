@@ -17,7 +17,7 @@ st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 bg = m._bg(None, True, dev)
 out = {"lib": os.path.basename(_lib.LIB_PATH)}
 
-def run(n, S, scatter, pose, tag):
+def run(n, S, scatter, pose, tag, flags=0):
     rays = allrays[torch.randint(0, allrays.shape[0], (n,), generator=g)].to(dev)
     need = C.c_size_t(0)
     lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need))
@@ -31,7 +31,7 @@ def run(n, S, scatter, pose, tag):
     g_fac = torch.zeros(int(d.n_factor_floats), device=dev) if scatter else None
     g_rays = torch.zeros((n, 6), device=dev) if pose else None
     def bwd():
-        _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, None, 0, _lib.ptr(d_feat), _lib.ptr(d_acc),
+        _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, None, flags, _lib.ptr(d_feat), _lib.ptr(d_acc),
                                      _lib.ptr(d_alpha), _lib.ptr(g_fac), _lib.ptr(g_rays), _lib.ptr(ws), ws.numel(), st), "bwd")
     for _ in range(3): bwd()
     torch.cuda.synchronize()
@@ -44,4 +44,6 @@ def run(n, S, scatter, pose, tag):
 run(4096, 1039, True, False, "train_4096")
 run(65536, 1036, False, True, "pose_65536")
 run(65536, 1039, True, False, "train_65536")
+run(4096, 1039, True, False, "train_4096_runs", _lib.F_BWD_RUNS)
+run(65536, 1039, True, False, "train_65536_runs", _lib.F_BWD_RUNS)
 print(json.dumps(out))

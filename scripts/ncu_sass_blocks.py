@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """Basic-block view of an .ncu-rep SASS page: runs of instructions with equal execution count, sorted by total
-warp-instructions.  Usage: ncu_sass_blocks.py rep [top]"""
+warp-instructions.  Usage: ncu_sass_blocks.py rep [top] [kernel-substring]   (first launch whose name contains it)"""
 import csv, io, subprocess, sys
 def fl(x):
     try: return float(x.replace(",", ""))
     except ValueError: return 0.0
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+want = sys.argv[3] if len(sys.argv) > 3 else ""
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr = None; data = []
+hdr = None; data = []; take = False
 for r in rows:
+    if r and r[0] == "Kernel Name":
+        if hdr is not None: break          # first matching launch only
+        take = want in r[1]
+        continue
+    if not take: continue
     if r and r[0] == "Address":
-        if hdr is not None: break          # first launch only
         hdr = r; continue
     if hdr is not None and len(r) == len(hdr): data.append(r)
 iS, iI, iN = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")

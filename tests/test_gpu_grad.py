@@ -200,3 +200,33 @@ def test_shade_backward_kernel_matches_torch_autograd_tail(dev, n):
         assert scale > 0, name
         assert (a - b).abs().max().item() <= 2e-4 * scale, (name, (a - b).abs().max().item(), scale)
     assert (ra - rb).abs().max().item() <= 2e-4 * rb.abs().max().item()
+
+
+def test_run_aggregated_scatter_equals_per_sample_scatter(lego, dev):
+    """march_bwd_kernel's opt-in TVM_F_BWD_RUNS path (quads walk runs of the block's samples and add equal texel
+    addresses in registers before one red.v4, tvm_gather.cuh::vm_run_bwd) against the default (one reduction per
+    sample, corner and slice): the same gradients up to fp32 summation order, for every factor."""
+    fld, rays, m = lego
+    sub, _ = fx.subsample(rays, 2048, seed=5)
+    torch.manual_seed(9)
+    jit = torch.rand(2048, device=dev)
+    target = torch.rand(2048, 3, device=dev)
+    grads = {}
+    m.train()
+    for per_sample in (False, True):
+        m.bwd_runs = not per_sample
+        try:
+            m.zero_grad()
+            rgb, _, _, alpha, _, _ = m(sub.to(dev), bg_color=torch.ones(3, device=dev), is_train=True, N_samples=1039,
+                                       jitter=jit)
+            (torch.mean((rgb - target) ** 2) + 0.1 * torch.mean(torch.exp(torch.abs(alpha)))).backward()
+            torch.cuda.synchronize()
+        finally:
+            m.bwd_runs = False
+        grads[per_sample] = [p.grad.detach().clone() for p in _module_params(m)]
+    m.eval()
+    for name, a, b in zip(GRAD_NAMES, grads[False], grads[True]):
+        scale = float(b.abs().max())
+        assert scale > 0, name
+        assert float((a - b).abs().max()) <= 2e-5 * scale, (name, float((a - b).abs().max()), scale)
+        assert int((a != 0).sum()) == int((b != 0).sum()), name          # the same texels are touched

@@ -87,3 +87,27 @@ def test_batched_candidate_poses_chain_to_pose_parameters(dev):
     scale = po.grad.abs().max()
     assert scale > 0
     assert (pd.grad.cpu() - po.grad).abs().max() <= 5e-3 * scale
+
+
+def test_pixel_rays_lie_equals_matrix_pose_and_backpropagates(dev):
+    """`get_rays_lie` (ray_utils.py:103-140) takes the pose as a Lie-group element (kornia Se3: `.rotation.matrix()`,
+    `.t`); pixel_rays_lie assembles [R | t] and must equal pixel_rays on the same matrix, with gradients reaching the
+    group parameters (here an axis-angle vector through the matrix exponential)."""
+    import types
+    import iffnerf_b200 as I
+    g = H.golden("c5_raygen")
+    K, pix = torch.from_numpy(g["K"]), torch.from_numpy(g["pixels"])
+    w = torch.tensor([0.02, -0.01, 0.03], device=dev, requires_grad=True)
+    t = torch.from_numpy(g["c2w"][:3, 3]).to(dev).requires_grad_(True)
+    base = torch.from_numpy(g["c2w"][:3, :3]).to(dev)
+
+    def rotation():
+        z = torch.zeros((), device=dev)
+        skew = torch.stack([torch.stack([z, -w[2], w[1]]), torch.stack([w[2], z, -w[0]]), torch.stack([-w[1], w[0], z])])
+        return torch.linalg.matrix_exp(skew) @ base
+    se3 = types.SimpleNamespace(rotation=types.SimpleNamespace(matrix=rotation), t=t)
+    rays = I.pixel_rays_lie(K, se3, pix)
+    ref = I.pixel_rays(K, torch.cat([rotation(), t[:, None]], -1).detach(), pix)
+    assert torch.equal(rays.detach(), ref)
+    rays.square().sum().backward()
+    assert w.grad is not None and t.grad is not None and float(w.grad.abs().max()) > 0 and float(t.grad.abs().max()) > 0
