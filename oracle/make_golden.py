@@ -270,6 +270,31 @@ def ref_head_case(R, name):
           f"({time.time()-t:.1f}s) reference outputs stored")
 
 
+def wide_head_case(R, name):
+    """The reference's DEFAULT positional-encoding widths (opt.py:131-133: fea_pe = view_pe = 6 -> in_mlpC = 390,
+    tensorBase.py:165-183).  No oracle restatement is needed: the golden is the reference's own render and pins the
+    product directly (its K-chunked tensor-core shading kernel and the fp32 SIMT one)."""
+    t = time.time()
+    aabb = torch.tensor([[-1.5] * 3, [1.5] * 3])
+    torch.manual_seed(fx.SEED)
+    kw = dict(REF_KW)
+    kw.update(shadingMode="MLP_Fea", view_pe=6, fea_pe=6)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = R.TensorVMSplit(aabb.clone(), [128] * 3, "cpu", **kw)
+    occ = fx.sphere_occupancy(aabb, 200, radius=1.0)
+    m.alphaMask = R.AlphaGridMask("cpu", occ.aabb.clone(), occ.volume.clone())
+    _, rays = fx.config1(0.0, None, 7)
+    sub, idx = fx.subsample(rays, 4096, seed=6)
+    with torch.no_grad():
+        rgb, _, depth, _, _ = R.OctreeRender_trilinear_fast(sub, m, chunk=4096, N_samples=-1, white_bg=True,
+                                                          ndc_ray=False, device="cpu")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), ray_index=idx.numpy(), rgb_map=rgb.numpy(),
+                        depth_map=depth.numpy(), in_mlpC=np.int32(m.renderModule.in_mlpC),
+                        param_checksum=np.array([p.double().sum().item() for p in m.state_dict().values()]))
+    print(f"[golden] {name}: in_mlpC={m.renderModule.in_mlpC} rays=4096 rgb_mean={rgb.mean():.4f} "
+          f"({time.time()-t:.1f}s) reference outputs stored")
+
+
 def raygen_case(R, name):
     """rays of 1024 random pixels through a perturbed orbit pose, exactly as the iNeRF loop builds them
     (inerf/estimate_pose_inerf.py:96-99,149-164), and the gradient of a fixed linear functional w.r.t. the pose."""
@@ -455,6 +480,8 @@ def main():
     if "c4_full" in only:
         fld, rays = fx.config4()
         full_image_case(R, "c4_full", fld, rays, 1920)
+    if want("c1_pe66"):
+        wide_head_case(R, "c1_pe66")
     if want("c_gridops"):
         gridops_case(R, "c_gridops", "c_ckpt_reference.th")
     if want("c4_sub"):

@@ -355,3 +355,24 @@ def test_generic_channel_counts_and_modes(cfg, dev):
     for p in params_ref:
         p.requires_grad_(False)
         p.grad = None
+
+
+@pytest.mark.parametrize("mlp", ["auto", "fp32"])
+def test_default_wide_head_matches_reference_golden(mlp, dev):
+    """fea_pe = view_pe = 6 (the reference's default, opt.py:131-133; in_mlpC = 390): 'auto' must pick the tensor-core
+    kernel (K-chunked bf16x3 variant, csrc/shade_tc3.cu::shade_tc3k_kernel) and match the reference's render to 1e-4;
+    the fp32 SIMT kernel is checked against the same golden."""
+    from iffnerf_b200 import synthetic as syn
+    g = H.golden("c1_pe66")
+    m = syn.build_model([128] * 3, dev, view_pe=6, fea_pe=6)
+    got = np.array([p.double().sum().item() for p in m.state_dict().values()])
+    np.testing.assert_allclose(got, g["param_checksum"], rtol=1e-10, atol=1e-10)
+    assert m.renderModule.in_mlpC == int(g["in_mlpC"]) == 390
+    _, rays = fx.config1(0.0, None, 7)
+    rays = rays[torch.from_numpy(g["ray_index"])].contiguous().to(dev)
+    m.mlp_precision = mlp
+    assert m._shade_mode() == ("tc3" if mlp == "auto" else "fp32")
+    o = m.render_eval(rays, white_bg=True)
+    torch.cuda.synchronize()
+    assert np.abs(o["rgb_map"].cpu().numpy() - g["rgb_map"]).max() <= TOL
+    assert np.abs(o["depth_map"].cpu().numpy() - g["depth_map"]).max() <= TOL
