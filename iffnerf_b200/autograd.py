@@ -379,7 +379,10 @@ def render_with_grad_torch_tail(model, rays_chunk, white_bg, bg_color, N_samples
     ray_feat, acc, depth_p, alpha, z, dists, app_count = _March.apply(model, rays, S, jitter, flags, *planes, *lines)
     if bg_color is None:
         bg_color = model._bg(None, white_bg, rays.device)
-    if getattr(model, "ref_kernel_train", False) and not model.native_shade and model.packed_ref_head() is not None:
+    if getattr(model, "ref_kernel_train", False) and not model.native_shade and model.packed_ref_head() is None:
+        raise _lib.TvmError("this `Ref` head configuration has no fused tail kernel and the render path has no eager "
+                            "fallback; ref_kernel_train = False runs the torch-op tail explicitly (cross-checks only)")
+    if getattr(model, "ref_kernel_train", False) and not model.native_shade:
         # fused Ref tail in both directions (csrc/shade_ref.cu); d(rgb_map)/d(acc) reaches the march backward through acc
         rgb_map, depth_map = _RefTail.apply(model, rays, bg_color, ray_feat, acc, depth_p, app_count,
                                             model.basis_mat.weight, *_ref_tail_params(model))

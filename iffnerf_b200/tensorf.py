@@ -122,8 +122,10 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
     # pose-refinement loop wants (inerf/estimate_pose_inerf.py:166 reads rgb and opacity only).
     eval_sample_outputs = True
     grad_forward_tc3 = True      # differentiable forward with a frozen MLP_Fea head (pose mode): tensor-core shading kernel
-    ref_kernel_train = True      # `Ref` head, training: fused tail backward kernel (False: torch autograd through the head)
-    ref_kernel = True            # `Ref` head, eval: fused tail kernel (False: the torch-op tail, kept for cross-checks)
+    # `Ref` head: fused tail kernels in both directions.  False = run the head as torch ops — an explicit cross-check
+    # switch for tests / scripts; there is no silent fallback: a head without a fused kernel raises while these are True
+    ref_kernel_train = True
+    ref_kernel = True
     # transmittance below which an eval ray stops marching (error on rgb/acc <= this value)
     early_term_eps = 1e-5
     # shading-stage arithmetic on the no-grad path:
@@ -661,7 +663,11 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
                                                      _lib.ptr(bg), _lib.ptr(out["rgb_map"]), _lib.ptr(out["depth_map"]),
                                                      _lib.ptr(out["acc_map"]), _lib.ptr(ws), ws.numel(), _stream(dev)),
                                "tvm_shade_ref_fwd")
-                else:
+                elif self.ref_kernel:
+                    raise _lib.TvmError("this `Ref` head configuration has no fused tail kernel (it needs predicted normals "
+                                        "and app_dim = 27) and the render path has no eager fallback; ref_kernel = False "
+                                        "runs the torch-op tail explicitly (cross-checks only)")
+                else:           # explicit cross-check switch (tests, scripts/bench_ref_head.py)
                     self._torch_shade_tail(rays, views, bg, out)
         return out
 
