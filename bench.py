@@ -5,8 +5,8 @@
 
 A "step" is one full-image render per GPU (800x800 = 640 000 rays, lego-shaped 300^3 VM field, 16x3/48x3 components,
 S=1036 samples/ray, synthetic sphere occupancy) — BASELINE.json configs[1].
-  value         rays/s with the rays already resident in HBM (march + shade kernels, device-timed, L2 flushed
-                between steps)
+  value         rays/s through OctreeRender_trilinear_fast with the rays already resident in HBM (march + shade
+                kernels, device-timed, L2 flushed between steps)
   e2e           the same through OctreeRender_trilinear_fast with HOST (pinned) rays: H2D of the rays and D2H of
                 rgb+depth inside the timed region
   roofline      the appearance-gather kernel: bytes it FETCHES (counted by a counting build of the same kernel) / its
@@ -586,7 +586,10 @@ def run_ours(args, rank, world, local_rank):
     timed = device_timer(torch, dev, flush, barrier)
 
     def step_device():
-        return model.render_eval(rays_dev, white_bg=True)
+        # the reference-facing call (renderer.py:12-25) on device-resident rays
+        rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(rays_dev, model, chunk=4096, N_samples=-1, white_bg=True,
+                                                          ndc_ray=False, device=dev)
+        return {"rgb_map": rgb, "depth_map": depth}
 
     d, keep = model.field_desc()
     need = C.c_size_t(0)

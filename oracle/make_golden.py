@@ -172,6 +172,12 @@ def train_case(R, name, fld, rays, n_samples):
         rec[f"g_sum/{nme}"] = np.float64(g.double().sum().item())
         rec[f"g_l2/{nme}"] = np.float64(g.double().norm().item())
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+    # complete gradient vectors of the small parameters (lines, basis, MLP): every entry is checked, small ones included
+    full = {"loss": np.float64(loss.item())}
+    for nme, g in zip(names, ref_grads):
+        if "plane" not in nme:
+            full[f"g_full/{nme}"] = g.detach().numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, name + "_full.npz"), **full)
     print(f"[golden] {name}: rays={N} S={n_samples} loss={loss.item():.6f} ({time.time()-t:.1f}s) "
           f"oracle==reference bit-exact fwd+bwd")
 
