@@ -59,6 +59,23 @@ def test_field_desc_struct_matches_header(built_lib):
     assert _lib.FieldDesc.factors.offset == o3
 
 
+def test_scatter_out_and_ref_head_structs_match_header(built_lib):
+    """tvm_scatter_out / tvm_ref_head: ctypes mirrors laid out exactly as the compiler lays out the header's structs."""
+    import ctypes as C, subprocess, tempfile
+    from iffnerf_b200 import _lib
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "sz.c")
+        open(c, "w").write('#include <stdio.h>\n#include <stddef.h>\n#include "tvm_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %d",'
+                           'sizeof(tvm_scatter_out), offsetof(tvm_scatter_out, n_dst), offsetof(tvm_scatter_out, rgb),'
+                           'offsetof(tvm_scatter_out, depth), sizeof(tvm_ref_head), TVM_MAX_PEERS);return 0;}')
+        exe = os.path.join(td, "sz")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        size, o1, o2, o3, ref_size, peers = map(int, subprocess.run([exe], capture_output=True, text=True).stdout.split())
+    assert C.sizeof(_lib.ScatterOut) == size and _lib.MAX_PEERS == peers
+    assert _lib.ScatterOut.n_dst.offset == o1 and _lib.ScatterOut.rgb.offset == o2 and _lib.ScatterOut.depth.offset == o3
+    assert C.sizeof(_lib.RefHead) == ref_size
+
+
 def _module(grid=(24, 20, 28), **kw):
     import iffnerf_b200 as I
     args = dict(density_n_comp=[16] * 3, appearance_n_comp=[48] * 3, app_dim=27, shadingMode="MLP_Fea",
