@@ -234,13 +234,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
                 const int nf = is_feat ? d.fea_pe : d.view_pe;
                 const int cc = is_feat ? ch : ch - d.app_dim;
                 const int sb = is_feat ? sin_f : sin_v, cb = is_feat ? cos_f : cos_v;
-                float scale = 1.f;
-                for (int j = 0; j < nf; ++j) {
-                    float sn, cs;
-                    sincosf(x * scale, &sn, &cs);
+                float sn = 0.f, cs = 1.f;
+                if (nf > 0) sincosf(x, &sn, &cs);
+                for (int j = 0; j < nf; ++j) {          // higher octaves by angle doubling (<= 2^(nf-1) ulp)
                     split_store1(s_ah, s_al, canon_off(row, sb + cc * nf + j, d.k1), sn);
                     split_store1(s_ah, s_al, canon_off(row, cb + cc * nf + j, d.k1), cs);
-                    scale *= 2.f;
+                    const float s2 = 2.f * sn * cs, c2 = (cs - sn) * (cs + sn);
+                    sn = s2; cs = c2;
                 }
             }
             if (cg == 3)
@@ -523,6 +523,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3k_kernel(const __grid_
             unsigned char* xh = s_a + buf * CHUNK_PAIR;
             unsigned char* xl = xh + CHUNK_HALF;
             const int k0p = c * KC + cg * (KC / 4);
+            // a thread's pairs are consecutive frequencies of one channel most of the time: the next octave comes from
+            // the angle-doubling identities (sin 2a = 2 sin a cos a, cos 2a = cos^2 a - sin^2 a; <= 2^5 ulp after the
+            // five doublings of fea_pe = 6, i.e. ~2e-6) and sincosf is evaluated only at a thread's first pair or a
+            // channel's first frequency
+            int prev_ch = -1, prev_j = -1;
+            float sn = 0.f, cs = 0.f;
 #pragma unroll 2
             for (int e = 0; e < KC / 4; e += 2) {
                 const int kp = k0p + e;
@@ -535,7 +541,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3k_kernel(const __grid_
                     int ch = -1, j = 0;
                     if (q < kd.n_fpairs) { ch = q / d.fea_pe; j = q - ch * d.fea_pe; }
                     else if (q - kd.n_fpairs < kd.n_vpairs) { const int qv = q - kd.n_fpairs; ch = qv / d.view_pe; j = qv - ch * d.view_pe; ch += d.app_dim; }
-                    if (ch >= 0) sincosf(s_feat[row * 32 + ch] * (float)(1 << j), &v0, &v1);
+                    if (ch >= 0) {
+                        if (ch == prev_ch && j == prev_j + 1) {
+                            const float s2 = 2.f * sn * cs, c2 = (cs - sn) * (cs + sn);
+                            sn = s2; cs = c2;
+                        } else {
+                            sincosf(s_feat[row * 32 + ch] * (float)(1 << j), &sn, &cs);
+                        }
+                        prev_ch = ch; prev_j = j;
+                        v0 = sn; v1 = cs;
+                    }
                 }
                 split_store2(xh, xl, canon_off(row, kp - c * KC, KC), v0, v1);
             }
