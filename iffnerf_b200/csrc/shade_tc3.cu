@@ -197,19 +197,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3_kernel(const __grid_c
         }
         // ---- stage the ray_feat tile as split A operand (K0); W1 (hi|lo) is already in flight into the weight buffer
         const bool lit_row = live && __ldg(a.app_count + r) > 0;      // unlit rows are never written by the split march
-        for (int kc = cg; kc < d.k0 / 8; kc += 4) {
-            float v[8];
+        {   // all loads of the row first (one exposed DRAM round trip instead of one per 32-byte piece), then the stores
+            constexpr int MAXIT = 5;                       // k0 <= 144 + pad: at most 5 pieces of 8 columns per column group
+            float4 lo[MAXIT], hi[MAXIT];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-            if (lit_row && kc * 8 < d.ta) {
-                const float4 lo = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8));
-                v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
-                if (kc * 8 + 4 < d.ta) {
-                    const float4 hi = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8 + 4));
-                    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+            for (int it = 0; it < MAXIT; ++it) {
+                const int kc = cg + 4 * it;
+                lo[it] = hi[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lit_row && kc * 8 < d.ta) {
+                    lo[it] = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8));
+                    if (kc * 8 + 4 < d.ta) hi[it] = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8 + 4));
                 }
             }
-            split_store8(s_ah, s_al, canon_off(row, kc * 8, d.k0), v);
+#pragma unroll
+            for (int it = 0; it < MAXIT; ++it) {
+                const int kc = cg + 4 * it;
+                if (kc < d.k0 / 8) {
+                    const float v[8] = {lo[it].x, lo[it].y, lo[it].z, lo[it].w, hi[it].x, hi[it].y, hi[it].z, hi[it].w};
+                    split_store8(s_ah, s_al, canon_off(row, kc * 8, d.k0), v);
+                }
+            }
         }
         fence_async_smem();
         tc_fence_before();
@@ -478,19 +485,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) shade_tc3k_kernel(const __grid_
         }
         // ---- stage ray_feat as split A operand (K0)
         const bool lit_row = live && __ldg(a.app_count + r) > 0;
-        for (int kc = cg; kc < d.k0 / 8; kc += 4) {
-            float v[8];
+        {   // all loads of the row first (one exposed DRAM round trip instead of one per 32-byte piece), then the stores
+            constexpr int MAXIT = 5;                       // k0 <= 144 + pad: at most 5 pieces of 8 columns per column group
+            float4 lo[MAXIT], hi[MAXIT];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-            if (lit_row && kc * 8 < d.ta) {
-                const float4 lo = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8));
-                v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
-                if (kc * 8 + 4 < d.ta) {
-                    const float4 hi = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8 + 4));
-                    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+            for (int it = 0; it < MAXIT; ++it) {
+                const int kc = cg + 4 * it;
+                lo[it] = hi[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lit_row && kc * 8 < d.ta) {
+                    lo[it] = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8));
+                    if (kc * 8 + 4 < d.ta) hi[it] = __ldg(reinterpret_cast<const float4*>(a.ray_feat + r * d.ta + kc * 8 + 4));
                 }
             }
-            split_store8(s_a, s_a + a0_half, canon_off(row, kc * 8, d.k0), v);
+#pragma unroll
+            for (int it = 0; it < MAXIT; ++it) {
+                const int kc = cg + 4 * it;
+                if (kc < d.k0 / 8) {
+                    const float v[8] = {lo[it].x, lo[it].y, lo[it].z, lo[it].w, hi[it].x, hi[it].y, hi[it].z, hi[it].w};
+                    split_store8(s_a, s_a + a0_half, canon_off(row, kc * 8, d.k0), v);
+                }
+            }
         }
         fence_async_smem();
         tc_fence_before();
