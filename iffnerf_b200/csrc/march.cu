@@ -36,13 +36,17 @@ namespace {
 #ifndef TVM_EMIT_MIN_BLOCKS
 #define TVM_EMIT_MIN_BLOCKS 8           // sigma-march kernel of the split path: 64 registers, 32 warps / SM
 #endif
+#ifndef TVM_APP_WARPS
+#define TVM_APP_WARPS 8                 // gather kernel: 8 adjacent rays in flight per CTA share first-touch texel misses
+#endif
 #ifndef TVM_APP_MIN_BLOCKS
-#define TVM_APP_MIN_BLOCKS 4
+#define TVM_APP_MIN_BLOCKS 2            // x 8 warps = 16 warps / SM at 128 registers (measured: 2.64 -> 2.55 ms vs 4 x 4)
 #endif
 #ifndef TVM_APP_CARVEOUT
 #define TVM_APP_CARVEOUT 25
 #endif
 constexpr int MARCH_WARPS = TVM_MARCH_WARPS;
+constexpr int APP_WARPS = TVM_APP_WARPS;
 constexpr int MARCH_RAYS_PER_CTA = TVM_MARCH_RAYS_PER_CTA;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -325,13 +329,13 @@ struct AppArgs {
 };
 
 template <int G, int CA4, bool COUNT = false>
-__global__ void __launch_bounds__(MARCH_WARPS * 32, TVM_APP_MIN_BLOCKS) app_gather_kernel(const __grid_constant__ AppArgs a) {
+__global__ void __launch_bounds__(APP_WARPS * 32, TVM_APP_MIN_BLOCKS) app_gather_kernel(const __grid_constant__ AppArgs a) {
     __shared__ int s_next;
-    __shared__ float4 s_w[MARCH_WARPS][TVM_APP_CAP];
-    __shared__ unsigned s_i[MARCH_WARPS][TVM_APP_CAP];
+    __shared__ float4 s_w[APP_WARPS][TVM_APP_CAP];
+    __shared__ unsigned s_i[APP_WARPS][TVM_APP_CAP];
     const tvm_field_desc& f = a.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 3;
-    if (threadIdx.x == 0) s_next = MARCH_WARPS;
+    if (threadIdx.x == 0) s_next = APP_WARPS;
     __syncthreads();
     const long long base = (long long)blockIdx.x * a.rays_per_cta;
     int local = warp;
@@ -506,26 +510,26 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
         g.f = *desc; g.sec = a.sec; g.app_w = a.app_w; g.app_i = a.app_i; g.app_count = a.app_count;
         g.ray_feat = a.ray_feat; g.n_rays = n_rays; g.ta = a.ta;
         g.app_off[0] = a.app_off[0]; g.app_off[1] = a.app_off[1]; g.app_off[2] = a.app_off[2];
-        g.rays_per_cta = a.rays_per_cta;
+        g.rays_per_cta = a.rays_per_cta > APP_WARPS ? a.rays_per_cta : APP_WARPS;
         g.zero_unlit = (flags & TVM_F_ZERO_UNLIT) ? 1 : 0;
         const unsigned ctas = (unsigned)((n_rays + g.rays_per_cta - 1) / g.rays_per_cta);
         if (flags & TVM_F_COUNT_FETCH) {           // measurement: per-ray count of the 16-byte fetches -> app_count output
             if (!lego || !gather_only || !app_count) return TVM_E_MODE;
             g.fetch_count = app_count;
             carveout_done((const void*)app_gather_kernel<3, 12, true>, TVM_APP_CARVEOUT);
-            tvm_count_launch(); app_gather_kernel<3, 12, true><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+            tvm_count_launch(); app_gather_kernel<3, 12, true><<<ctas, APP_WARPS * 32, 0, st>>>(g);
         } else if (lego) {
             carveout_done((const void*)app_gather_kernel<3, 12>, TVM_APP_CARVEOUT);
-            tvm_count_launch(); app_gather_kernel<3, 12><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+            tvm_count_launch(); app_gather_kernel<3, 12><<<ctas, APP_WARPS * 32, 0, st>>>(g);
         } else if (gmax <= 1) {
             carveout_done((const void*)app_gather_kernel<1, 0>, TVM_APP_CARVEOUT);
-            tvm_count_launch(); app_gather_kernel<1, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+            tvm_count_launch(); app_gather_kernel<1, 0><<<ctas, APP_WARPS * 32, 0, st>>>(g);
         } else if (gmax == 2) {
             carveout_done((const void*)app_gather_kernel<2, 0>, TVM_APP_CARVEOUT);
-            tvm_count_launch(); app_gather_kernel<2, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+            tvm_count_launch(); app_gather_kernel<2, 0><<<ctas, APP_WARPS * 32, 0, st>>>(g);
         } else {
             carveout_done((const void*)app_gather_kernel<3, 0>, TVM_APP_CARVEOUT);
-            tvm_count_launch(); app_gather_kernel<3, 0><<<ctas, MARCH_WARPS * 32, 0, st>>>(g);
+            tvm_count_launch(); app_gather_kernel<3, 0><<<ctas, APP_WARPS * 32, 0, st>>>(g);
         }
         TVM_LAUNCH_CHECK();
         if (gather_only) return 0;
