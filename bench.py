@@ -717,7 +717,7 @@ def run_ours(args, rank, world, local_rank):
         fetched_bytes = 16.0 * fetched16 * per
         alg_app = 3456.0 * a_samples * per
         alg_sigma = (44.0 * n_global + 32.0 * v0 + 1152.0 * v) * per
-        list_bytes = 20.0 * a_samples * per
+        list_bytes = 8.0 * a_samples * per
         feat_bytes = 576.0 * lit * per
         factor_touch = 4.0 * model.packed_factors().numel() * 0.8
         l1_peak = gather_peak.get("l1_resident_64B_gbs") or None
@@ -729,7 +729,7 @@ def run_ours(args, rank, world, local_rank):
             "peak_source": "tvm_gather_microbench over an L1-resident 64 KB set, measured in this run (LDG.128 by quads, "
                            "8 texels per warp request)",
             "traffic": list_bytes + feat_bytes + factor_touch,
-            "traffic_source": "derived: appearance lists read (20 B/sample) + ray_feat rows written (576 B/lit ray) + "
+            "traffic_source": "derived: appearance lists read (8 B/sample) + ray_feat rows written (576 B/lit ray) + "
                               "first touch of the appearance factors (80 % of the 69.6 MB set); ncu dram__bytes of the "
                               "same launch is in profiles/",
             "ms_per_launch": ms_gather / K,

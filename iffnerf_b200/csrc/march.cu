@@ -77,8 +77,7 @@ struct MarchArgs {
     int rays_per_cta;
     TvmSections sec;
     // split path (TVM_F_SPLIT_APP): per-ray appearance sample lists, TVM_APP_CAP entries per ray
-    float4* app_w;          // (frac_x, frac_y, frac_z, weight)
-    unsigned* app_i;        // packed base texel indices (tvm_slot_from_idx)
+    float2* app_list;       // per entry: (sample index as int bits, weight) — 8 bytes; the gather re-derives the position
     int spill_cap;          // fused kernel as the overflow pass: only rays with app_count > spill_cap are marched (0 = all)
 };
 
@@ -89,7 +88,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // EMIT: split path, stage 1 — everything but the appearance gathers: samples with weight > rayMarch_weight_thres are
-// written to the ray's list (a.app_w / a.app_i) for app_gather_kernel instead of being gathered here, so the kernel
+// written to the ray's list (a.app_list: sample index + weight) for app_gather_kernel instead of being gathered here, so the kernel
 // carries no accumulator and runs at twice the occupancy of the fused one.
 // MODE 2: the fused kernel as the split path's overflow pass (only rays whose list overflowed are marched); a separate
 // instantiation because the fused kernel sits exactly at its 128-register budget.
@@ -232,13 +231,8 @@ march_fwd_kernel(const __grid_constant__ MarchArgs a) {
                     if (EMIT) {
                         if (amask) {
                             const int slot = n_app + __popc(amask & lt_mask);
-                            if (app && slot < TVM_APP_CAP) {
-                                float4 sw;
-                                unsigned si;
-                                tvm_slot_from_idx(f, n, w, sw, si);
-                                a.app_w[r * TVM_APP_CAP + slot] = sw;
-                                a.app_i[r * TVM_APP_CAP + slot] = si;
-                            }
+                            if (app && slot < TVM_APP_CAP)
+                                a.app_list[r * TVM_APP_CAP + slot] = make_float2(__int_as_float(i), w);
                             n_app += __popc(amask);
                         }
                     } else if (amask) {
@@ -316,8 +310,12 @@ march_fwd_kernel(const __grid_constant__ MarchArgs a) {
 struct AppArgs {
     tvm_field_desc f;
     TvmSections sec;
-    const float4* app_w;
-    const unsigned* app_i;
+    const float2* app_list;
+    const float* rays;          // the gather re-derives each listed sample's position exactly like the sigma-march
+    const float* jitter;
+    int ray_stride;
+    int S;
+    unsigned flags;
     const int* app_count;
     float* ray_feat;
     long long n_rays;
@@ -344,11 +342,24 @@ __global__ void __launch_bounds__(APP_WARPS * 32, TVM_APP_MIN_BLOCKS) app_gather
         if (r >= a.n_rays) break;
         const int n = __ldg(a.app_count + r);
         if (n > 0 && n <= TVM_APP_CAP) {
-            const float4* ew = a.app_w + r * TVM_APP_CAP;
-            const unsigned* ei = a.app_i + r * TVM_APP_CAP;
+            // stage the list: 8 bytes per entry (sample index, weight), streamed once; the sample position is re-derived
+            // with the sigma-march's own functions (bit-identical) and turned into base texel indices + fractions
+            TvmRay ray;
+            {
+                const float* rp = a.rays + r * a.ray_stride;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { ray.o[c] = __ldg(rp + c); ray.d[c] = __ldg(rp + 3 + c); }
+            }
+            tvm_init_ray(f, ray, a.jitter ? __ldg(a.jitter + r) : 0.f, a.S, (a.flags & TVM_F_POINT_SAMPLES) != 0);
+            const float2* el = a.app_list + r * TVM_APP_CAP;
             for (int t = lane; t < n; t += 32) {
-                s_w[warp][t] = __ldcs(ew + t);          // streamed once: do not displace the factor texels in L1
-                s_i[warp][t] = __ldcs(ei + t);
+                const float2 e = __ldcs(el + t);
+                float p[3], nrm[3];
+                tvm_sample_point(f, ray, tvm_sample_z(f, ray, __float_as_int(e.x)), p);
+                tvm_normalize(f, p, nrm);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) nrm[c] = tvm_unnormalize(nrm[c], f.grid[c]);
+                tvm_slot_from_idx(f, nrm, e.y, s_w[warp][t], s_i[warp][t]);
             }
             __syncwarp();
             const int R = (n + 7) >> 3, b = (lane >> 2) * R, e = min(b + R, n);      // quad q walks the q-th eighth of the list
@@ -496,8 +507,7 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
     bool split = (flags & TVM_F_SPLIT_APP) && !alpha && !z_vals && !dists && !valid_bits && ws_bytes >= ws_split.total;
     for (int k = 0; k < 3; ++k) split = split && desc->grid[k] <= TVM_PACKED_GRID_MAX;
     if (split) {
-        a.app_w = (float4*)(base + ws_split.app_w);
-        a.app_i = (unsigned*)(base + ws_split.app_i);
+        a.app_list = (float2*)(base + ws_split.app_list);
         // TVM_F_GATHER_ONLY (measurement): re-run only the appearance-gather stage on the lists already in the workspace
         const bool gather_only = (flags & TVM_F_GATHER_ONLY) != 0;
         if (!gather_only) {
@@ -507,7 +517,8 @@ int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t 
             a.rays_per_cta = pick_rays_per_cta(a.n_rays, MARCH_WARPS, MARCH_RAYS_PER_CTA);
         }
         AppArgs g{};
-        g.f = *desc; g.sec = a.sec; g.app_w = a.app_w; g.app_i = a.app_i; g.app_count = a.app_count;
+        g.f = *desc; g.sec = a.sec; g.app_list = a.app_list; g.app_count = a.app_count;
+        g.rays = rays; g.jitter = jitter; g.ray_stride = ray_stride; g.S = n_samples; g.flags = flags;
         g.ray_feat = a.ray_feat; g.n_rays = n_rays; g.ta = a.ta;
         g.app_off[0] = a.app_off[0]; g.app_off[1] = a.app_off[1]; g.app_off[2] = a.app_off[2];
         g.rays_per_cta = a.rays_per_cta > APP_WARPS ? a.rays_per_cta : APP_WARPS;

@@ -94,9 +94,9 @@ static inline size_t tvm_align(size_t v, size_t a = 256) { return (v + a - 1) / 
 //   ray_feat [n][TA] f32 | acc [n] f32 | depth [n] f32 | sigma_count [n] i32 (density samples evaluated)
 //   | app_count [n] i32 (appearance samples evaluated) | occ_count [n] i32 (occupancy tests = in-aabb samples visited)
 //   with TVM_F_SPLIT_APP additionally (at the end, so the common offsets do not move):
-//   | app_w [n][TVM_APP_CAP] float4 | app_i [n][TVM_APP_CAP] u32   (per-ray appearance sample lists)
+//   | app_list [n][TVM_APP_CAP] (int sample index, float weight)   (per-ray appearance sample lists, 8 B per entry)
 struct TvmWorkspace {
-    size_t ray_feat, acc, depth, sigma_count, app_count, occ_count, app_w, app_i, total;
+    size_t ray_feat, acc, depth, sigma_count, app_count, occ_count, app_list, total;
 };
 static inline TvmWorkspace tvm_ws_layout(const tvm_field_desc* d, int64_t n, uint32_t flags = 0) {
     TvmWorkspace w;
@@ -107,11 +107,8 @@ static inline TvmWorkspace tvm_ws_layout(const tvm_field_desc* d, int64_t n, uin
     w.sigma_count = off; off = tvm_align(off + (size_t)n * sizeof(int32_t));
     w.app_count = off;   off = tvm_align(off + (size_t)n * sizeof(int32_t));
     w.occ_count = off;   off = tvm_align(off + (size_t)n * sizeof(int32_t));
-    w.app_w = w.app_i = off;
-    if (flags & TVM_F_SPLIT_APP) {
-        w.app_w = off;   off = tvm_align(off + (size_t)n * TVM_APP_CAP * 4 * sizeof(float));
-        w.app_i = off;   off = tvm_align(off + (size_t)n * TVM_APP_CAP * sizeof(uint32_t));
-    }
+    w.app_list = off;
+    if (flags & TVM_F_SPLIT_APP) off = tvm_align(off + (size_t)n * TVM_APP_CAP * 2 * sizeof(float));
     w.total = off;
     return w;
 }
