@@ -458,14 +458,10 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
                 return None
             h.m[:h.n_pairs] = ml[0].tolist()
             h.l[:h.n_pairs] = ml[1].tolist()
-            pre, bias = 1.0, 0.0
-            for mod in rm.specular_mlp[1:]:
-                if type(mod).__name__ == "_Scale":
-                    pre = float(mod.value)
-                elif type(mod).__name__ == "_Shift":
-                    bias = float(mod.value)
+            pre = rm.rgb_premultiplier if abs(rm.rgb_premultiplier - 1.0) > 1e-7 else 1.0
+            bias = rm.rgb_bias if rm.rgb_bias > 1e-7 else 0.0
             h.rgb_premultiplier, h.rgb_bias, h.rgb_padding = pre, bias, float(rm.rgb_padding)
-            h.diffuse_shift, h.rough_shift = float(rm.diffuse_color_mlp[1].value), float(rm.roughness_mlp[1].value)
+            h.diffuse_shift, h.rough_shift = float(rm.diffuse_shift), float(rm.rough_shift)
             lib = _lib.load()
             offs = (C.c_int32 * 8)()
             _lib.check(lib.tvm_ref_head_layout(C.byref(h), offs), "tvm_ref_head_layout")
