@@ -757,7 +757,13 @@ def run_ours(args, rank, world, local_rank):
                     "units_per_launch": {"rays": n_global * per, "occupancy_tests": v0 * per, "sigma_samples": v * per},
                     "note": "includes the ~8 us overflow pass; time = march - gather-only"},
                 "march_total": {"ms_per_launch": ms_march / K,
+                                "algorithmic_bytes_per_launch": alg_sigma + alg_app,
                                 "algorithmic_gbs": (alg_sigma + alg_app) / (ms_march / K / 1e3) / 1e9,
+                                "frac_of_l1_gather_algorithmic": ((alg_sigma + alg_app) / (ms_march / K / 1e3) / 1e9
+                                                                  / l1_peak) if l1_peak else None,
+                                "note": "SURVEY 8d bytes of the whole march / its device time against the measured "
+                                        "L1 gather ceiling (round 1: 0.74); the gather kernel's own `frac` above "
+                                        "counts only the bytes it still fetches",
                                 "frac_of_hbm_algorithmic": (alg_sigma + alg_app) / (ms_march / K / 1e3) / 1e9 / hbm_peak}}}
         line = {"metric": METRIC, "value": n_global * K / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world,
                 "steps": K, "warmup": args.warmup, "ms_per_step": ms_dev / K, "higher_is_better": True,
