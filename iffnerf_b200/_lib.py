@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_B200_LIB lets the tuning scripts load a differently-compiled build of the SAME sources
 LIB_PATH = os.environ.get("TVM_B200_LIB") or os.path.join(_HERE, "libtvm_b200.so")
 
-ABI_VERSION = 12
+ABI_VERSION = 11
 
 F_EARLY_TERM = 1 << 0
 F_MLP_BF16 = 1 << 1
@@ -25,7 +25,6 @@ F_MASK_ANYWHERE = 1 << 7
 F_GATHER_ONLY = 1 << 8
 F_COUNT_FETCH = 1 << 9
 F_BWD_RUNS = 1 << 10
-F_BWD_SPLIT = 1 << 11
 
 _f3 = C.c_float * 3
 _f6 = C.c_float * 6

@@ -64,19 +64,6 @@ def _mlp_params(model):
     return [mods[0].weight, mods[0].bias, mods[1].weight, mods[1].bias, mods[2].weight, mods[2].bias]
 
 
-def _bwd_ws_flags(model, factors):
-    """Workspace flavour of a differentiable forward: the split backward (csrc/march_bwd.cu, TVM_F_BWD_SPLIT) keeps its
-    per-ray appearance lists in the forward workspace, so that is sized with the list section when factor gradients
-    may be asked for."""
-    if getattr(model, "bwd_split", False) and any(p.requires_grad for p in factors):
-        return _lib.F_SPLIT_APP
-    return 0
-
-
-def _bwd_split_flag(model, want_factors, want_rays):
-    return _lib.F_BWD_SPLIT if (getattr(model, "bwd_split", False) and want_factors and not want_rays) else 0
-
-
 class _Render(torch.autograd.Function):
     """inputs: model, rays, S, jitter, bg, flags, 12 factors, basis, w1, b1, w2, b2, w3, b3.
     flags & F_EARLY_TERM: the caller does not want the per-sample outputs (alpha / z_vals / dists come back as None),
@@ -92,8 +79,7 @@ class _Render(torch.autograd.Function):
         d, keep = model.field_desc()
         lib = _lib.load()
         need = C.c_size_t(0)
-        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, _bwd_ws_flags(model, params[:12]), C.byref(need)),
-                   "tvm_workspace_bytes")
+        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need)), "tvm_workspace_bytes")
         ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
         rgb = torch.empty((n, 3), device=dev)
         depth = torch.empty((n,), device=dev)
@@ -152,8 +138,7 @@ class _Render(torch.autograd.Function):
         g_packed = ws_f if want_factors else None
         g_rays6 = torch.zeros((n, 6), device=dev) if want_rays else None
         _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], ctx.S, _lib.ptr(ctx.jit),
-                                     ctx.flags | _bwd_split_flag(model, want_factors, want_rays),
-                                     _lib.ptr(d_feat), _lib.ptr(d_acc), _lib.ptr(g_alpha), _lib.ptr(g_packed),
+                                     ctx.flags, _lib.ptr(d_feat), _lib.ptr(d_acc), _lib.ptr(g_alpha), _lib.ptr(g_packed),
                                      _lib.ptr(g_rays6), _lib.ptr(ctx.ws), ctx.ws.numel(), st), "tvm_march_bwd")
         scale = 1.0
         sync = getattr(model, "grad_sync", None)
@@ -226,8 +211,7 @@ class _March(torch.autograd.Function):
         d, keep = model.field_desc()
         lib = _lib.load()
         need = C.c_size_t(0)
-        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, _bwd_ws_flags(model, factors), C.byref(need)),
-                   "tvm_workspace_bytes")
+        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need)), "tvm_workspace_bytes")
         ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
         want_samples = not (flags & _lib.F_EARLY_TERM)     # without per-sample outputs both directions terminate early
         alpha, z, dists = (torch.empty((n, S), device=dev) for _ in range(3)) if want_samples else (None, None, None)
@@ -262,8 +246,7 @@ class _March(torch.autograd.Function):
         g_packed = torch.zeros(int(d.n_factor_floats), device=dev) if want_factors else None
         g_rays = torch.zeros((n, 6), device=dev) if want_rays else None
         _lib.check(lib.tvm_march_bwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], ctx.S, _lib.ptr(ctx.jit),
-                                     ctx.flags | _bwd_split_flag(model, want_factors, want_rays),
-                                     _lib.ptr(_c(g_feat)), _lib.ptr(_c(g_acc)), _lib.ptr(_c(g_alpha)),
+                                     ctx.flags, _lib.ptr(_c(g_feat)), _lib.ptr(_c(g_acc)), _lib.ptr(_c(g_alpha)),
                                      _lib.ptr(g_packed), _lib.ptr(g_rays), _lib.ptr(ctx.ws), ctx.ws.numel(),
                                      _stream(dev)), "tvm_march_bwd")
         grads = [None] * 12

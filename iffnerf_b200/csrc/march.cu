@@ -474,29 +474,6 @@ extern "C" int tvm_sample_mask(const tvm_field_desc* desc, const float* rays, in
     return launch(march_fwd_kernel<1, true, 0, 0, 0>, a, (cudaStream_t)stream);
 }
 
-// Split backward (march_bwd.cu), stage 1: re-run the sigma-march over the forward's workspace so that it holds the
-// per-ray appearance lists (sample index, weight) — acc / depth / counts are rewritten with the values the forward
-// computed (same kernel family, same arithmetic); ray_feat is not touched.
-int tvm_emit_lists_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,
-                          const float* jitter, uint32_t flags, void* ws, size_t ws_bytes, cudaStream_t st) {
-    MarchArgs a;
-    int rc = fill_args(a, desc, rays, n_rays, ray_stride, n_samples, jitter);
-    if (rc) return rc;
-    const TvmWorkspace w = tvm_ws_layout(desc, n_rays, TVM_F_SPLIT_APP);
-    if (ws_bytes < w.total) return TVM_E_WORKSPACE;
-    char* base = (char*)ws;
-    a.flags = flags;
-    a.acc = (float*)(base + w.acc);
-    a.depth = (float*)(base + w.depth);
-    a.sigma_count = (int*)(base + w.sigma_count);
-    a.app_count = (int*)(base + w.app_count);
-    a.occ_count = (int*)(base + w.occ_count);
-    a.app_list = (float2*)(base + w.app_list);
-    bool lego = true;
-    for (int k = 0; k < 3; ++k) lego = lego && desc->n_sigma[k] == 16 && desc->n_app[k] == 48;
-    return lego ? launch(march_fwd_kernel<1, false, 4, 12, 1>, a, st) : launch(march_fwd_kernel<1, false, 0, 0, 1>, a, st);
-}
-
 // march stage of tvm_render_fwd (shade.cu finishes the job)
 int tvm_march_fwd_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,
                          const float* jitter, uint32_t flags, float* alpha, float* z_vals, float* dists,

@@ -30,21 +30,6 @@ namespace {
 #ifndef TVM_BWD_WARPS
 #define TVM_BWD_WARPS 4
 #endif
-#ifndef TVM_BWD_REUSE
-#define TVM_BWD_REUSE 0
-#endif
-#ifndef TVM_BWD_PREFETCH
-#define TVM_BWD_PREFETCH 0            // training instantiations: L1 prefetch of a sample's texels (1 density, 2 appearance)
-#endif
-#ifndef TVM_BWD_MIN_BLOCKS_LISTS
-#define TVM_BWD_MIN_BLOCKS_LISTS 5   // split backward, sigma stage (no appearance code)
-#endif
-#ifndef TVM_APPB_WARPS
-#define TVM_APPB_WARPS 4
-#endif
-#ifndef TVM_APPB_MIN_BLOCKS
-#define TVM_APPB_MIN_BLOCKS 5
-#endif
 constexpr int BWD_WARPS = TVM_BWD_WARPS;
 constexpr int BWD_RAYS_PER_CTA = 16;
 constexpr unsigned FULL = 0xffffffffu;
@@ -68,10 +53,6 @@ struct BwdArgs {
     int app_off[3];
     int rays_per_cta;
     TvmSections sec;
-    // split backward (TVM_F_BWD_SPLIT): per-ray appearance lists in the workspace (written by the sigma-march, see
-    // tvm_emit_lists_launch) — app_bwd_kernel replaces each entry's weight by c_i = gF . phi_i
-    float2* app_list;
-    const int* app_count;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -85,14 +66,9 @@ __device__ __forceinline__ float quad_sum(float v) {
     return v;
 }
 
-// MODE 0: everything in one kernel.  MODE 1 (split backward, stage 3): the appearance part was done by app_bwd_kernel —
-// c_i of every appearance sample is read from the ray's list; rays whose list overflowed are skipped.  MODE 2: MODE 0
-// restricted to the rays whose list overflowed (one wave of CTAs; almost always nothing to do).
-template <int G, bool SCATTER, bool POSE, int CS4, int CA4, int MODE = 0>
-__global__ void __launch_bounds__(BWD_WARPS * 32, MODE == 1 ? TVM_BWD_MIN_BLOCKS_LISTS
-                                                             : (SCATTER ? TVM_BWD_MIN_BLOCKS : TVM_BWD_MIN_BLOCKS_POSE))
+template <int G, bool SCATTER, bool POSE, int CS4, int CA4>
+__global__ void __launch_bounds__(BWD_WARPS * 32, SCATTER ? TVM_BWD_MIN_BLOCKS : TVM_BWD_MIN_BLOCKS_POSE)
 march_bwd_kernel(const __grid_constant__ BwdArgs a) {
-    constexpr bool LISTS = MODE == 1, SPILL = MODE == 2;
     __shared__ int s_next;
     __shared__ float4 s_slot[BWD_WARPS][32];
     __shared__ float s_ret[BWD_WARPS][32];
@@ -102,11 +78,7 @@ march_bwd_kernel(const __grid_constant__ BwdArgs a) {
     // per-(sample, plane) tap records, the upstream scalar of each compacted sample, the per-lane shares of gF . phi.
     // Measured (65 536 rays): L2 reduction traffic -60 % (lts 56 % -> 21 %) but +71 % instructions; the kernel is
     // latency-bound at 12 warps/SM, not L2-bound, so it is slower (5.18 vs 3.74 ms) and stays opt-in.
-    constexpr bool RUNS = SCATTER && !POSE && MODE == 0;
-    // training instantiations: the density scatter re-uses the recompute pass's interpolated plane / line slices
-    // (tvm_gather.cuh::density_partial_keep) from dynamic shared memory instead of gathering them again
-    constexpr bool REUSE = SCATTER && !POSE && TVM_BWD_REUSE;
-    extern __shared__ float4 s_dyn[];
+    constexpr bool RUNS = SCATTER && !POSE;
     __shared__ CellTaps s_cell[RUNS ? BWD_WARPS : 1][RUNS ? 32 * 3 : 1];
     __shared__ float s_wt[RUNS ? BWD_WARPS : 1][32];
     __shared__ __align__(16) float s_part[RUNS ? BWD_WARPS : 1][RUNS ? 128 : 4];
@@ -119,28 +91,12 @@ march_bwd_kernel(const __grid_constant__ BwdArgs a) {
     if (threadIdx.x == 0) s_next = BWD_WARPS;
     __syncthreads();
     const long long base = (long long)blockIdx.x * a.rays_per_cta;
-    if (SPILL) {
-        bool over = false;
-        for (int i = threadIdx.x; i < a.rays_per_cta; i += BWD_WARPS * 32)
-            over = over || (base + i < a.n_rays && __ldg(a.app_count + base + i) > TVM_APP_CAP);
-        if (!__syncthreads_or(over)) return;
-    }
     const int S = a.S;
     int local = warp;
 
     while (local < a.rays_per_cta) {
         const long long r = base + local;
         if (r >= a.n_rays) break;
-        int n_list = 0, cur = 0;
-        if (LISTS || SPILL) {
-            n_list = __ldg(a.app_count + r);
-            if (LISTS ? n_list > TVM_APP_CAP : n_list <= TVM_APP_CAP) {
-                int nx = 0;
-                if (lane == 0) nx = atomicAdd(&s_next, 1);
-                local = __shfl_sync(FULL, nx, 0);
-                continue;
-            }
-        }
         TvmRay ray;
         {
             const float* rp = a.rays + r * a.ray_stride;
@@ -189,8 +145,6 @@ march_bwd_kernel(const __grid_constant__ BwdArgs a) {
             if (vmask) {
                 float n[3];
                 tvm_normalize(f, p, n);
-                if (SCATTER && !POSE && (TVM_BWD_PREFETCH & 1) && keep)
-                    vm_prefetch<CS4>(f, n, f.n_sigma, f.dplane_off, f.dline_off);
                 const float zn = tvm_sample_z(f, ray, i + 1);
                 const float dist = (i < S - 1) ? rn_sub(zn, z) : 0.f;
                 const float delta = rn_mul(dist, f.distance_scale);
@@ -209,7 +163,6 @@ march_bwd_kernel(const __grid_constant__ BwdArgs a) {
                         // the upstream scalar, so it is taken here, on the texels this pass loads anyway, and the
                         // second density pass below disappears
                         if (POSE && !SCATTER) part = density_bwd<false, true, CS4>(f, q, 1.0f, sub, nullptr, dq);
-                        else if (REUSE) part = density_partial_keep<CS4>(f, q, sub, s_dyn + warp * TVM_KEEP_F4_PER_WARP + ci * 4 + sub);
                         else part = density_partial<CS4>(f, q, sub);
                     }
                     part = quad_sum(part);
@@ -238,28 +191,8 @@ march_bwd_kernel(const __grid_constant__ BwdArgs a) {
                 T *= __shfl_sync(FULL, incl, 31);
                 // ---- appearance: c_i = g_acc + gF . phi_i, scatter w_i * gF into the app factors
                 float c = g_acc;
-                if (LISTS) {
-                    // the list's entries of this block (sorted by sample index): entry -> lane of its sample
-                    if (cur < n_list) {
-                        const int t = cur + lane;
-                        int ie = 0x7fffffff;
-                        float ce = 0.f;
-                        if (t < n_list) {
-                            const float2 e = __ldcs(a.app_list + r * TVM_APP_CAP + t);
-                            ie = __float_as_int(e.x);
-                            ce = e.y;
-                        }
-                        const bool mine = ie < i0 + 32;
-                        const unsigned lmask = __reduce_or_sync(FULL, mine ? 1u << (ie - i0) : 0u);
-                        const float cs = __shfl_sync(FULL, ce, __popc(lmask & lt_mask));
-                        if ((lmask >> lane) & 1u) c += cs;
-                        cur += __popc(lmask);
-                    }
-                }
-                const bool app = !LISTS && keep && (w > f.weight_thres);
+                const bool app = keep && (w > f.weight_thres);
                 const unsigned amask = __ballot_sync(FULL, app);
-                if (SCATTER && !POSE && (TVM_BWD_PREFETCH & 2) && app && a.d_ray_feat)
-                    vm_prefetch<CA4>(f, n, f.n_app, f.aplane_off, f.aline_off);
                 if (RUNS && runs && amask && a.d_ray_feat) {
                     // quad q walks the contiguous run q of the block's appearance samples, one (plane, slice) at a time,
                     // with the pending corner / tap gradients in registers
@@ -385,10 +318,7 @@ march_bwd_kernel(const __grid_constant__ BwdArgs a) {
                 } else if (dmask) {
                     const int nd = __popc(dmask), rankd = __popc(dmask & lt_mask);
                     __syncwarp();
-                    if (live) {
-                        s_slot[warp][rankd] = make_float4(n[0], n[1], n[2], dfeat);
-                        s_z[warp][rankd] = REUSE ? __int_as_float(rank) : z;       // REUSE: slot of the kept slices
-                    }
+                    if (live) { s_slot[warp][rankd] = make_float4(n[0], n[1], n[2], dfeat); s_z[warp][rankd] = z; }
                     __syncwarp();
                     for (int g = 0; g * 8 < nd; ++g) {
                         const int ci = g * 8 + quad;
@@ -396,11 +326,7 @@ march_bwd_kernel(const __grid_constant__ BwdArgs a) {
                         if (ci < nd) {
                             const float4 s = s_slot[warp][ci];
                             const float q[3] = {s.x, s.y, s.z};
-                            if (REUSE)
-                                density_scatter_kept<CS4>(f, q, s.w, sub, a.g_factors, s_dyn + warp * TVM_KEEP_F4_PER_WARP +
-                                                                                          __float_as_int(s_z[warp][ci]) * 4 + sub);
-                            else
-                                density_bwd<SCATTER, POSE, CS4>(f, q, s.w, sub, a.g_factors, dn);
+                            density_bwd<SCATTER, POSE, CS4>(f, q, s.w, sub, a.g_factors, dn);
                         }
                         if (POSE) {
 #pragma unroll
@@ -456,105 +382,12 @@ march_bwd_kernel(const __grid_constant__ BwdArgs a) {
     }
 }
 
-
-// Split backward, stage 2 — the appearance part of the backward for every listed sample: gather the sample's plane /
-// line texels, scatter w_i * gF into the appearance factor gradients (red.global.add.v4.f32) and replace the entry's
-// weight by c_i = gF . phi_i, which the sigma stage (march_bwd_kernel MODE 1) needs for dL/dalpha.  Neither depends on
-// dL/dalpha, so this runs as its own kernel: one warp per ray, one quad per listed sample, no compositing state.
-constexpr int APPB_WARPS = TVM_APPB_WARPS;
-
-template <int G, int CA4>
-__global__ void __launch_bounds__(APPB_WARPS * 32, TVM_APPB_MIN_BLOCKS) app_bwd_kernel(const __grid_constant__ BwdArgs a) {
-    __shared__ int s_next;
-    __shared__ float4 s_e[APPB_WARPS][TVM_APP_CAP];
-    const tvm_field_desc& f = a.f;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane & 3, quad = lane >> 2;
-    if (threadIdx.x == 0) s_next = APPB_WARPS;
-    __syncthreads();
-    const long long base = (long long)blockIdx.x * a.rays_per_cta;
-    int local = warp;
-    while (local < a.rays_per_cta) {
-        const long long r = base + local;
-        if (r >= a.n_rays) break;
-        const int n = __ldg(a.app_count + r);
-        if (n > 0 && n <= TVM_APP_CAP) {
-            TvmRay ray;
-            {
-                const float* rp = a.rays + r * a.ray_stride;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) { ray.o[c] = __ldg(rp + c); ray.d[c] = __ldg(rp + 3 + c); }
-            }
-            tvm_init_ray(f, ray, a.jitter ? __ldg(a.jitter + r) : 0.f, a.S, (a.flags & TVM_F_POINT_SAMPLES) != 0);
-            float2* el = a.app_list + r * TVM_APP_CAP;
-            for (int t = lane; t < n; t += 32) {
-                const float2 e = el[t];
-                float p[3], nrm[3];
-                tvm_sample_point(f, ray, tvm_sample_z(f, ray, __float_as_int(e.x)), p);
-                tvm_normalize(f, p, nrm);
-                s_e[warp][t] = make_float4(nrm[0], nrm[1], nrm[2], e.y);
-            }
-            __syncwarp();
-            const float* gRow = a.d_ray_feat + r * a.ta;
-            for (int g = 0; g * 8 < n; ++g) {
-                const int ci = g * 8 + quad;
-                float dot = 0.f;
-                float dn[3] = {0.f, 0.f, 0.f};
-                if (ci < n) {
-                    const float4 s = s_e[warp][ci];
-                    const float q[3] = {s.x, s.y, s.z};
-                    dot = app_bwd_rolled<G, true, false, CA4>(f, q, s.w, sub, gRow, a.app_off, a.g_factors, dn);
-                }
-                dot = quad_sum(dot);
-                if (sub == 0 && ci < n) el[ci].y = dot;
-            }
-            __syncwarp();
-        }
-        int nxt = 0;
-        if (lane == 0) nxt = atomicAdd(&s_next, 1);
-        local = __shfl_sync(FULL, nxt, 0);
-    }
-}
-
-// launch of a training instantiation (scatter, no pose): dynamic shared memory for the kept density slices
-constexpr size_t BWD_KEEP_BYTES = TVM_BWD_REUSE ? (size_t)BWD_WARPS * TVM_KEEP_F4_PER_WARP * sizeof(float4) : 0;
-template <int G, int CS4, int CA4, int MODE>
-int launch_train(const BwdArgs& a, long long ctas, cudaStream_t st) {
-    static TvmDevMemo memo;
-    auto kernel = march_bwd_kernel<G, true, false, CS4, CA4, MODE>;
-    if (BWD_KEEP_BYTES) {
-        const int rc = tvm_ensure_dyn_smem(kernel, BWD_KEEP_BYTES, memo);
-        if (rc) return rc;
-    }
-    tvm_count_launch(); kernel<<<(unsigned)ctas, BWD_WARPS * 32, BWD_KEEP_BYTES, st>>>(a);
-    TVM_LAUNCH_CHECK();
-    return 0;
-}
-
 template <int G, int CS4, int CA4>
-int dispatch_split(BwdArgs& a, cudaStream_t st) {
-    // stage 2: appearance (8 warps' worth of rays per CTA at least)
-    BwdArgs g = a;
-    const long long ctas = (a.n_rays + a.rays_per_cta - 1) / a.rays_per_cta;
-    tvm_count_launch(); app_bwd_kernel<G, CA4><<<(unsigned)ctas, APPB_WARPS * 32, 0, st>>>(g);
-    TVM_LAUNCH_CHECK();
-    // stage 3: sigma re-march with c_i from the lists
-    int rc = launch_train<G, CS4, CA4, 1>(a, ctas, st);
-    if (rc) return rc;
-    // rays whose list overflowed: the fused kernel, one resident wave scanning long ray ranges
-    BwdArgs o = a;
-    const long long per = (a.n_rays + TVM_SM_COUNT * TVM_BWD_MIN_BLOCKS - 1) / (TVM_SM_COUNT * TVM_BWD_MIN_BLOCKS);
-    if (per > o.rays_per_cta) o.rays_per_cta = (int)(per > (1 << 20) ? (1 << 20) : per);
-    const long long octas = (a.n_rays + o.rays_per_cta - 1) / o.rays_per_cta;
-    return launch_train<G, CS4, CA4, 2>(o, octas, st);
-}
-
-template <int G, int CS4, int CA4>
-int dispatch(BwdArgs& a, cudaStream_t st) {
-    if (a.app_list) return dispatch_split<G, CS4, CA4>(a, st);
+int dispatch(const BwdArgs& a, cudaStream_t st) {
     const long long ctas = (a.n_rays + a.rays_per_cta - 1) / a.rays_per_cta;
     const bool scatter = a.g_factors != nullptr, pose = a.g_rays != nullptr;
     if (scatter && pose) { tvm_count_launch(); march_bwd_kernel<G, true, true, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a); }
-    else if (scatter) return launch_train<G, CS4, CA4, 0>(a, ctas, st);
+    else if (scatter) { tvm_count_launch(); march_bwd_kernel<G, true, false, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a); }
     else if (pose) { tvm_count_launch(); march_bwd_kernel<G, false, true, CS4, CA4><<<(unsigned)ctas, BWD_WARPS * 32, 0, st>>>(a); }
     TVM_LAUNCH_CHECK();
     return 0;
@@ -565,7 +398,7 @@ int dispatch(BwdArgs& a, cudaStream_t st) {
 extern "C" int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride,
                              int n_samples, const float* jitter, uint32_t flags, const float* d_ray_feat,
                              const float* d_acc, const float* d_alpha, float* g_factors, float* g_rays,
-                             void* ws, size_t ws_bytes, void* stream) {
+                             const void* ws, size_t ws_bytes, void* stream) {
     int rc = tvm_check_desc(desc);
     if (rc) return rc;
     if (ray_stride < 6 || n_samples <= 0 || n_samples > 32 * TVM_MAX_BLOCKS || n_rays < 0) return TVM_E_SHAPE;
@@ -594,19 +427,6 @@ extern "C" int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int6
     int gmax = 0;
     for (int k = 0; k < 3; ++k) gmax = max(gmax, (desc->n_app[k] + 15) / 16);
     cudaStream_t st = (cudaStream_t)stream;
-    // split backward (training scatter without pose gradients): sigma-march emits the appearance lists into the
-    // workspace, app_bwd_kernel does the appearance gathers + scatter, the sigma stage re-marches with c_i from the lists
-    const TvmWorkspace wsp = tvm_ws_layout(desc, n_rays, TVM_F_SPLIT_APP);
-    bool split = (flags & TVM_F_BWD_SPLIT) && g_factors && !g_rays && d_ray_feat && ws_bytes >= wsp.total &&
-                 !(flags & (TVM_F_BWD_RUNS | TVM_F_POINT_SAMPLES));
-    if (split) {
-        const bool early = (flags & TVM_F_EARLY_TERM) && !d_alpha;
-        rc = tvm_emit_lists_launch(desc, rays, n_rays, ray_stride, n_samples, jitter,
-                                   early ? TVM_F_EARLY_TERM : 0u, ws, ws_bytes, st);
-        if (rc) return rc;
-        a.app_list = (float2*)((char*)ws + wsp.app_list);
-        a.app_count = (const int*)((const char*)ws + wsp.app_count);
-    }
     bool lego = true;
     for (int k = 0; k < 3; ++k) lego = lego && desc->n_sigma[k] == 16 && desc->n_app[k] == 48;
     if (lego) return dispatch<3, 4, 12>(a, st);

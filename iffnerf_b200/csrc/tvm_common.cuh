@@ -150,8 +150,3 @@ static inline int tvm_check_desc(const tvm_field_desc* d) {
     if (d->act != 0 && d->act != 1) return TVM_E_MODE;
     return 0;
 }
-
-// march.cu: the sigma-march of the split path as a stand-alone stage (split backward): fills the workspace's per-ray
-// appearance lists and counts
-int tvm_emit_lists_launch(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,
-                          const float* jitter, uint32_t flags, void* ws, size_t ws_bytes, cudaStream_t st);

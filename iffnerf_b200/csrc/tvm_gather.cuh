@@ -473,92 +473,6 @@ TVM_HD float density_bwd(const tvm_field_desc& f, const float n[3], float dfeat,
     return tot;
 }
 
-// L1 prefetch of the texels one sample will gather (training backward): issued by the lane that owns the sample right
-// after its position is known, so that the quad passes that follow — one L2 round trip per pass for density, nine per
-// pass for appearance when the rays of a batch are random and nothing is L1-resident — find the lines on their way.
-// Fire-and-forget (CCTL.E.PF1): no destination register, no scoreboard.
-TVM_HD void tvm_prefetch_l1(const void* p) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-#else
-    (void)p;
-#endif
-}
-// two adjacent texels of C4 float4s each starting at p (a plane row pair or a line tap pair)
-TVM_HD void tvm_prefetch_pair(const float4* p, int C4) {
-    for (int o = 0; o < 2 * C4 - 1; o += 8) tvm_prefetch_l1(p + o);
-    tvm_prefetch_l1(p + 2 * C4 - 1);
-}
-template <int CN4 = 0>
-TVM_HD void vm_prefetch(const tvm_field_desc& f, const float n[3], const int (&n_comp)[3], const int64_t (&plane_off)[3],
-                        const int64_t (&line_off)[3]) {
-    const float4* F4 = reinterpret_cast<const float4*>(f.factors);
-    const SampleTaps st = make_sample_taps(f, n);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int C4 = CN4 > 0 ? CN4 : (n_comp[k] >> 2);
-        const PlaneTaps t = make_taps(f, st, k, C4);
-        const float4* r0 = F4 + (t.pbase + (unsigned)(plane_off[k] >> 2));
-        tvm_prefetch_pair(r0, C4);
-        tvm_prefetch_pair(r0 + t.prow, C4);
-        tvm_prefetch_pair(F4 + (t.lbase + (unsigned)(line_off[k] >> 2)), C4);
-    }
-}
-
-// Training backward, density part without a second gather: the recompute pass keeps this lane's interpolated plane and
-// line slices of every sample in shared memory (layout [k][plane|line][sample 0..31][slice 0..3], float4), and the
-// scatter pass — which runs after the compositing scan produced dL/dfeat — forms its six reductions per plane from
-// them.  With the random rays of a training batch the factor gathers are served by L2 (L1 hit rate ~25 %), so this
-// removes a third of the kernel's L2 loads and one L2 round trip from every block's dependency chain.
-constexpr int TVM_KEEP_STRIDE = 32 * 4;          // float4s between consecutive [k][plane|line] sections
-constexpr int TVM_KEEP_F4_PER_WARP = 3 * 2 * TVM_KEEP_STRIDE;
-template <int CS4 = 0>
-TVM_HD float density_partial_keep(const tvm_field_desc& f, const float n[3], int sub, float4* __restrict__ kept) {
-    float tot = 0.f;
-    const float4* F4 = reinterpret_cast<const float4*>(f.factors);
-    const SampleTaps st = make_sample_taps(f, n);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int C4 = CS4 > 0 ? CS4 : (f.n_sigma[k] >> 2);
-        if (sub < C4) {
-            const PlaneTaps t = make_taps(f, st, k, C4);
-            const unsigned po = (unsigned)(f.dplane_off[k] >> 2) + (unsigned)sub, lo = (unsigned)(f.dline_off[k] >> 2) + (unsigned)sub;
-            const float4 pl = vm_plane(F4 + (t.pbase + po), F4 + (t.pbase + t.prow + po), t, C4, 0);
-            const float4 ln = vm_line(F4 + (t.lbase + lo), t.lw0, t.lw1, C4, 0);
-            kept[(2 * k) * TVM_KEEP_STRIDE] = pl;
-            kept[(2 * k + 1) * TVM_KEEP_STRIDE] = ln;
-            const float4 v = f4_mul(pl, ln);
-            const float sm = (v.x + v.y) + (v.z + v.w);
-            tot = (k == 0) ? sm : tot + sm;
-        }
-    }
-    return tot;
-}
-template <int CS4 = 0>
-TVM_HD void density_scatter_kept(const tvm_field_desc& f, const float n[3], float dfeat, int sub, float* gbuf,
-                                 const float4* __restrict__ kept) {
-    float4* G4 = reinterpret_cast<float4*>(gbuf);
-    const SampleTaps st = make_sample_taps(f, n);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int C4 = CS4 > 0 ? CS4 : (f.n_sigma[k] >> 2);
-        if (sub < C4) {
-            const PlaneTaps t = make_taps(f, st, k, C4);
-            const float4 up_ln = f4_scale(dfeat, kept[(2 * k + 1) * TVM_KEEP_STRIDE]);      // d/d(plane value)
-            const float4 up_pl = f4_scale(dfeat, kept[(2 * k) * TVM_KEEP_STRIDE]);          // d/d(line value)
-            float4* gpb = G4 + (t.pbase + (unsigned)(f.dplane_off[k] >> 2) + (unsigned)sub);
-            float4* gpb1 = gpb + t.prow;
-            float4* glb = G4 + (t.lbase + (unsigned)(f.dline_off[k] >> 2) + (unsigned)sub);
-            TVM_RED4(gpb, f4_scale(t.w00, up_ln));
-            TVM_RED4(gpb + C4, f4_scale(t.w01, up_ln));
-            TVM_RED4(gpb1, f4_scale(t.w10, up_ln));
-            TVM_RED4(gpb1 + C4, f4_scale(t.w11, up_ln));
-            TVM_RED4(glb, f4_scale(t.lw0, up_pl));
-            TVM_RED4(glb + C4, f4_scale(t.lw1, up_pl));
-        }
-    }
-}
-
 // appearance, compact-code form: the upstream slices are re-read from the ray's d_ray_feat row (L1-resident, one
 // broadcast wavefront per slice) instead of living in 9 float4 registers, and the channel-group loop is not unrolled —
 // a third of the instructions of app_bwd for the same arithmetic.  gRow = d_ray_feat + r * ta (16-byte aligned).

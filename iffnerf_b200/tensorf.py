@@ -137,9 +137,6 @@ class TensorVMSplit(FieldOpsMixin, torch.nn.Module):
     # eval renders without per-sample outputs: two-kernel march (a 64-register sigma-march that emits per-ray appearance
     # sample lists + an appearance-gather kernel with a register texel cache) instead of the fused one-kernel march
     split_app = True
-    # factor-gradient backward without pose gradients: three kernels (sigma-march re-emitting the appearance lists,
-    # appearance gather + scatter per listed sample, sigma re-march + density scatter) instead of one fused kernel
-    bwd_split = False
 
     def __init__(self, aabb, gridSize, device, density_n_comp=8, appearance_n_comp=24, app_dim=27,
                  shadingMode="MLP_PE", alphaMask=None, near_far=[2.0, 6.0], density_shift=-10,

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 12
+#define TVM_ABI_VERSION 11
 
 /* argument errors (negative so they cannot collide with cudaError_t) */
 #define TVM_E_NULL        (-1)   /* required pointer is NULL                      */
@@ -53,10 +53,6 @@ extern "C" {
 #define TVM_F_BWD_RUNS     (1u << 10) /* tvm_march_bwd, training scatter: quads walk runs of the block's samples and add equal
                                          texel addresses in registers before one red.v4 (-60 % L2 reduction traffic, +71 %
                                          instructions; slower at the measured sizes, opt-in) */
-#define TVM_F_BWD_SPLIT    (1u << 11) /* tvm_march_bwd, training scatter without pose gradients: three stages at higher occupancy —
-                                         sigma-march (re-emits the appearance lists into ws), appearance gather + scatter
-                                         per listed sample, sigma re-march + density scatter; needs the workspace of
-                                         tvm_workspace_bytes(..., TVM_F_SPLIT_APP) */
 #define TVM_APP_CAP        128        /* entries per ray in the appearance lists; longer rays take the fused kernel */
 #define TVM_F_POINT_SAMPLES (1u << 3) /* sampler of sample_point_color (tensorBase.py:623-638): n_samples samples
                                          centred on the ray origin, z_i = stepSize*(i - n_samples/2)          */
@@ -195,12 +191,11 @@ int tvm_render_fwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays
  * (any NULL = zero) it re-marches the rays and scatters into g_factors (packed layout, pre-zeroed or
  * accumulating) and, when g_rays != NULL, writes d(rays) [n][6] (pose mode).  With TVM_F_EARLY_TERM (and
  * d_alpha == NULL) the re-march stops at T < early_term_eps like the forward it pairs with.  ws is the forward workspace
- * (with TVM_F_BWD_SPLIT its appearance-list section is used as scratch; ray_feat / acc keep the forward's values)
  * (tvm_render_fwd with the same rays / n_samples / jitter; replaces autograd through grid_sampler_2d_backward,
  * cumprod, softplus ... driven by train.py:338 and inerf/estimate_pose_inerf.py:178). */
 int tvm_march_bwd(const tvm_field_desc* desc, const float* rays, int64_t n_rays, int ray_stride, int n_samples,
                   const float* jitter, uint32_t flags, const float* d_ray_feat, const float* d_acc,
-                  const float* d_alpha, float* g_factors, float* g_rays, void* ws, size_t ws_bytes,
+                  const float* d_alpha, float* g_factors, float* g_rays, const void* ws, size_t ws_bytes,
                   void* stream);
 
 /* Shade stage alone (basis_mat + MLPRender_Fea + background blend + depth tail, tensorBase.py:886-908),

@@ -25,7 +25,7 @@ def run(n, S, scatter, pose, tag, flags=0):
         return
     rays = allrays[torch.randint(0, allrays.shape[0], (n,), generator=g)].to(dev)
     need = C.c_size_t(0)
-    lib.tvm_workspace_bytes(C.byref(d), n, _lib.F_SPLIT_APP, C.byref(need))
+    lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need))
     ws = torch.empty((need.value,), dtype=torch.uint8, device=dev)
     _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays), n, rays.shape[1], S, None, _lib.ptr(bg), _lib.F_NO_SHADE,
                                   None, None, None, None, None, None, None, None, None, _lib.ptr(ws), ws.numel(), st), "fwd")
@@ -51,6 +51,4 @@ run(65536, 1036, False, True, "pose_65536")
 run(65536, 1039, True, False, "train_65536")
 run(4096, 1039, True, False, "train_4096_runs", _lib.F_BWD_RUNS)
 run(65536, 1039, True, False, "train_65536_runs", _lib.F_BWD_RUNS)
-run(4096, 1039, True, False, "train_4096_split", _lib.F_BWD_SPLIT)
-run(65536, 1039, True, False, "train_65536_split", _lib.F_BWD_SPLIT)
 print(json.dumps(out))

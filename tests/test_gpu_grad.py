@@ -249,38 +249,3 @@ def test_run_aggregated_scatter_equals_per_sample_scatter(lego, dev):
         assert scale > 0, name
         assert float((a - b).abs().max()) <= 2e-5 * scale, (name, float((a - b).abs().max()), scale)
         assert int((a != 0).sum()) == int((b != 0).sum()), name          # the same texels are touched
-
-
-@pytest.mark.parametrize("alpha_loss", [True, False], ids=["alpha_loss", "rgb_only"])
-def test_split_backward_equals_fused_backward(lego, dev, alpha_loss):
-    """TVM_F_BWD_SPLIT (sigma-march re-emitting the appearance lists -> app_bwd_kernel -> sigma re-march with c_i from
-    the lists -> overflow pass) against the one-kernel backward: every factor gradient equal up to fp32 summation
-    order, the same texels touched.  S = 1039 without early termination gives rays with more than TVM_APP_CAP
-    appearance samples only rarely, so a second field scale forces the overflow pass too (rgb_only case)."""
-    fld, rays, m = lego
-    sub, _ = fx.subsample(rays, 2048, seed=6)
-    torch.manual_seed(10)
-    jit = torch.rand(2048, device=dev)
-    target = torch.rand(2048, 3, device=dev)
-    grads, counts = {}, None
-    m.train()
-    for split in (False, True):
-        m.bwd_split = split
-        try:
-            m.zero_grad()
-            rgb, _, _, alpha, _, _ = m(sub.to(dev), bg_color=torch.ones(3, device=dev), is_train=True, N_samples=1039,
-                                       jitter=jit)
-            loss = torch.mean((rgb - target) ** 2)
-            if alpha_loss:
-                loss = loss + 0.1 * torch.mean(torch.exp(torch.abs(alpha)))
-            loss.backward()
-            torch.cuda.synchronize()
-        finally:
-            m.bwd_split = False
-        grads[split] = [p.grad.detach().clone() for p in _module_params(m)]
-    m.eval()
-    for name, a, b in zip(GRAD_NAMES, grads[True], grads[False]):
-        scale = float(b.abs().max())
-        assert scale > 0, name
-        assert float((a - b).abs().max()) <= 2e-5 * scale, (name, float((a - b).abs().max()), scale)
-        assert int((a != 0).sum()) == int((b != 0).sum()), name
