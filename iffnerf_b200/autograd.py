@@ -64,6 +64,14 @@ def _mlp_params(model):
     return [mods[0].weight, mods[0].bias, mods[1].weight, mods[1].bias, mods[2].weight, mods[2].bias]
 
 
+def _split_flags(model, want_samples):
+    """Differentiable forward without per-sample outputs (the pose loop): the two-kernel march of the eval path.  The
+    backward kernels read every ray's ray_feat row, so rays without appearance samples get their zero rows."""
+    if model.split_app and not want_samples:
+        return _lib.F_SPLIT_APP | _lib.F_ZERO_UNLIT
+    return 0
+
+
 class _Render(torch.autograd.Function):
     """inputs: model, rays, S, jitter, bg, flags, 12 factors, basis, w1, b1, w2, b2, w3, b3.
     flags & F_EARLY_TERM: the caller does not want the per-sample outputs (alpha / z_vals / dists come back as None),
@@ -78,18 +86,20 @@ class _Render(torch.autograd.Function):
         n = rays_c.shape[0]
         d, keep = model.field_desc()
         lib = _lib.load()
+        want_samples = not (flags & _lib.F_EARLY_TERM)
+        fwd_flags = flags | _split_flags(model, want_samples)
         need = C.c_size_t(0)
-        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need)), "tvm_workspace_bytes")
+        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, fwd_flags & _lib.F_SPLIT_APP, C.byref(need)),
+                   "tvm_workspace_bytes")
         ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
         rgb = torch.empty((n, 3), device=dev)
         depth = torch.empty((n,), device=dev)
         acc = torch.empty((n,), device=dev)
-        want_samples = not (flags & _lib.F_EARLY_TERM)
         alpha, z, dists = (torch.empty((n, S), device=dev) for _ in range(3)) if want_samples else (None, None, None)
         jit = None if jitter is None else jitter.detach().to(dev).float().reshape(-1).contiguous()
         bg_c = _c(bg)
         _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], S, _lib.ptr(jit),
-                                      _lib.ptr(bg_c), flags, _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc),
+                                      _lib.ptr(bg_c), fwd_flags, _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(acc),
                                       _lib.ptr(alpha), _lib.ptr(z), _lib.ptr(dists), None, None, None,
                                       _lib.ptr(ws), ws.numel(), _stream(dev)), "tvm_render_fwd")
         ctx.model, ctx.S, ctx.jit, ctx.rays_c, ctx.ws, ctx.bg = model, S, jit, rays_c, ws, bg_c
@@ -210,15 +220,17 @@ class _March(torch.autograd.Function):
         n = rays_c.shape[0]
         d, keep = model.field_desc()
         lib = _lib.load()
-        need = C.c_size_t(0)
-        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, 0, C.byref(need)), "tvm_workspace_bytes")
-        ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
         want_samples = not (flags & _lib.F_EARLY_TERM)     # without per-sample outputs both directions terminate early
+        fwd_flags = flags | _split_flags(model, want_samples)
+        need = C.c_size_t(0)
+        _lib.check(lib.tvm_workspace_bytes(C.byref(d), n, fwd_flags & _lib.F_SPLIT_APP, C.byref(need)),
+                   "tvm_workspace_bytes")
+        ws = torch.empty((max(need.value, 1),), dtype=torch.uint8, device=dev)
         alpha, z, dists = (torch.empty((n, S), device=dev) for _ in range(3)) if want_samples else (None, None, None)
         jit = None if jitter is None else jitter.detach().to(dev).float().reshape(-1).contiguous()
         bg = model._bg(None, False, dev)
         _lib.check(lib.tvm_render_fwd(C.byref(d), _lib.ptr(rays_c), n, rays_c.shape[1], S, _lib.ptr(jit),
-                                      _lib.ptr(bg), _lib.F_NO_SHADE | flags, None, None, None, _lib.ptr(alpha), _lib.ptr(z),
+                                      _lib.ptr(bg), _lib.F_NO_SHADE | fwd_flags, None, None, None, _lib.ptr(alpha), _lib.ptr(z),
                                       _lib.ptr(dists), None, None, None, _lib.ptr(ws), ws.numel(), _stream(dev)),
                    "tvm_render_fwd")
         v = model.workspace_views(d, ws, n)

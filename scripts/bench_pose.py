@@ -14,7 +14,13 @@ for p in m.parameters():
 m.eval_sample_outputs = "--samples" in sys.argv
 g = torch.Generator().manual_seed(0)
 allrays = syn.config2_rays()
-prays = allrays[torch.randint(0, allrays.shape[0], (64 * 1024,), generator=g)].to(dev)
+pick = torch.randint(0, allrays.shape[0], (64 * 1024,), generator=g)
+if "--sorted" in sys.argv:          # locality probe: the same rays in pixel order
+    pick = pick.sort().values
+if "--tiled" in sys.argv:           # ... in 8x4-pixel tile order
+    y, x = pick // 800, pick % 800
+    pick = pick[torch.argsort(((y // 4) * 100 + x // 8) * 32 + (y % 4) * 8 + x % 8)]
+prays = allrays[pick].to(dev)
 target = torch.rand(64 * 1024, 3, device=dev)
 bg = torch.rand(3, device=dev)
 def step():
@@ -27,4 +33,4 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record()
 for _ in range(5): step()
 e1.record(); torch.cuda.synchronize()
-print(json.dumps({"sample_outputs": m.eval_sample_outputs, "pose_step_ms": round(e0.elapsed_time(e1) / 5, 3)}))
+print(json.dumps({"order": "sorted" if "--sorted" in sys.argv else ("tiled" if "--tiled" in sys.argv else "random"), "sample_outputs": m.eval_sample_outputs, "pose_step_ms": round(e0.elapsed_time(e1) / 5, 3)}))
