@@ -12,7 +12,7 @@
 
 namespace {
 
-constexpr int TP = 32;   // pixels per tile
+constexpr int TP = 128;  // pixels per tile
 
 // The 12 factor tensors are converted by ONE launch: blockIdx.y selects the tensor, blockIdx.x the pixel tile.
 // P pixels in rows of W; the channel-last side pads each row to `pitch` texels (tvm_plane_pitch; lines: W = pitch = P)
@@ -35,7 +35,8 @@ __device__ __forceinline__ long long padded_pixel(const TileOrigin& t, long long
 }
 struct TransposeJobs { TransposeJob j[12]; int accumulate; float scale; int rezero; };
 
-// src [C][P] -> dst [P][C]
+// src [C][P] -> dst [P][C].  The channel-last side moves as float4s (C is a multiple of 4 and every texel starts on a
+// 16-byte boundary), the [C][P] side as 128-pixel rows: 512 contiguous bytes per channel.
 __global__ void __launch_bounds__(256) cp_to_pc_kernel(const __grid_constant__ TransposeJobs jobs) {
     __shared__ float tile[TVM_MAX_APP_C][TP + 1];
     const float* __restrict__ src = jobs.j[blockIdx.y].src;
@@ -44,22 +45,22 @@ __global__ void __launch_bounds__(256) cp_to_pc_kernel(const __grid_constant__ T
     const long long P = jobs.j[blockIdx.y].P;
     const long long p0 = (long long)blockIdx.x * TP;
     if (p0 >= P) return;
-    const int px = threadIdx.x & 31, cy = threadIdx.x >> 5;
-    for (int c = cy; c < C; c += 8) {
-        const long long p = p0 + px;
-        tile[c][px] = (p < P) ? __ldg(src + (long long)c * P + p) : 0.f;
+    const int npix = (int)min((long long)TP, P - p0);
+    for (int i = threadIdx.x; i < C * TP; i += 256) {
+        const int c = i / TP, px = i - c * TP;
+        if (px < npix) tile[c][px] = __ldg(src + (long long)c * P + p0 + px);
     }
     __syncthreads();
-    const long long lim = min((long long)TP, P - p0) * C;
-    const int W = jobs.j[blockIdx.y].W, pitch = jobs.j[blockIdx.y].pitch;
+    const int W = jobs.j[blockIdx.y].W, pitch = jobs.j[blockIdx.y].pitch, C4 = C >> 2;
     const TileOrigin org = tile_origin(p0, W);
-    for (int i = threadIdx.x; i < lim; i += 256) {
-        const int p = i / C, c = i - p * C;
-        dst[padded_pixel(org, p0, p, W, pitch) * C + c] = tile[c][p];
+    for (int i = threadIdx.x; i < npix * C4; i += 256) {
+        const int px = i / C4, c = (i - px * C4) * 4;
+        reinterpret_cast<float4*>(dst + padded_pixel(org, p0, px, W, pitch) * C)[c >> 2] =
+            make_float4(tile[c][px], tile[c + 1][px], tile[c + 2][px], tile[c + 3][px]);
     }
 }
 
-// src [P][C] -> dst [C][P]  (dst = src^T, or dst += src^T)
+// src [P][C] -> dst [C][P]  (dst = scale * src^T, or dst += ...; optionally leaves src zeroed)
 __global__ void __launch_bounds__(256) pc_to_cp_kernel(const __grid_constant__ TransposeJobs jobs) {
     __shared__ float tile[TVM_MAX_APP_C][TP + 1];
     const float* __restrict__ src = jobs.j[blockIdx.y].src;
@@ -69,28 +70,30 @@ __global__ void __launch_bounds__(256) pc_to_cp_kernel(const __grid_constant__ T
     const long long P = jobs.j[blockIdx.y].P;
     const long long p0 = (long long)blockIdx.x * TP;
     if (p0 >= P) return;
-    const long long lim = min((long long)TP, P - p0) * C;
-    const int W = jobs.j[blockIdx.y].W, pitch = jobs.j[blockIdx.y].pitch;
+    const int npix = (int)min((long long)TP, P - p0);
+    const int W = jobs.j[blockIdx.y].W, pitch = jobs.j[blockIdx.y].pitch, C4 = C >> 2;
     const TileOrigin org = tile_origin(p0, W);
-    for (int i = threadIdx.x; i < lim; i += 256) {
-        const int p = i / C, c = i - p * C;
-        tile[c][p] = jobs.scale * __ldg(src + padded_pixel(org, p0, p, W, pitch) * C + c);
+    for (int i = threadIdx.x; i < npix * C4; i += 256) {
+        const int px = i / C4, c = (i - px * C4) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + padded_pixel(org, p0, px, W, pitch) * C) + (c >> 2));
+        tile[c][px] = jobs.scale * v.x; tile[c + 1][px] = jobs.scale * v.y;
+        tile[c + 2][px] = jobs.scale * v.z; tile[c + 3][px] = jobs.scale * v.w;
     }
     __syncthreads();
     if (jobs.rezero) {            // leave the scatter buffer zeroed for the next step (stores only: a separate loop keeps
         float* z = const_cast<float*>(src);     // the loads above independent of them, several in flight per thread)
-        for (int i = threadIdx.x; i < lim; i += 256) {
-            const int p = i / C, c = i - p * C;
-            z[padded_pixel(org, p0, p, W, pitch) * C + c] = 0.f;
+        for (int i = threadIdx.x; i < npix * C4; i += 256) {
+            const int px = i / C4, c4 = i - px * C4;
+            reinterpret_cast<float4*>(z + padded_pixel(org, p0, px, W, pitch) * C)[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    const int px = threadIdx.x & 31, cy = threadIdx.x >> 5;
-    const long long p = p0 + px;
-    if (p < P)
-        for (int c = cy; c < C; c += 8) {
-            float* d = dst + (long long)c * P + p;
+    for (int i = threadIdx.x; i < C * TP; i += 256) {
+        const int c = i / TP, px = i - c * TP;
+        if (px < npix) {
+            float* d = dst + (long long)c * P + p0 + px;
             *d = accumulate ? (*d + tile[c][px]) : tile[c][px];
         }
+    }
 }
 
 __global__ void occupancy_cells_kernel(const float* __restrict__ vol, int dx, int dy, int dz,
