@@ -611,10 +611,8 @@ def run_ours(args, rank, world, local_rank):
         march(_lib.F_GATHER_ONLY)
 
     def step_e2e():
-        rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(rays_host, model, chunk=4096, N_samples=-1, white_bg=True,
-                                                          ndc_ray=False, device=dev)
-        rgb_host.copy_(rgb, non_blocking=True)
-        depth_host.copy_(depth, non_blocking=True)
+        I.OctreeRender_trilinear_fast(rays_host, model, chunk=4096, N_samples=-1, white_bg=True, ndc_ray=False,
+                                      device=dev, out_host=(rgb_host, depth_host))
         torch.cuda.current_stream(dev).synchronize()
 
     with ClockSampler(local_rank) as clk:

@@ -13,8 +13,13 @@ import torch
 
 
 def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray=False, bg_color=None, white_bg=None,
-                                is_train=False, device="cuda"):
-    """Returns (rgb [N,3], None, depth [N], None, None) on `device`, like the reference."""
+                                is_train=False, device="cuda", out_host=None):
+    """Returns (rgb [N,3], None, depth [N], None, None) on `device`, like the reference.
+
+    out_host (extension, eval path only): `(rgb_host [N,3], depth_host [N])` pinned CPU tensors that also receive the
+    results — the download of each ray slice runs on its own stream behind the kernels of the next slice instead of
+    after the whole call (what `evaluation()`'s `.cpu()` does in the reference, renderer.py:77-80).  The copies are
+    ordered before anything the caller enqueues on the current stream afterwards."""
     if ndc_ray:
         raise NotImplementedError("ndc_ray sampling is outside the B200 render path")
     dev = torch.device(device)
@@ -26,6 +31,10 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
         rays = rays.to(dev)                      # outputs live on `device`, like the reference's per-chunk .to(device)
     n = rays.shape[0]
     grad_path = is_train or (torch.is_grad_enabled() and rays.requires_grad)
+    if out_host is not None and (grad_path or len(out_host) != 2 or any(
+            t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous() for t in out_host)
+            or out_host[0].shape != (n, 3) or out_host[1].shape != (n,)):
+        raise ValueError("out_host must be (rgb [N,3], depth [N]) contiguous fp32 CPU tensors on the no-grad path")
     if grad_path:
         rgbs, depths = [], []
         for a in range(0, n, chunk):
@@ -61,9 +70,12 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
                 cur = cur.to(dev, non_blocking=True)
             tensorf.render_eval(cur, N_samples=N_samples, white_bg=bool(white_bg), bg_color=bg_color,
                                 out_rgb=rgb[a:a + step], out_depth=depth[a:a + step])
+        if out_host is not None:
+            out_host[0].copy_(rgb, non_blocking=True)
+            out_host[1].copy_(depth, non_blocking=True)
         return rgb, None, depth, None, None
 
-    copy_stream, compute = _side_streams(dev)
+    copy_stream, compute, down_stream = _side_streams(dev)
     tensorf.field_desc()                       # (re)pack parameter shadows on the caller's stream before forking
     tensorf._bg(bg_color, bool(white_bg), dev)  # ... and create the cached background constant there too
     if not tensorf.native_shade and tensorf.ref_kernel:
@@ -88,8 +100,19 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
             ev = torch.cuda.Event()
             ev.record(cs)
         done.append(ev)
+        if out_host is not None:            # this slice's download, behind the next slice's kernels
+            down_stream.wait_event(ev)
+            with torch.cuda.stream(down_stream):
+                out_host[0][a:b].copy_(rgb[a:b], non_blocking=True)
+                out_host[1][a:b].copy_(depth[a:b], non_blocking=True)
     for ev in done[-len(compute):]:
         main.wait_event(ev)
+    if out_host is not None:
+        rgb.record_stream(down_stream)
+        depth.record_stream(down_stream)
+        landed = torch.cuda.Event()
+        landed.record(down_stream)
+        main.wait_event(landed)
     return rgb, None, depth, None, None
 
 
@@ -97,8 +120,9 @@ _streams = {}
 
 
 def _side_streams(dev):
-    """(copy stream, [two compute streams]) of a device, created once."""
+    """(upload stream, [two compute streams], download stream) of a device, created once."""
     key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
     if key not in _streams:
-        _streams[key] = (torch.cuda.Stream(device=dev), [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)])
+        _streams[key] = (torch.cuda.Stream(device=dev), [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)],
+                         torch.cuda.Stream(device=dev))
     return _streams[key]

@@ -29,11 +29,15 @@ rd = torch.empty_like(rays, device=dev); rgb_d = torch.empty((n, 3), device=dev)
 print(json.dumps({"h2d_ms": timeit(lambda: rd.copy_(rays, non_blocking=True)),
                   "d2h_ms": timeit(lambda: (rgb_h.copy_(rgb_d, non_blocking=True), depth_h.copy_(dep_d, non_blocking=True))),
                   "device_ms": timeit(lambda: m.render_eval(rd, white_bg=True))}), flush=True)
-for slices, frac in ((1, 1.0), (2, 1.0), (2, 0.6), (2, 0.4), (2, 0.25), (2, 0.15), (3, 0.4), (4, 0.4)):
+for slices, frac in ((1, 1.0), (2, 1.0), (2, 0.5), (2, 0.25), (3, 0.5), (3, 0.3), (4, 0.5), (4, 0.3), (5, 0.5), (6, 0.5)):
     m.host_ray_slices = slices
     m.host_first_slice_frac = frac
     def step():
         rgb, _, depth, _, _ = I.OctreeRender_trilinear_fast(rays, m, white_bg=True, device=dev)
         rgb_h.copy_(rgb, non_blocking=True); depth_h.copy_(depth, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    print(json.dumps({"slices": slices, "first_frac": frac, "e2e_ms": timeit(step)}), flush=True)
+    def step_piped():           # downloads of a slice behind the kernels of the next (out_host)
+        I.OctreeRender_trilinear_fast(rays, m, white_bg=True, device=dev, out_host=(rgb_h, depth_h))
+        torch.cuda.current_stream().synchronize()
+    print(json.dumps({"slices": slices, "first_frac": frac, "e2e_ms": timeit(step), "e2e_out_host_ms": timeit(step_piped)}),
+          flush=True)

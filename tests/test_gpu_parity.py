@@ -205,6 +205,20 @@ def test_octree_render_cpu_rays_and_chunking(dev):
     assert rgb.is_cuda and rgb.shape == (10000, 3) and depth.shape == (10000,)
     assert np.abs(rgb.cpu().numpy() - g["rgb_map"]).max() <= TOL
     assert np.abs(depth.cpu().numpy() - g["depth_map"]).max() <= TOL
+    # out_host: pinned result buffers filled slice by slice behind the kernels of the next slice (and on the
+    # single-launch path), identical to the returned device tensors
+    rgb_h, depth_h = torch.full((10000, 3), -1.0).pin_memory(), torch.full((10000,), -1.0).pin_memory()
+    for cap in (3000, type(m).max_launch_rays):
+        m.max_launch_rays = cap
+        try:
+            rgb2, _, depth2, _, _ = I.OctreeRender_trilinear_fast(rays, m, chunk=4096, white_bg=True, device=dev,
+                                                              out_host=(rgb_h.fill_(-1.0), depth_h.fill_(-1.0)))
+            torch.cuda.current_stream(dev).synchronize()
+        finally:
+            m.max_launch_rays = type(m).max_launch_rays
+        assert torch.equal(rgb_h, rgb2.cpu()) and torch.equal(depth_h, depth2.cpu()) and torch.equal(rgb2, rgb)
+    with pytest.raises(ValueError):
+        I.OctreeRender_trilinear_fast(rays, m, white_bg=True, device=dev, out_host=(rgb_h[:5], depth_h))
 
 
 def test_edge_cases(dev):
